@@ -1,0 +1,268 @@
+/* meepo.h — C ABI of the B200-native dynamic embedding table ("meepo-b200").
+ *
+ * Provenance. The upstream repository MoFHeka/MeepoEmbedding ships no code: its
+ * whole product content is /root/reference/README.md:1-2 ("A distributed
+ * high-performance dynamic lookuptable-style Embedding ... Supports GPU, CPU,
+ * remote distributed KV (such as Redis), SSD, and other backends."). There is
+ * therefore no reference FFI to bind to; every entry point below is DERIVED
+ * from that sentence (R1 "dynamic lookuptable-style" -> find_or_insert / evict,
+ * R2 "distributed" -> the sharded verbs, R4 "recommendation ... CTR" ->
+ * apply_gradients with sparse optimizers) and from BASELINE.json:north_star.
+ * The derivation table lives in BASELINE.md section 5; this header is the
+ * normative statement of the semantics.
+ *
+ * Two shared libraries export exactly these symbols:
+ *   meepoembedding_b200/libmeepo.so   CUDA sm_100a product; data pointers are
+ *                                     DEVICE pointers unless the verb ends in
+ *                                     _host.
+ *   oracle/libmeepo_oracle.so         authored C++/OpenMP CPU restatement (test
+ *                                     infrastructure only); all pointers are
+ *                                     HOST pointers, `stream` is ignored.
+ *
+ * ---------------------------------------------------------------------------
+ * Normative semantics (both libraries implement these bit for bit)
+ * ---------------------------------------------------------------------------
+ * Keys      uint64. 0xFFFFFFFFFFFFFFFF (EMPTY) and 0xFFFFFFFFFFFFFFFE (RESERVED)
+ *           are not storable: they get per-key status MEEPO_KEY_INVALID and an
+ *           all-zero row.
+ * Rows      `dim` elements of fp32 or bf16, row-major, contiguous; row bytes
+ *           must be a multiple of 16 (dim % 4 == 0 for fp32, dim % 8 == 0 for
+ *           bf16).
+ * Init      A row created by find_or_insert is a pure function of
+ *           (key, init_seed, column) — never of slot or arrival order:
+ *             p   = column >> 1
+ *             x   = mix64(key + (init_seed ^ ((p + 1) * 0x9E3779B97F4A7C15)))
+ *             u32 = (column & 1) ? (x >> 32) : (x & 0xFFFFFFFF)
+ *             v   = ((float)(u32 >> 8) * 2^-23 - 1.0f) * init_scale   (fp32 ops)
+ *           mix64 is the splitmix64 finaliser:
+ *             z ^= z >> 30; z *= 0xBF58476D1CE4E5B9; z ^= z >> 27;
+ *             z *= 0x94D049BB133111EB; z ^= z >> 31.
+ *           bf16 tables store round-to-nearest-even(v).
+ *           Optimizer state of a new row: Adagrad accumulator = init_accum,
+ *           Adam m = v = 0 and step = 0.
+ * Status    find_or_insert reports per key: MEEPO_KEY_FOUND if the key was in
+ *           the table when the call started; MEEPO_KEY_INSERTED if it was not
+ *           (EVERY duplicate of such a key inside the batch reports INSERTED and
+ *           receives the same freshly initialised row; one slot is used);
+ *           MEEPO_KEY_FULL if no free slot exists anywhere (row = zeros);
+ *           MEEPO_KEY_INVALID for the two reserved keys. lookup reports
+ *           MEEPO_KEY_FOUND / MEEPO_KEY_MISS (row = zeros) / MEEPO_KEY_INVALID.
+ *           The physical slot index is NOT part of the contract.
+ * Update    apply_gradients sums the gradients of duplicate keys, then performs
+ *           exactly one optimizer step per unique key. Keys that are not in the
+ *           table (or invalid) are skipped. The sum is taken in fp32 in this
+ *           fixed order (g_0..g_{n-1} = the key's gradients by increasing batch
+ *           index; L = MEEPO_REDUCE_LEAF = 256):
+ *             leaf_c = ((g_{cL} + g_{cL+1}) + g_{cL+2}) + ...   (up to L terms)
+ *             G      = ((leaf_0 + leaf_1) + leaf_2) + ...
+ *           Optimizers, element-wise, fp32 arithmetic, every operation rounded
+ *           individually (no fused multiply-add), w = row, g = G:
+ *             SGD      w = w - lr*g
+ *             ADAGRAD  a = a + g*g ;  w = w - (lr*g) / (sqrt(a) + eps)
+ *             ADAM     t = t+1 (per row); m = beta1*m + (1-beta1)*g ;
+ *                      v = beta2*v + (1-beta2)*(g*g) ;
+ *                      w = w - (lr * sqrt(1-beta2^t)/(1-beta1^t)) * m
+ *                              / (sqrt(v) + eps)
+ *                      (the scalar step size is computed in double and rounded
+ *                      to float once per row)
+ *           bf16 rows: w is widened to fp32, updated, stored RNE. Gradients have
+ *           the table's dtype and are widened to fp32 before summation.
+ * Evict     Removes the lowest-score keys until size <= floor(target_load *
+ *           capacity). Two uint32 scores are kept per key when
+ *           MEEPO_FLAG_TRACK_SCORES is set: freq = number of occurrences of the
+ *           key in find_or_insert / lookup batches while resident (the inserting
+ *           batch included, wrapping at 2^32), and last_epoch = the table's batch
+ *           epoch at the last such occurrence (the epoch increments once per
+ *           find_or_insert / lookup call, first call = 1). LFU orders by freq,
+ *           LRU by last_epoch; ties are broken by key, smaller key evicted
+ *           first. apply_gradients does not touch the scores. Evicted
+ *           (key,row,state,scores,step) tuples go to the pinned host spill tier
+ *           when host_spill_bytes > 0: it holds floor(host_spill_bytes /
+ *           (24 + row_bytes + state_bytes)) tuples, victims are appended in
+ *           eviction order (ascending (score,key)), the oldest tuple is dropped
+ *           when it is full, and a newer copy of a key replaces an older one.
+ *           meepo_spill_readmit restores tuples; find_or_insert of a key that
+ *           sits in the spill tier re-initialises it unless the caller re-admits
+ *           first.
+ * Sharding  owner(key, G) = umulhi64(mix64(key ^ 0xD6E8FEB86659FD93), G).
+ */
+#ifndef MEEPO_H_
+#define MEEPO_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define MEEPO_API __attribute__((visibility("default")))
+#else
+#define MEEPO_API
+#endif
+
+#define MEEPO_ABI_VERSION 1u
+#define MEEPO_KEY_EMPTY 0xFFFFFFFFFFFFFFFFull
+#define MEEPO_KEY_RESERVED 0xFFFFFFFFFFFFFFFEull
+#define MEEPO_REDUCE_LEAF 256u
+#define MEEPO_OWNER_SALT 0xD6E8FEB86659FD93ull
+
+typedef struct meepo_table meepo_table; /* opaque */
+
+typedef enum {
+  MEEPO_OK = 0,
+  MEEPO_EINVAL = 1,
+  MEEPO_ENOMEM = 2,
+  MEEPO_ECUDA = 3,
+  MEEPO_ENCCL = 4,
+  MEEPO_EIO = 5
+} meepo_status;
+
+typedef enum { MEEPO_F32 = 0, MEEPO_BF16 = 1 } meepo_dtype;
+typedef enum { MEEPO_SGD = 0, MEEPO_ADAGRAD = 1, MEEPO_ADAM = 2 } meepo_opt;
+typedef enum { MEEPO_LRU = 0, MEEPO_LFU = 1 } meepo_policy;
+
+/* per-key status bytes */
+enum {
+  MEEPO_KEY_MISS = 0,
+  MEEPO_KEY_FOUND = 1,
+  MEEPO_KEY_INSERTED = 2,
+  MEEPO_KEY_FULL = 3,
+  MEEPO_KEY_INVALID = 4
+};
+
+enum { MEEPO_FLAG_TRACK_SCORES = 1u };
+
+typedef struct {
+  uint32_t dim;          /* elements per row */
+  uint32_t flags;        /* MEEPO_FLAG_* */
+  uint64_t capacity;     /* number of key slots (rounded up to a multiple of 32) */
+  int32_t dtype;         /* meepo_dtype */
+  int32_t opt;           /* meepo_opt */
+  float lr, eps, beta1, beta2, init_accum;
+  float init_scale;
+  uint64_t init_seed;
+  int32_t device;            /* CUDA ordinal (ignored by the oracle) */
+  int32_t reserved0;
+  uint64_t host_spill_bytes; /* size of the pinned host spill tier, 0 = none */
+} meepo_config;
+
+typedef struct {
+  uint64_t capacity;     /* slots */
+  uint64_t size;         /* live keys */
+  uint64_t inserts;      /* keys inserted since create */
+  uint64_t hits;         /* key occurrences that were found (foi + lookup) */
+  uint64_t misses;       /* lookup occurrences not found */
+  uint64_t full;         /* occurrences rejected because the table was full */
+  uint64_t evictions;    /* keys removed by meepo_evict */
+  uint64_t updates;      /* unique-key optimizer steps applied */
+  uint64_t grad_dropped; /* gradient occurrences whose key was absent/invalid */
+  uint64_t spill_keys;   /* tuples currently held in the host spill tier */
+  uint64_t spill_bytes;  /* bytes currently held in the host spill tier */
+  uint64_t epoch;        /* batch epoch */
+  uint64_t overflow_buckets; /* buckets whose overflow flag is set */
+  uint64_t row_bytes, state_bytes; /* per slot */
+} meepo_stats_t;
+
+/* --- life cycle (synchronous) ------------------------------------------- */
+MEEPO_API uint32_t meepo_abi_version(void);
+/* "cuda-sm_100a" for the product, "oracle-cpu" for the authored CPU library. */
+MEEPO_API const char* meepo_backend(void);
+MEEPO_API meepo_status meepo_create(const meepo_config* cfg, meepo_table** out);
+MEEPO_API meepo_status meepo_destroy(meepo_table* t);
+MEEPO_API meepo_status meepo_stats(meepo_table* t, meepo_stats_t* out);
+/* thread-local, never NULL */
+MEEPO_API const char* meepo_last_error(void);
+
+/* --- hot path (stream-ordered, asynchronous; device pointers) ------------ */
+/* rows_out: n*dim elements; status_out: n bytes (may be NULL). */
+MEEPO_API meepo_status meepo_find_or_insert(meepo_table* t, const uint64_t* keys, uint64_t n,
+                                            void* rows_out, uint8_t* status_out, void* stream);
+MEEPO_API meepo_status meepo_lookup(meepo_table* t, const uint64_t* keys, uint64_t n,
+                                    void* rows_out, uint8_t* found_out, void* stream);
+/* grads: n*dim elements of the table dtype. */
+MEEPO_API meepo_status meepo_apply_gradients(meepo_table* t, const uint64_t* keys,
+                                             const void* grads, uint64_t n, void* stream);
+
+/* --- host-buffer front ends (pageable or pinned host pointers) ----------- *
+ * Same semantics; the library stages through its own pinned ring and
+ * overlaps H2D, kernels and D2H in chunks. They return after the results are
+ * in the caller's buffers. */
+MEEPO_API meepo_status meepo_find_or_insert_host(meepo_table* t, const uint64_t* keys, uint64_t n,
+                                                 void* rows_out, uint8_t* status_out);
+MEEPO_API meepo_status meepo_lookup_host(meepo_table* t, const uint64_t* keys, uint64_t n,
+                                         void* rows_out, uint8_t* found_out);
+MEEPO_API meepo_status meepo_apply_gradients_host(meepo_table* t, const uint64_t* keys,
+                                                  const void* grads, uint64_t n);
+
+/* --- capacity management -------------------------------------------------- */
+MEEPO_API meepo_status meepo_evict(meepo_table* t, int32_t policy, double target_load,
+                                   uint64_t* n_evicted, void* stream);
+/* Re-admit keys from the host spill tier (row, state and score restored).
+ * keys: HOST pointer. status_out (host, may be NULL): FOUND = already in table
+ * (spill copy dropped), INSERTED = restored, MISS = not in the spill tier,
+ * FULL / INVALID as above. */
+MEEPO_API meepo_status meepo_spill_readmit(meepo_table* t, const uint64_t* keys, uint64_t n,
+                                           uint8_t* status_out);
+
+/* --- bulk dump / load (synchronous) --------------------------------------- *
+ * meepo_export_buffers compacts the live tuples into caller buffers (device
+ * pointers for the CUDA library), sorted by key ascending. rows/state/scores/
+ * steps may each be NULL. score = (last_epoch << 32) | freq; steps = Adam's
+ * per-row step count (0 for the other optimizers). *n_out receives the number
+ * of live tuples; keys == NULL makes the call a pure size query; max_n is the
+ * size of the buffers in tuples (MEEPO_EINVAL if too small). */
+MEEPO_API meepo_status meepo_export_buffers(meepo_table* t, uint64_t* keys, void* rows, void* state,
+                                            uint64_t* scores, uint32_t* steps, uint64_t max_n,
+                                            uint64_t* n_out);
+/* meepo_import_buffers: bulk insert-or-overwrite of tuples with DISTINCT keys.
+ * state == NULL -> state initialised as for a new row; scores/steps == NULL ->
+ * 0. status_out (may be NULL): FOUND = overwritten, INSERTED, FULL, INVALID. */
+MEEPO_API meepo_status meepo_import_buffers(meepo_table* t, const uint64_t* keys, const void* rows,
+                                            const void* state, const uint64_t* scores,
+                                            const uint32_t* steps, uint64_t n, uint8_t* status_out);
+/* File format "MEEPOTB1": 64-byte header {magic[8], u32 version, dim, dtype,
+ * opt, u64 n, row_bytes, state_bytes, epoch} then keys[n], rows[n], state[n],
+ * scores[n], steps[n], tuples sorted by key. Both libraries write identical
+ * files for identical tables. */
+MEEPO_API meepo_status meepo_export(meepo_table* t, const char* path);
+MEEPO_API meepo_status meepo_import(meepo_table* t, const char* path);
+
+/* --- sharding helpers (one process per GPU; the exchange itself is the
+ *     caller's collective: torch.distributed / NCCL all-to-all, or the fused
+ *     peer-memory kernels below) ------------------------------------------- */
+/* owner(key, num_shards) on the host, for tests and callers. */
+MEEPO_API uint32_t meepo_owner(uint64_t key, uint32_t num_shards);
+/* Stable counting sort of a batch by owner(key, num_shards):
+ *   counts_out[num_shards]  keys per destination
+ *   perm_out[n]             perm_out[j] = batch index of the j-th key in
+ *                           destination-major order (may be NULL)
+ *   keys_sorted_out[n]      keys in that order (may be NULL)
+ * Device pointers, stream-ordered. */
+MEEPO_API meepo_status meepo_shard_partition(meepo_table* t, const uint64_t* keys, uint64_t n,
+                                             uint32_t num_shards, uint64_t* counts_out,
+                                             uint32_t* perm_out, uint64_t* keys_sorted_out,
+                                             void* stream);
+/* Sender-side pre-reduction before every exchange (NVLink is ~3x tighter than
+ * HBM without it): the distinct valid keys of the batch, each with the
+ * fixed-shape sum (meepo.h "Update") of its gradient rows rounded to the table
+ * dtype. grads/grads_out may both be NULL (keys only — the forward path).
+ * inverse_out (may be NULL): inverse_out[i] = position of keys[i] in
+ * unique_keys_out, 0xFFFFFFFF for invalid keys. The ORDER of the unique keys is
+ * unspecified; results are compared as a key -> row map. *n_unique_out is a
+ * device pointer in the CUDA library. */
+MEEPO_API meepo_status meepo_reduce_duplicates(meepo_table* t, const uint64_t* keys, const void* grads,
+                                               uint64_t n, uint64_t* unique_keys_out, void* grads_out,
+                                               uint32_t* inverse_out, uint64_t* n_unique_out,
+                                               void* stream);
+/* rows_out[i] = rows_in[index[i]] (16-byte vectorised gather of dense rows; the
+ * un-permute / duplicate-expand step after the row exchange). index ==
+ * 0xFFFFFFFF writes a zero row. */
+MEEPO_API meepo_status meepo_gather_rows(meepo_table* t, const void* rows_in, const uint32_t* index,
+                                         uint64_t n, void* rows_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MEEPO_H_ */

@@ -1,0 +1,182 @@
+"""Trivially-correct dict model of include/meepo.h, in numpy fp32 (one rounding per op).
+
+Used to pin the authored oracle (tests/test_oracle_model.py). Small cases only.
+"""
+import math
+
+import numpy as np
+
+from meepoembedding_b200 import _capi as capi
+from meepoembedding_b200 import keygen
+
+F = np.float32
+LEAF = capi.REDUCE_LEAF
+
+
+def mix64(z):
+    z &= 0xFFFFFFFFFFFFFFFF
+    z ^= z >> 30
+    z = (z * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    z ^= z >> 27
+    z = (z * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    z ^= z >> 31
+    return z
+
+
+def init_row(key, seed, dim, scale):
+    out = np.empty(dim, dtype=F)
+    for c in range(dim):
+        p = c >> 1
+        x = mix64((key + (seed ^ (((p + 1) * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF))) & 0xFFFFFFFFFFFFFFFF)
+        u = (x >> 32) if (c & 1) else (x & 0xFFFFFFFF)
+        a = F(u >> 8) * F(2.0**-23)
+        out[c] = (a - F(1.0)) * F(scale)
+    return out
+
+
+def owner(key, g):
+    return (mix64(key ^ 0xD6E8FEB86659FD93) * g) >> 64
+
+
+class Model:
+    def __init__(self, dim, capacity, dtype=capi.F32, opt=capi.ADAGRAD, lr=0.01, eps=1e-8, beta1=0.9,
+                 beta2=0.999, init_accum=0.1, init_scale=0.01, init_seed=0, track=False, spill_tuples=0):
+        self.dim, self.dtype, self.opt = dim, dtype, opt
+        self.capacity = (capacity + 31) // 32 * 32
+        self.lr, self.eps, self.b1, self.b2 = F(lr), F(eps), F(beta1), F(beta2)
+        self.init_accum, self.init_scale, self.seed = F(init_accum), init_scale, init_seed
+        self.track = track
+        self.rows = {}    # key -> fp32 array holding the stored (possibly bf16-rounded) values
+        self.state = {}   # key -> fp32 array (dim or 2*dim)
+        self.step = {}
+        self.freq = {}
+        self.last = {}
+        self.epoch = 0
+        self.spill = {}   # key -> tuple, insertion-ordered (python dicts keep order)
+        self.spill_tuples = spill_tuples
+
+    # storage rounding
+    def _store(self, v):
+        if self.dtype == capi.F32:
+            return v.astype(F)
+        return keygen.bf16_bits_to_f32(keygen.f32_to_bf16_bits(v))
+
+    def _new_state(self):
+        if self.opt == capi.SGD:
+            return np.zeros(0, dtype=F)
+        if self.opt == capi.ADAGRAD:
+            return np.full(self.dim, self.init_accum, dtype=F)
+        return np.zeros(2 * self.dim, dtype=F)
+
+    @staticmethod
+    def valid(k):
+        return k < capi.KEY_RESERVED
+
+    def _probe(self, keys, insert):
+        self.epoch += 1
+        n = len(keys)
+        rows = np.zeros((n, self.dim), dtype=F)
+        st = np.zeros(n, dtype=np.uint8)
+        present_at_start = set(self.rows.keys())
+        for i, k in enumerate(int(x) for x in keys):
+            if not self.valid(k):
+                st[i] = capi.KEY_INVALID
+                continue
+            if k not in self.rows:
+                if not insert:
+                    st[i] = capi.KEY_MISS
+                    continue
+                if len(self.rows) >= self.capacity:
+                    st[i] = capi.KEY_FULL
+                    continue
+                self.rows[k] = self._store(init_row(k, self.seed, self.dim, self.init_scale))
+                self.state[k] = self._new_state()
+                self.step[k] = 0
+                self.freq[k] = 0
+                self.last[k] = 0
+            st[i] = capi.KEY_FOUND if k in present_at_start else capi.KEY_INSERTED
+            rows[i] = self.rows[k]
+            if self.track:
+                self.freq[k] = (self.freq[k] + 1) & 0xFFFFFFFF
+                self.last[k] = self.epoch
+        return rows, st
+
+    def find_or_insert(self, keys):
+        return self._probe(keys, True)
+
+    def lookup(self, keys):
+        return self._probe(keys, False)
+
+    @staticmethod
+    def reduce(glist):
+        total = None
+        for c0 in range(0, len(glist), LEAF):
+            leaf = glist[c0].astype(F).copy()
+            for g in glist[c0 + 1:c0 + LEAF]:
+                leaf = leaf + g
+            total = leaf if total is None else total + leaf
+        return total
+
+    def _round_grad(self, g):
+        return self._store(np.asarray(g, dtype=F))
+
+    def apply_gradients(self, keys, grads):
+        groups = {}
+        for i, k in enumerate(int(x) for x in keys):
+            if self.valid(k) and k in self.rows:
+                groups.setdefault(k, []).append(np.asarray(grads[i], dtype=F))
+        for k, gl in groups.items():
+            g = self.reduce(gl)
+            w = self.rows[k]
+            if self.opt == capi.SGD:
+                w = w - self.lr * g
+            elif self.opt == capi.ADAGRAD:
+                a = self.state[k] + g * g
+                w = w - (self.lr * g) / (np.sqrt(a) + self.eps)
+                self.state[k] = a
+            else:
+                self.step[k] += 1
+                t = self.step[k]
+                bc1 = 1.0 - float(self.b1) ** t
+                bc2 = 1.0 - float(self.b2) ** t
+                alpha = F(float(self.lr) * math.sqrt(bc2) / bc1)
+                m, v = self.state[k][:self.dim], self.state[k][self.dim:]
+                m = self.b1 * m + (F(1.0) - self.b1) * g
+                v = self.b2 * v + (F(1.0) - self.b2) * (g * g)
+                w = w - (alpha * m) / (np.sqrt(v) + self.eps)
+                self.state[k] = np.concatenate([m, v])
+            self.rows[k] = self._store(w)
+
+    def evict(self, policy, target_load):
+        target = int(math.floor(target_load * self.capacity))
+        if len(self.rows) <= target:
+            return 0
+        k = len(self.rows) - target
+        score = self.freq if policy == capi.LFU else self.last
+        victims = sorted(self.rows.keys(), key=lambda key: (score[key], key))[:k]
+        for key in victims:
+            if self.spill_tuples:
+                self.spill.pop(key, None)
+                while len(self.spill) >= self.spill_tuples:
+                    self.spill.pop(next(iter(self.spill)))
+                self.spill[key] = (self.rows[key], self.state[key], self.step[key], self.freq[key], self.last[key])
+            for d in (self.rows, self.state, self.step, self.freq, self.last):
+                del d[key]
+        return k
+
+    def readmit(self, keys):
+        st = np.zeros(len(keys), dtype=np.uint8)
+        for i, k in enumerate(int(x) for x in keys):
+            if not self.valid(k):
+                st[i] = capi.KEY_INVALID
+            elif k in self.rows:
+                st[i] = capi.KEY_FOUND
+                self.spill.pop(k, None)
+            elif k not in self.spill:
+                st[i] = capi.KEY_MISS
+            elif len(self.rows) >= self.capacity:
+                st[i] = capi.KEY_FULL
+            else:
+                self.rows[k], self.state[k], self.step[k], self.freq[k], self.last[k] = self.spill.pop(k)
+                st[i] = capi.KEY_INSERTED
+        return st

@@ -1,0 +1,220 @@
+"""Pins the AUTHORED oracle (oracle/meepo_oracle.cc) against the pure-Python dict model.
+
+The upstream reference ships no tests or vectors (/root/reference/README.md:1-2), so this is the
+first of the three pins listed in the oracle's header. CPU only.
+"""
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st
+
+from meepoembedding_b200 import Table
+from meepoembedding_b200 import _capi as capi
+
+from pymodel import Model, owner
+from util import DT, OPT, export_sorted, grads_for, make_keys, rows_as_f32, table_kwargs
+
+
+def make_pair(oracle_lib, **kw):
+    kw = table_kwargs(**kw)
+    t = Table(lib=oracle_lib, **kw)
+    spill_tuples = kw.get("host_spill_bytes", 0) // (24 + t.row_bytes + t.state_bytes)
+    m = Model(kw["dim"], kw["capacity"], DT[kw["dtype"]], OPT[kw["optimizer"]], kw["lr"], kw["eps"], kw["beta1"],
+              kw["beta2"], kw["init_accum"], kw["init_scale"], kw["init_seed"], kw.get("track_scores", False),
+              spill_tuples)
+    return t, m
+
+
+def check_table_equal(t, m, dtype):
+    keys, rows, state, scores, steps = export_sorted(t)
+    assert keys.tolist() == sorted(m.rows.keys())
+    r32 = rows_as_f32(rows, dtype)
+    for j, k in enumerate(keys.tolist()):
+        np.testing.assert_array_equal(r32[j], m.rows[k], err_msg=f"row of key {k}")
+        if t.state_bytes:
+            np.testing.assert_array_equal(state[j], m.state[k], err_msg=f"state of key {k}")
+        assert steps[j] == (m.step[k] if m.opt == capi.ADAM else 0)
+        if m.track:
+            assert int(scores[j]) == (m.last[k] << 32) | m.freq[k]
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+@pytest.mark.parametrize("optimizer", ["sgd", "adagrad", "adam"])
+def test_stream_matches_model(oracle_lib, dtype, optimizer):
+    rng = np.random.default_rng(42)
+    t, m = make_pair(oracle_lib, dim=16, capacity=2048, dtype=dtype, optimizer=optimizer, track_scores=True)
+    for step in range(6):
+        keys = make_keys(rng, 300, 700)
+        rows, st_ = t.find_or_insert(keys)
+        mrows, mst = m.find_or_insert(keys)
+        np.testing.assert_array_equal(st_, mst)
+        np.testing.assert_array_equal(rows_as_f32(rows, dtype), mrows)
+        lk = make_keys(rng, 200, 1400)
+        rows, fd = t.lookup(lk)
+        mrows, mfd = m.lookup(lk)
+        np.testing.assert_array_equal(fd, mfd)
+        np.testing.assert_array_equal(rows_as_f32(rows, dtype), mrows)
+        g32 = rng.normal(0, 0.01, size=(keys.size, 16)).astype(np.float32)
+        g = grads_for(dtype, g32)
+        t.apply_gradients(keys, g)
+        m.apply_gradients(keys, rows_as_f32(g, dtype))
+        check_table_equal(t, m, dtype)
+    s = t.stats()
+    assert s["size"] == len(m.rows) and s["epoch"] == m.epoch
+
+
+def test_long_segment_reduction_tree(oracle_lib):
+    """One key repeated > LEAF times: the two-level tree must be followed exactly."""
+    rng = np.random.default_rng(3)
+    t, m = make_pair(oracle_lib, dim=8, capacity=64, optimizer="sgd")
+    keys = np.full(1000, 12345, dtype=np.uint64)
+    keys[::7] = 999  # interleave a second key
+    t.find_or_insert(keys), m.find_or_insert(keys)
+    g = (rng.normal(0, 1.0, size=(1000, 8)) * 10.0 ** rng.integers(-3, 4, size=(1000, 1))).astype(np.float32)
+    t.apply_gradients(keys, g), m.apply_gradients(keys, g)
+    check_table_equal(t, m, "f32")
+
+
+def test_known_answers(oracle_lib):
+    """Closed-form anchors: K duplicates with grad 1.0 sum to K exactly; one Adagrad step."""
+    t = Table(lib=oracle_lib, **table_kwargs(dim=4, capacity=64, optimizer="sgd", lr=1.0, init_scale=0.0))
+    keys = np.full(4097, 5, dtype=np.uint64)
+    t.find_or_insert(keys)
+    t.apply_gradients(keys, np.ones((4097, 4), dtype=np.float32))
+    rows, _ = t.lookup(np.array([5], dtype=np.uint64))
+    np.testing.assert_array_equal(rows, np.full((1, 4), -4097.0, dtype=np.float32))
+    t = Table(lib=oracle_lib, **table_kwargs(dim=4, capacity=64, optimizer="adagrad", lr=0.5, eps=0.0,
+                                              init_accum=0.0, init_scale=0.0))
+    k = np.array([9], dtype=np.uint64)
+    t.find_or_insert(k)
+    t.apply_gradients(k, np.full((1, 4), 2.0, dtype=np.float32))
+    rows, _ = t.lookup(k)  # a = 4, w = 0 - 0.5*2/sqrt(4) = -0.5
+    np.testing.assert_array_equal(rows, np.full((1, 4), -0.5, dtype=np.float32))
+
+
+def test_full_table_and_sentinels(oracle_lib):
+    t, m = make_pair(oracle_lib, dim=4, capacity=64, optimizer="sgd")
+    rng = np.random.default_rng(5)
+    keys = make_keys(rng, 200, 10_000, dup_frac=0.2)
+    rows, st_ = t.find_or_insert(keys)
+    mrows, mst = m.find_or_insert(keys)
+    np.testing.assert_array_equal(st_, mst)
+    np.testing.assert_array_equal(rows, mrows)
+    assert (st_ == capi.KEY_FULL).any() and (st_ == capi.KEY_INVALID).sum() == 2
+    assert t.stats()["size"] == 64
+    # empty batch is legal
+    t.find_or_insert(np.empty(0, dtype=np.uint64))
+    m.find_or_insert(np.empty(0, dtype=np.uint64))
+    assert t.stats()["epoch"] == m.epoch
+
+
+@pytest.mark.parametrize("policy", ["lfu", "lru"])
+def test_evict_spill_readmit(oracle_lib, policy):
+    rng = np.random.default_rng(11)
+    t, m = make_pair(oracle_lib, dim=8, capacity=256, dtype="bf16", optimizer="adam", track_scores=True,
+                     host_spill_bytes=40 * (24 + 16 + 64))
+    for _ in range(5):
+        keys = make_keys(rng, 120, 400, dup_frac=0.5)
+        t.find_or_insert(keys), m.find_or_insert(keys)
+        g = grads_for("bf16", rng.normal(0, 0.1, size=(keys.size, 8)))
+        t.apply_gradients(keys, g), m.apply_gradients(keys, rows_as_f32(g, "bf16"))
+    pol = capi.LFU if policy == "lfu" else capi.LRU
+    n = t.evict(policy, 0.5)
+    assert n == m.evict(pol, 0.5) and n > 40  # more victims than spill room: FIFO drop exercised
+    check_table_equal(t, m, "bf16")
+    assert t.stats()["spill_keys"] == len(m.spill)
+    probe = np.array(list(m.spill.keys())[:10] + [1, 2, capi.KEY_EMPTY] + list(m.rows.keys())[:3], dtype=np.uint64)
+    np.testing.assert_array_equal(t.spill_readmit(probe), m.readmit(probe))
+    check_table_equal(t, m, "bf16")
+    assert t.evict(policy, 1.0) == 0
+
+
+def test_export_import_roundtrip(oracle_lib, tmp_path):
+    rng = np.random.default_rng(13)
+    kw = table_kwargs(dim=8, capacity=512, dtype="bf16", optimizer="adam", track_scores=True)
+    a = Table(lib=oracle_lib, **kw)
+    for _ in range(3):
+        keys = make_keys(rng, 150, 300)
+        a.find_or_insert(keys)
+        a.apply_gradients(keys, grads_for("bf16", rng.normal(0, 0.1, size=(keys.size, 8))))
+    path = str(tmp_path / "t.meepo")
+    a.export_file(path)
+    b = Table(lib=oracle_lib, **kw)
+    b.import_file(path)
+    for x, y in zip(export_sorted(a), export_sorted(b)):
+        np.testing.assert_array_equal(x, y)
+    # a table with another shape refuses the file
+    c = Table(lib=oracle_lib, **table_kwargs(dim=16, capacity=512, dtype="bf16", optimizer="adam"))
+    with pytest.raises(capi.MeepoError):
+        c.import_file(path)
+
+
+def test_partition_reduce_gather(oracle_lib):
+    rng = np.random.default_rng(17)
+    t = Table(lib=oracle_lib, **table_kwargs(dim=8, capacity=64))
+    keys = make_keys(rng, 500, 200, dup_frac=0.4)
+    G = 4
+    counts = np.zeros(G, dtype=np.uint64)
+    perm = np.empty(keys.size, dtype=np.uint32)
+    ks = np.empty(keys.size, dtype=np.uint64)
+    t.shard_partition(keys, G, counts, perm, ks)
+    own = np.array([owner(int(k), G) for k in keys])
+    assert [t.owner(int(k), G) for k in keys[:50]] == own[:50].tolist()
+    np.testing.assert_array_equal(counts, np.bincount(own, minlength=G))
+    np.testing.assert_array_equal(perm, np.argsort(own, kind="stable"))
+    np.testing.assert_array_equal(ks, keys[perm])
+    g = rng.normal(0, 1, size=(keys.size, 8)).astype(np.float32)
+    uk = np.empty(keys.size, dtype=np.uint64)
+    ug = np.empty((keys.size, 8), dtype=np.float32)
+    inv = np.empty(keys.size, dtype=np.uint32)
+    nu = np.zeros(1, dtype=np.uint64)
+    t.reduce_duplicates(keys, g, uk, ug, inv, nu)
+    n_u = int(nu[0])
+    valid = keys < np.uint64(capi.KEY_RESERVED)
+    assert n_u == np.unique(keys[valid]).size
+    np.testing.assert_array_equal(uk[inv[valid]], keys[valid])
+    assert (inv[~valid] == 0xFFFFFFFF).all()
+    for u in range(n_u):
+        np.testing.assert_array_equal(ug[u], Model.reduce([g[i] for i in np.flatnonzero(keys == uk[u])]))
+    out = np.empty((keys.size, 8), dtype=np.float32)
+    t.gather_rows(ug, inv, out)
+    np.testing.assert_array_equal(out[valid], ug[inv[valid]])
+    assert (out[~valid] == 0).all()
+
+
+def test_bad_arguments(oracle_lib):
+    with pytest.raises(capi.MeepoError):
+        Table(lib=oracle_lib, **table_kwargs(dim=6))  # row bytes not a multiple of 16
+    with pytest.raises(capi.MeepoError):
+        Table(lib=oracle_lib, **table_kwargs(capacity=0))
+    t = Table(lib=oracle_lib, **table_kwargs())
+    with pytest.raises(capi.MeepoError):
+        t.evict("lfu", 0.5)  # scores not tracked
+
+
+@settings(max_examples=40, deadline=None)
+@given(st.lists(st.tuples(st.sampled_from(["foi", "lookup", "grad", "evict"]),
+                          st.lists(st.integers(0, 40), min_size=0, max_size=60)), min_size=1, max_size=8),
+       st.sampled_from(["f32", "bf16"]), st.sampled_from(["sgd", "adagrad", "adam"]))
+def test_hypothesis_streams(oracle_lib, ops, dtype, optimizer):
+    special = {38: capi.KEY_EMPTY, 39: capi.KEY_RESERVED, 40: capi.KEY_RESERVED - 1, 0: 0}
+    t, m = make_pair(oracle_lib, dim=8, capacity=32, dtype=dtype, optimizer=optimizer, track_scores=True)
+    rng = np.random.default_rng(0)
+    for op, ids in ops:
+        keys = np.array([special.get(i, i * 0x9E3779B97F4A7C15 & 0xFFFFFFFFFFFFFFFF) for i in ids], dtype=np.uint64)
+        if op == "foi":
+            r, s = t.find_or_insert(keys)
+            mr, ms = m.find_or_insert(keys)
+            np.testing.assert_array_equal(s, ms)
+            np.testing.assert_array_equal(rows_as_f32(r, dtype), mr)
+        elif op == "lookup":
+            r, s = t.lookup(keys)
+            mr, ms = m.lookup(keys)
+            np.testing.assert_array_equal(s, ms)
+            np.testing.assert_array_equal(rows_as_f32(r, dtype), mr)
+        elif op == "grad":
+            g = grads_for(dtype, rng.normal(0, 0.5, size=(keys.size, 8)))
+            t.apply_gradients(keys, g)
+            m.apply_gradients(keys, rows_as_f32(g, dtype))
+        else:
+            assert t.evict("lfu", 0.5) == m.evict(capi.LFU, 0.5)
+    check_table_equal(t, m, dtype)
