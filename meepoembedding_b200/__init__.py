@@ -4,6 +4,7 @@ Importing this package never falls back to a CPU implementation: `Table()`
 loads meepoembedding_b200/libmeepo.so (CUDA) and raises if it is missing.
 """
 from . import _capi as capi
+from . import keygen
 from ._capi import MeepoError, load_library, product_library
 from .table import Table
 

@@ -1,0 +1,185 @@
+// table.cu — life cycle of the CUDA table: create / destroy / stats, workspace, error state.
+// Implements the life-cycle block of include/meepo.h (DERIVED API; the upstream repository has
+// no code to mirror — /root/reference/README.md:1-2).
+#include "table.h"
+
+#include <cstdio>
+#include <cstring>
+
+namespace meepo {
+
+static thread_local std::string g_err;
+void set_error(const std::string& m) { g_err = m; }
+meepo_status fail(meepo_status s, const std::string& m) {
+  g_err = m;
+  return s;
+}
+const char* last_error_cstr() { return g_err.c_str(); }
+
+meepo_status Workspace::reserve(size_t need, cudaStream_t stream) {
+  used = 0;
+  if (need <= bytes) return MEEPO_OK;
+  // growing is rare (first call at a new batch size): drain the stream, then swap buffers
+  MEEPO_CUDA_TRY(cudaStreamSynchronize(stream));
+  if (base) MEEPO_CUDA_TRY(cudaFree(base));
+  base = nullptr;
+  bytes = 0;
+  size_t want = need + need / 4;
+  MEEPO_CUDA_TRY(cudaMalloc(&base, want));
+  bytes = want;
+  return MEEPO_OK;
+}
+
+int grid_for(const meepo_table* t, const void* kernel, int block, size_t smem, uint64_t blocks_needed) {
+  int per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem) != cudaSuccess || per_sm < 1)
+    per_sm = 1;
+  uint64_t cap = (uint64_t)t->num_sms * per_sm;
+  uint64_t g = blocks_needed < cap ? blocks_needed : cap;
+  return (int)(g < 1 ? 1 : g);
+}
+
+}  // namespace meepo
+
+using namespace meepo;
+
+extern "C" {
+
+MEEPO_API uint32_t meepo_abi_version(void) { return MEEPO_ABI_VERSION; }
+MEEPO_API const char* meepo_backend(void) { return "cuda-sm_100a"; }
+MEEPO_API const char* meepo_last_error(void) { return meepo::last_error_cstr(); }
+MEEPO_API uint32_t meepo_owner(uint64_t key, uint32_t num_shards) {
+  return (uint32_t)(((unsigned __int128)mix64(key ^ MEEPO_OWNER_SALT) * num_shards) >> 64);
+}
+
+MEEPO_API meepo_status meepo_destroy(meepo_table* t);
+
+MEEPO_API meepo_status meepo_create(const meepo_config* cfg, meepo_table** out) {
+  if (!cfg || !out) return fail(MEEPO_EINVAL, "null argument");
+  if (cfg->dtype != MEEPO_F32 && cfg->dtype != MEEPO_BF16) return fail(MEEPO_EINVAL, "bad dtype");
+  if (cfg->opt < MEEPO_SGD || cfg->opt > MEEPO_ADAM) return fail(MEEPO_EINVAL, "bad optimizer");
+  const uint32_t esz = cfg->dtype == MEEPO_F32 ? 4 : 2;
+  if (cfg->dim == 0 || ((uint64_t)cfg->dim * esz) % 16 != 0)
+    return fail(MEEPO_EINVAL, "row bytes must be a positive multiple of 16");
+  if (cfg->capacity == 0 || cfg->capacity > 0xFFFFFFC0ull) return fail(MEEPO_EINVAL, "bad capacity");
+  int ndev = 0;
+  MEEPO_CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(MEEPO_EINVAL, "bad device ordinal");
+  DeviceGuard guard(cfg->device);
+  if (!guard.ok) return fail(MEEPO_ECUDA, "cudaSetDevice failed");
+
+  meepo_table* t = new meepo_table();
+  t->cfg = *cfg;
+  t->device = cfg->device;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) {
+    delete t;
+    return fail(MEEPO_ECUDA, "cudaGetDeviceProperties failed");
+  }
+  t->num_sms = prop.multiProcessorCount;
+  const uint64_t slots = (cfg->capacity + kBucket - 1) / kBucket * kBucket;
+  t->row_bytes = cfg->dim * esz;
+  t->state_bytes = cfg->opt == MEEPO_SGD ? 0 : (cfg->opt == MEEPO_ADAGRAD ? cfg->dim * 4 : cfg->dim * 8);
+  TableView& v = t->v;
+  v.slots = (uint32_t)slots;
+  v.num_buckets = (uint32_t)(slots / kBucket);
+  v.cpr = t->row_bytes / 16;
+  v.scpr = t->state_bytes / 16;
+  v.dim = cfg->dim;
+  v.dtype = cfg->dtype;
+  v.opt = cfg->opt;
+  v.lr = cfg->lr;
+  v.eps = cfg->eps;
+  v.beta1 = cfg->beta1;
+  v.beta2 = cfg->beta2;
+  v.init_accum = cfg->init_accum;
+  v.init_scale = cfg->init_scale;
+  v.init_seed = cfg->init_seed;
+  v.epoch = 0;
+
+  auto bail = [&](cudaError_t e, const char* what) {
+    std::string m = std::string(what) + ": " + cudaGetErrorString(e);
+    meepo_destroy(t);
+    return fail(e == cudaErrorMemoryAllocation ? MEEPO_ENOMEM : MEEPO_ECUDA, m);
+  };
+  cudaError_t e;
+  const size_t ovf_words = (v.num_buckets + 31) / 32;
+  if ((e = cudaMalloc(&v.keys, slots * 8)) != cudaSuccess) return bail(e, "cudaMalloc(keys)");
+  if ((e = cudaMalloc(&v.digests, slots)) != cudaSuccess) return bail(e, "cudaMalloc(digests)");
+  if ((e = cudaMalloc(&v.overflow, ovf_words * 4)) != cudaSuccess) return bail(e, "cudaMalloc(overflow)");
+  if ((e = cudaMalloc(&v.rows, slots * (size_t)t->row_bytes)) != cudaSuccess) return bail(e, "cudaMalloc(rows)");
+  if (t->state_bytes &&
+      (e = cudaMalloc(&v.state, slots * (size_t)t->state_bytes)) != cudaSuccess)
+    return bail(e, "cudaMalloc(state)");
+  if ((cfg->flags & MEEPO_FLAG_TRACK_SCORES) && (e = cudaMalloc(&v.scores, slots * 8)) != cudaSuccess)
+    return bail(e, "cudaMalloc(scores)");
+  if (cfg->opt == MEEPO_ADAM && (e = cudaMalloc(&v.steps, slots * 4)) != cudaSuccess)
+    return bail(e, "cudaMalloc(steps)");
+  if ((e = cudaMalloc(&t->dstate, sizeof(DeviceState))) != cudaSuccess) return bail(e, "cudaMalloc(dstate)");
+  v.counters = t->dstate->counters;
+  if ((e = cudaMemset(v.keys, 0xFF, slots * 8)) != cudaSuccess) return bail(e, "memset");
+  if ((e = cudaMemset(v.digests, 0, slots)) != cudaSuccess) return bail(e, "memset");
+  if ((e = cudaMemset(v.overflow, 0, ovf_words * 4)) != cudaSuccess) return bail(e, "memset");
+  if (v.scores && (e = cudaMemset(v.scores, 0, slots * 8)) != cudaSuccess) return bail(e, "memset");
+  if (v.steps && (e = cudaMemset(v.steps, 0, slots * 4)) != cudaSuccess) return bail(e, "memset");
+  if ((e = cudaMemset(t->dstate, 0, sizeof(DeviceState))) != cudaSuccess) return bail(e, "memset");
+  if (cfg->host_spill_bytes) {
+    t->spill_cap_tuples = cfg->host_spill_bytes / t->tuple_bytes();
+    if (t->spill_cap_tuples) {
+      if ((e = cudaHostAlloc(&t->spill_ring, t->spill_cap_tuples * t->tuple_bytes(), cudaHostAllocDefault)) !=
+          cudaSuccess)
+        return bail(e, "cudaHostAlloc(spill)");
+      t->spill_ring_key.assign(t->spill_cap_tuples, MEEPO_KEY_EMPTY);
+      t->spill_ring_seq.assign(t->spill_cap_tuples, 0);
+    }
+  }
+  if ((e = cudaDeviceSynchronize()) != cudaSuccess) return bail(e, "cudaDeviceSynchronize");
+  *out = t;
+  return MEEPO_OK;
+}
+
+MEEPO_API meepo_status meepo_destroy(meepo_table* t) {
+  if (!t) return MEEPO_OK;
+  DeviceGuard guard(t->device);
+  cudaDeviceSynchronize();
+  destroy_host_pipe(t);
+  cudaFree(t->v.keys);
+  cudaFree(t->v.digests);
+  cudaFree(t->v.overflow);
+  cudaFree(t->v.rows);
+  cudaFree(t->v.state);
+  cudaFree(t->v.scores);
+  cudaFree(t->v.steps);
+  cudaFree(t->dstate);
+  cudaFree(t->ws.base);
+  if (t->spill_ring) cudaFreeHost(t->spill_ring);
+  delete t;
+  return MEEPO_OK;
+}
+
+MEEPO_API meepo_status meepo_stats(meepo_table* t, meepo_stats_t* out) {
+  if (!t || !out) return fail(MEEPO_EINVAL, "null argument");
+  DeviceGuard guard(t->device);
+  unsigned long long c[16];
+  MEEPO_CUDA_TRY(cudaDeviceSynchronize());
+  MEEPO_CUDA_TRY(cudaMemcpy(c, t->dstate->counters, sizeof c, cudaMemcpyDeviceToHost));
+  memset(out, 0, sizeof *out);
+  out->capacity = t->v.slots;
+  out->size = c[C_SIZE];
+  out->inserts = c[C_INSERTS];
+  out->hits = c[C_HITS];
+  out->misses = c[C_MISSES];
+  out->full = c[C_FULL];
+  out->evictions = c[C_EVICTIONS];
+  out->updates = c[C_UPDATES];
+  out->grad_dropped = c[C_DROPPED];
+  out->overflow_buckets = c[C_OVERFLOW];
+  out->spill_keys = t->spill_index.size();
+  out->spill_bytes = t->spill_index.size() * t->tuple_bytes();
+  out->epoch = t->epoch;
+  out->row_bytes = t->row_bytes;
+  out->state_bytes = t->state_bytes;
+  return MEEPO_OK;
+}
+
+}  // extern "C"

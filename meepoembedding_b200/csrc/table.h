@@ -1,0 +1,110 @@
+// table.h — host-side object behind the opaque meepo_table handle (CUDA build).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "common.cuh"
+
+namespace meepo {
+
+void set_error(const std::string& m);
+meepo_status fail(meepo_status s, const std::string& m);
+
+#define MEEPO_CUDA_TRY(expr)                                                                     \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess)                                                                       \
+      return ::meepo::fail(_e == cudaErrorMemoryAllocation ? MEEPO_ENOMEM : MEEPO_ECUDA,         \
+                           std::string(#expr) + ": " + cudaGetErrorString(_e));                  \
+  } while (0)
+
+#define MEEPO_TRY(expr)                \
+  do {                                 \
+    meepo_status _s = (expr);          \
+    if (_s != MEEPO_OK) return _s;     \
+  } while (0)
+
+// Bump allocator over one growable device buffer; reset at the start of every verb.
+struct Workspace {
+  char* base = nullptr;
+  size_t bytes = 0, used = 0;
+  meepo_status reserve(size_t need, cudaStream_t stream);
+  void reset() { used = 0; }
+  template <typename T>
+  T* take(size_t count) {
+    size_t off = (used + 255) & ~size_t(255);
+    used = off + count * sizeof(T);
+    return reinterpret_cast<T*>(base + off);
+  }
+  static size_t pad(size_t b) { return (b + 255) & ~size_t(255); }
+};
+
+// Small always-resident device block.
+struct DeviceState {
+  unsigned long long counters[16];
+  uint32_t new_count[2];   // ping-pong counters of slots claimed by find_or_insert
+  uint32_t num_segments;   // apply_gradients scratch
+  uint32_t num_long, num_leaves;
+  uint32_t evict_count;
+  uint32_t pad[2];
+  unsigned long long scratch64[8];
+};
+
+struct SpillTuple {  // host spill tier bookkeeping (payload lives in the pinned ring)
+  uint64_t seq;
+  uint64_t ring_index;
+};
+
+}  // namespace meepo
+
+struct meepo_table {
+  meepo_config cfg{};
+  meepo::TableView v{};
+  int device = 0;
+  int num_sms = 0;
+  uint32_t row_bytes = 0, state_bytes = 0;
+  meepo::DeviceState* dstate = nullptr;
+  meepo::Workspace ws;
+  uint32_t foi_parity = 0;
+  uint64_t epoch = 0;
+  // host-buffer front end (pinned staging + private streams), created lazily
+  struct HostPipe* pipe = nullptr;
+  // host spill tier
+  char* spill_ring = nullptr;       // pinned
+  uint64_t spill_cap_tuples = 0;
+  uint64_t spill_seq = 0;
+  std::unordered_map<uint64_t, meepo::SpillTuple> spill_index;  // key -> newest tuple
+  std::vector<uint64_t> spill_ring_key;                         // ring position -> key (EMPTY = free)
+  std::vector<uint64_t> spill_ring_seq;
+  uint64_t spill_head = 0;  // next ring position to write (FIFO)
+
+  uint64_t tuple_bytes() const { return 24 + (uint64_t)row_bytes + state_bytes; }
+};
+
+namespace meepo {
+// RAII device guard: every verb runs on the table's device.
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) ok = false;
+    if (ok && prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    want = dev;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0 && prev != want) cudaSetDevice(prev);
+  }
+  int want;
+};
+
+// kernels' host launchers (defined across the .cu files)
+meepo_status launch_probe_gather(meepo_table* t, const uint64_t* keys, uint64_t n, void* rows_out,
+                                 uint8_t* status_out, bool insert, cudaStream_t stream);
+meepo_status launch_apply_gradients(meepo_table* t, const uint64_t* keys, const void* grads, uint64_t n,
+                                    cudaStream_t stream);
+int grid_for(const meepo_table* t, const void* kernel, int block, size_t smem, uint64_t blocks_needed);
+void destroy_host_pipe(meepo_table* t);
+}  // namespace meepo

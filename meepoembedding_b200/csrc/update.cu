@@ -1,0 +1,495 @@
+// update.cu — apply_gradients: probe -> sort by slot -> segment heads -> fused reduce + optimizer
+// (semantics in include/meepo.h "Update").
+//
+// Duplicates are grouped by sorting (slot, batch index) pairs on the SLOT (<= 32 bits, and only
+// ceil(log2(slots+1)) of them) instead of the 64-bit key: the slot identifies the key, the sort is
+// stable so each segment lists its gradients by increasing batch index, and the per-key result
+// does not depend on where the slot happens to be. One sub-warp group of lanes then owns one
+// unique key: it sums the key's gradient rows in the normative order (leaves of 256, then leaf
+// partials) with 16-byte loads, and applies the optimizer to row + state in the same registers.
+// Segments longer than one leaf (hot Zipf keys, up to ~8% of the batch) are split into leaves that
+// run in parallel (leaf_kernel) and are finished by long_finish_kernel.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "table.h"
+
+namespace meepo {
+
+constexpr uint32_t kLeaf = MEEPO_REDUCE_LEAF;
+constexpr int kSegTile = 1024;  // sorted positions per CTA in the segment-head passes
+
+struct LongSeg {
+  uint32_t seg, base, nleaf, pad;
+};
+
+// ---------------------------------------------------------------------------------------------
+// A1: slot of every key (sort key) + iota (sort value)
+__global__ void __launch_bounds__(256) grad_slots_kernel(TableView t, const uint64_t* __restrict__ keys,
+                                                         uint32_t n, uint32_t* __restrict__ sort_key,
+                                                         uint32_t* __restrict__ sort_val) {
+  uint32_t dropped = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint64_t key = __ldg(keys + i);
+    uint32_t s = key_valid(key) ? probe_find(t, key) : kNil;
+    if (s == kNil) {
+      s = t.slots;  // sorts after every real slot
+      dropped++;
+    }
+    sort_key[i] = s;
+    sort_val[i] = i;
+  }
+  dropped = __reduce_add_sync(0xFFFFFFFFu, dropped);
+  if ((threadIdx.x & 31) == 0 && dropped) atomicAdd(t.counters + C_DROPPED, (unsigned long long)dropped);
+}
+
+// ---------------------------------------------------------------------------------------------
+// A3: segment heads of the sorted slot array -> seg_start[0..U] (compaction by a 3-pass scan)
+__device__ __forceinline__ bool is_head(const uint32_t* __restrict__ sk, uint32_t i) {
+  return i == 0 || sk[i] != sk[i - 1];
+}
+
+__global__ void __launch_bounds__(256) seg_count_kernel(const uint32_t* __restrict__ sk, uint32_t n,
+                                                        uint32_t* __restrict__ tile_count) {
+  const uint32_t base = blockIdx.x * kSegTile;
+  int total = 0;
+#pragma unroll
+  for (int k = 0; k < kSegTile / 256; k++) {
+    const uint32_t i = base + k * 256 + threadIdx.x;
+    total += __syncthreads_count(i < n && is_head(sk, i));
+  }
+  if (threadIdx.x == 0) tile_count[blockIdx.x] = (uint32_t)total;
+}
+
+// single CTA: exclusive scan of tile counts; publishes U and resets the long-segment counters
+__global__ void __launch_bounds__(1024) seg_scan_kernel(const uint32_t* __restrict__ tile_count,
+                                                        uint32_t ntiles, uint32_t* __restrict__ tile_off,
+                                                        uint32_t* __restrict__ seg_start, uint32_t n,
+                                                        const uint32_t* __restrict__ sk, uint32_t miss_key,
+                                                        DeviceState* ds) {
+  __shared__ uint32_t warp_sum[32];
+  __shared__ uint32_t carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (uint32_t base = 0; base < ntiles; base += 1024) {
+    const uint32_t i = base + threadIdx.x;
+    const uint32_t v = i < ntiles ? tile_count[i] : 0;
+    uint32_t x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+      if (lane >= d) x += y;
+    }
+    if (lane == 31) warp_sum[w] = x;
+    __syncthreads();
+    if (w == 0) {
+      uint32_t s = warp_sum[lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        uint32_t y = __shfl_up_sync(0xFFFFFFFFu, s, d);
+        if (lane >= d) s += y;
+      }
+      warp_sum[lane] = s;  // inclusive over warps
+    }
+    __syncthreads();
+    const uint32_t carry = carry_s;
+    const uint32_t incl = x + (w ? warp_sum[w - 1] : 0);
+    if (i < ntiles) tile_off[i] = carry + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = carry + incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const uint32_t U = carry_s;
+    seg_start[U] = n;
+    ds->num_segments = U;
+    ds->num_long = 0;
+    ds->num_leaves = 0;
+    const uint32_t applied = U - (n && sk[n - 1] == miss_key ? 1u : 0u);
+    if (applied) atomicAdd(ds->counters + C_UPDATES, (unsigned long long)applied);
+  }
+}
+
+__global__ void __launch_bounds__(256) seg_fill_kernel(const uint32_t* __restrict__ sk, uint32_t n,
+                                                       const uint32_t* __restrict__ tile_off,
+                                                       uint32_t* __restrict__ seg_start) {
+  __shared__ uint32_t warp_cnt[8];
+  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint32_t running = tile_off[blockIdx.x];
+  const uint32_t base = blockIdx.x * kSegTile;
+#pragma unroll 1
+  for (int k = 0; k < kSegTile / 256; k++) {
+    const uint32_t i = base + k * 256 + threadIdx.x;
+    const bool head = i < n && is_head(sk, i);
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, head);
+    if (lane == 0) warp_cnt[w] = __popc(m);
+    __syncthreads();
+    uint32_t before = 0, total = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const uint32_t c = warp_cnt[j];
+      before += j < (int)w ? c : 0;
+      total += c;
+    }
+    if (head) seg_start[running + before + __popc(m & ((1u << lane) - 1u))] = i;
+    running += total;
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// gradient chunk helpers. E = fp32 elements per 16-byte chunk (4 for fp32 tables, 8 for bf16).
+template <bool BF16>
+struct Chunk {
+  static constexpr int E = BF16 ? 8 : 4;
+};
+
+template <bool BF16>
+__device__ __forceinline__ void widen(const uint4& raw, float (&g)[Chunk<BF16>::E]) {
+  if constexpr (BF16) {
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      g[2 * i] = __uint_as_float(w[i] << 16);
+      g[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+    }
+  } else {
+    g[0] = __uint_as_float(raw.x);
+    g[1] = __uint_as_float(raw.y);
+    g[2] = __uint_as_float(raw.z);
+    g[3] = __uint_as_float(raw.w);
+  }
+}
+
+// acc = ((g[s0] + g[s0+1]) + ...) over sorted positions [s0, s1), chunk q of every row.
+template <bool BF16>
+__device__ __forceinline__ void reduce_positions(const uint4* __restrict__ grads,
+                                                 const uint32_t* __restrict__ sidx, uint32_t s0, uint32_t s1,
+                                                 uint32_t cpr, uint32_t q, float (&acc)[Chunk<BF16>::E]) {
+  constexpr int E = Chunk<BF16>::E;
+  widen<BF16>(ld_nc(grads + (size_t)sidx[s0] * cpr + q), acc);
+  uint32_t j = s0 + 1;
+  for (; j + 4 <= s1; j += 4) {
+    uint4 raw[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) raw[u] = ld_nc(grads + (size_t)sidx[j + u] * cpr + q);
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      float g[E];
+      widen<BF16>(raw[u], g);
+#pragma unroll
+      for (int e = 0; e < E; e++) acc[e] = __fadd_rn(acc[e], g[e]);
+    }
+  }
+  for (; j < s1; j++) {
+    float g[E];
+    widen<BF16>(ld_nc(grads + (size_t)sidx[j] * cpr + q), g);
+#pragma unroll
+    for (int e = 0; e < E; e++) acc[e] = __fadd_rn(acc[e], g[e]);
+  }
+}
+
+// One optimizer step on chunk q of the row in `slot` (meepo.h "Update"; every op rounded once).
+template <bool BF16, int OPT>
+__device__ __forceinline__ void optimizer_chunk(const TableView& t, uint32_t slot, uint32_t q,
+                                                const float (&g)[Chunk<BF16>::E], float alpha) {
+  constexpr int E = Chunk<BF16>::E;
+  constexpr int SQ = E / 4;  // state uint4s per chunk
+  uint4* rowp = t.rows + (size_t)slot * t.cpr + q;
+  float w[E];
+  widen<BF16>(ld_stream(rowp), w);
+  if constexpr (OPT == MEEPO_SGD) {
+#pragma unroll
+    for (int e = 0; e < E; e++) w[e] = __fsub_rn(w[e], __fmul_rn(t.lr, g[e]));
+  } else if constexpr (OPT == MEEPO_ADAGRAD) {
+    uint4* sp = t.state + (size_t)slot * t.scpr + (size_t)q * SQ;
+    float a[E];
+#pragma unroll
+    for (int k = 0; k < SQ; k++) {
+      const uint4 raw = ld_stream(sp + k);
+      a[4 * k] = __uint_as_float(raw.x);
+      a[4 * k + 1] = __uint_as_float(raw.y);
+      a[4 * k + 2] = __uint_as_float(raw.z);
+      a[4 * k + 3] = __uint_as_float(raw.w);
+    }
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+      a[e] = __fadd_rn(a[e], __fmul_rn(g[e], g[e]));
+      const float den = __fadd_rn(__fsqrt_rn(a[e]), t.eps);
+      w[e] = __fsub_rn(w[e], __fdiv_rn(__fmul_rn(t.lr, g[e]), den));
+    }
+#pragma unroll
+    for (int k = 0; k < SQ; k++)
+      st_stream(sp + k, make_uint4(__float_as_uint(a[4 * k]), __float_as_uint(a[4 * k + 1]),
+                                   __float_as_uint(a[4 * k + 2]), __float_as_uint(a[4 * k + 3])));
+  } else {
+    uint4* mp = t.state + (size_t)slot * t.scpr + (size_t)q * SQ;
+    uint4* vp = mp + (size_t)t.cpr * SQ;
+    float m[E], v[E];
+#pragma unroll
+    for (int k = 0; k < SQ; k++) {
+      const uint4 a = ld_stream(mp + k), b = ld_stream(vp + k);
+      m[4 * k] = __uint_as_float(a.x), m[4 * k + 1] = __uint_as_float(a.y);
+      m[4 * k + 2] = __uint_as_float(a.z), m[4 * k + 3] = __uint_as_float(a.w);
+      v[4 * k] = __uint_as_float(b.x), v[4 * k + 1] = __uint_as_float(b.y);
+      v[4 * k + 2] = __uint_as_float(b.z), v[4 * k + 3] = __uint_as_float(b.w);
+    }
+    const float omb1 = __fsub_rn(1.0f, t.beta1), omb2 = __fsub_rn(1.0f, t.beta2);
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+      m[e] = __fadd_rn(__fmul_rn(t.beta1, m[e]), __fmul_rn(omb1, g[e]));
+      v[e] = __fadd_rn(__fmul_rn(t.beta2, v[e]), __fmul_rn(omb2, __fmul_rn(g[e], g[e])));
+      const float den = __fadd_rn(__fsqrt_rn(v[e]), t.eps);
+      w[e] = __fsub_rn(w[e], __fdiv_rn(__fmul_rn(alpha, m[e]), den));
+    }
+#pragma unroll
+    for (int k = 0; k < SQ; k++) {
+      st_stream(mp + k, make_uint4(__float_as_uint(m[4 * k]), __float_as_uint(m[4 * k + 1]),
+                                   __float_as_uint(m[4 * k + 2]), __float_as_uint(m[4 * k + 3])));
+      st_stream(vp + k, make_uint4(__float_as_uint(v[4 * k]), __float_as_uint(v[4 * k + 1]),
+                                   __float_as_uint(v[4 * k + 2]), __float_as_uint(v[4 * k + 3])));
+    }
+  }
+  uint4 outv;
+  if constexpr (BF16) {
+    outv = make_uint4(pack_bf16x2(w[0], w[1]), pack_bf16x2(w[2], w[3]), pack_bf16x2(w[4], w[5]),
+                      pack_bf16x2(w[6], w[7]));
+  } else {
+    outv = make_uint4(__float_as_uint(w[0]), __float_as_uint(w[1]), __float_as_uint(w[2]),
+                      __float_as_uint(w[3]));
+  }
+  st_stream(rowp, outv);
+}
+
+// Adam: per-row step count -> scalar step size (double math, rounded once). Every lane of the
+// group reads the old count, the group syncs, lane 0 writes the new one.
+template <int OPT>
+__device__ __forceinline__ float adam_alpha(const TableView& t, uint32_t slot, unsigned gmask, bool leader) {
+  if constexpr (OPT != MEEPO_ADAM) return 0.0f;
+  const uint32_t tt = t.steps[slot] + 1;
+  __syncwarp(gmask);
+  if (leader) t.steps[slot] = tt;
+  const double bc1 = 1.0 - pow((double)t.beta1, (double)tt);
+  const double bc2 = 1.0 - pow((double)t.beta2, (double)tt);
+  return (float)((double)t.lr * sqrt(bc2) / bc1);
+}
+
+struct ApplyArgs {
+  const uint4* grads;
+  const uint32_t* sorted_slot;
+  const uint32_t* sorted_idx;
+  const uint32_t* seg_start;
+  DeviceState* ds;
+  LongSeg* long_seg;
+  uint2* leaf_desc;
+  float* partial;  // [leaves][dim]
+  uint32_t group_lanes;  // power of two <= min(cpr, 32)
+};
+
+// A4: one group of lanes per segment (unique key)
+template <bool BF16, int OPT>
+__global__ void __launch_bounds__(256) apply_kernel(TableView t, ApplyArgs a) {
+  constexpr int E = Chunk<BF16>::E;
+  const uint32_t GL = a.group_lanes;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t gl = lane & (GL - 1);
+  const unsigned gmask = (GL == 32 ? 0xFFFFFFFFu : ((1u << GL) - 1u) << (lane & ~(GL - 1)));
+  const uint32_t groups_per_block = blockDim.x / GL;
+  const uint32_t group = blockIdx.x * groups_per_block + threadIdx.x / GL;
+  const uint32_t ngroups = gridDim.x * groups_per_block;
+  const uint32_t U = a.ds->num_segments;
+  for (uint32_t u = group; u < U; u += ngroups) {
+    const uint32_t s0 = a.seg_start[u], s1 = a.seg_start[u + 1];
+    const uint32_t slot = a.sorted_slot[s0];
+    if (slot >= t.slots) continue;  // the segment of absent / invalid keys
+    const uint32_t cnt = s1 - s0;
+    if (cnt > kLeaf) {  // hand over to the leaf kernels
+      const uint32_t nleaf = (cnt + kLeaf - 1) / kLeaf;
+      uint32_t base = 0;
+      if (gl == 0) {
+        const uint32_t li = atomicAdd(&a.ds->num_long, 1u);
+        base = atomicAdd(&a.ds->num_leaves, nleaf);
+        a.long_seg[li] = LongSeg{u, base, nleaf, 0};
+      }
+      base = __shfl_sync(gmask, base, lane & ~(GL - 1));
+      for (uint32_t c = gl; c < nleaf; c += GL) a.leaf_desc[base + c] = make_uint2(u, c);
+      continue;
+    }
+    const float alpha = adam_alpha<OPT>(t, slot, gmask, gl == 0);
+    for (uint32_t q = gl; q < t.cpr; q += GL) {
+      float acc[E];
+      reduce_positions<BF16>(a.grads, a.sorted_idx, s0, s1, t.cpr, q, acc);
+      optimizer_chunk<BF16, OPT>(t, slot, q, acc, alpha);
+    }
+  }
+}
+
+// A5: one group per leaf of a long segment -> partial[leaf]
+template <bool BF16>
+__global__ void __launch_bounds__(256) leaf_kernel(TableView t, ApplyArgs a) {
+  constexpr int E = Chunk<BF16>::E;
+  const uint32_t GL = a.group_lanes;
+  const uint32_t gl = threadIdx.x & (GL - 1);
+  const uint32_t groups_per_block = blockDim.x / GL;
+  const uint32_t group = blockIdx.x * groups_per_block + threadIdx.x / GL;
+  const uint32_t ngroups = gridDim.x * groups_per_block;
+  const uint32_t nleaves = a.ds->num_leaves;
+  for (uint32_t l = group; l < nleaves; l += ngroups) {
+    const uint2 d = a.leaf_desc[l];
+    const uint32_t s0 = a.seg_start[d.x] + d.y * kLeaf;
+    const uint32_t s1 = min(a.seg_start[d.x + 1], s0 + kLeaf);
+    for (uint32_t q = gl; q < t.cpr; q += GL) {
+      float acc[E];
+      reduce_positions<BF16>(a.grads, a.sorted_idx, s0, s1, t.cpr, q, acc);
+      float4* p = reinterpret_cast<float4*>(a.partial + (size_t)l * t.dim + (size_t)q * E);
+#pragma unroll
+      for (int k = 0; k < E / 4; k++) p[k] = make_float4(acc[4 * k], acc[4 * k + 1], acc[4 * k + 2], acc[4 * k + 3]);
+    }
+  }
+}
+
+// A6: one group per long segment: G = ((leaf_0 + leaf_1) + leaf_2) + ..., then the optimizer
+template <bool BF16, int OPT>
+__global__ void __launch_bounds__(256) long_finish_kernel(TableView t, ApplyArgs a) {
+  constexpr int E = Chunk<BF16>::E;
+  const uint32_t GL = a.group_lanes;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t gl = lane & (GL - 1);
+  const unsigned gmask = (GL == 32 ? 0xFFFFFFFFu : ((1u << GL) - 1u) << (lane & ~(GL - 1)));
+  const uint32_t groups_per_block = blockDim.x / GL;
+  const uint32_t group = blockIdx.x * groups_per_block + threadIdx.x / GL;
+  const uint32_t ngroups = gridDim.x * groups_per_block;
+  const uint32_t nlong = a.ds->num_long;
+  for (uint32_t li = group; li < nlong; li += ngroups) {
+    const LongSeg ls = a.long_seg[li];
+    const uint32_t slot = a.sorted_slot[a.seg_start[ls.seg]];
+    const float alpha = adam_alpha<OPT>(t, slot, gmask, gl == 0);
+    for (uint32_t q = gl; q < t.cpr; q += GL) {
+      float acc[E];
+      const float* p0 = a.partial + (size_t)ls.base * t.dim + (size_t)q * E;
+#pragma unroll
+      for (int e = 0; e < E; e++) acc[e] = p0[e];
+      for (uint32_t c = 1; c < ls.nleaf; c++) {
+        const float4* p = reinterpret_cast<const float4*>(a.partial + (size_t)(ls.base + c) * t.dim + (size_t)q * E);
+#pragma unroll
+        for (int k = 0; k < E / 4; k++) {
+          const float4 x = p[k];
+          acc[4 * k] = __fadd_rn(acc[4 * k], x.x);
+          acc[4 * k + 1] = __fadd_rn(acc[4 * k + 1], x.y);
+          acc[4 * k + 2] = __fadd_rn(acc[4 * k + 2], x.z);
+          acc[4 * k + 3] = __fadd_rn(acc[4 * k + 3], x.w);
+        }
+      }
+      optimizer_chunk<BF16, OPT>(t, slot, q, acc, alpha);
+    }
+  }
+}
+
+template <bool BF16>
+static void pick_apply(int opt, const void*& apply, const void*& finish) {
+  switch (opt) {
+    case MEEPO_SGD:
+      apply = (const void*)apply_kernel<BF16, MEEPO_SGD>;
+      finish = (const void*)long_finish_kernel<BF16, MEEPO_SGD>;
+      break;
+    case MEEPO_ADAGRAD:
+      apply = (const void*)apply_kernel<BF16, MEEPO_ADAGRAD>;
+      finish = (const void*)long_finish_kernel<BF16, MEEPO_ADAGRAD>;
+      break;
+    default:
+      apply = (const void*)apply_kernel<BF16, MEEPO_ADAM>;
+      finish = (const void*)long_finish_kernel<BF16, MEEPO_ADAM>;
+  }
+}
+
+meepo_status launch_apply_gradients(meepo_table* t, const uint64_t* keys, const void* grads, uint64_t n,
+                                    cudaStream_t stream) {
+  if (n == 0) return MEEPO_OK;
+  const uint32_t n32 = (uint32_t)n;
+  const uint32_t ntiles = (n32 + kSegTile - 1) / kSegTile;
+  const size_t max_long = n / (kLeaf + 1) + 1;
+  const size_t max_leaves = n / 128 + 2;
+  int end_bit = 1;
+  while (end_bit < 32 && (t->v.slots >> end_bit)) end_bit++;
+
+  size_t cub_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                  (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n32, 0, end_bit, stream);
+  size_t need = 4 * Workspace::pad(n * 4) + Workspace::pad(cub_bytes) + 2 * Workspace::pad(ntiles * 4) +
+                Workspace::pad((n + 2) * 4) + Workspace::pad(max_long * sizeof(LongSeg)) +
+                Workspace::pad(max_leaves * 8) + Workspace::pad(max_leaves * t->v.dim * 4) + 4096;
+  MEEPO_TRY(t->ws.reserve(need, stream));
+  uint32_t* sk_in = t->ws.take<uint32_t>(n);
+  uint32_t* sk_out = t->ws.take<uint32_t>(n);
+  uint32_t* sv_in = t->ws.take<uint32_t>(n);
+  uint32_t* sv_out = t->ws.take<uint32_t>(n);
+  char* cub_tmp = t->ws.take<char>(cub_bytes);
+  uint32_t* tile_count = t->ws.take<uint32_t>(ntiles);
+  uint32_t* tile_off = t->ws.take<uint32_t>(ntiles);
+  uint32_t* seg_start = t->ws.take<uint32_t>(n + 2);
+  LongSeg* long_seg = t->ws.take<LongSeg>(max_long);
+  uint2* leaf_desc = t->ws.take<uint2>(max_leaves);
+  float* partial = t->ws.take<float>(max_leaves * t->v.dim);
+
+  {
+    const int grid = grid_for(t, (const void*)grad_slots_kernel, 256, 0, (n + 255) / 256);
+    grad_slots_kernel<<<grid, 256, 0, stream>>>(t->v, keys, n32, sk_in, sv_in);
+    MEEPO_CUDA_TRY(cudaGetLastError());
+  }
+  MEEPO_CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, (const uint32_t*)sk_in, sk_out,
+                                                 (const uint32_t*)sv_in, sv_out, (int)n32, 0, end_bit, stream));
+  seg_count_kernel<<<ntiles, 256, 0, stream>>>(sk_out, n32, tile_count);
+  seg_scan_kernel<<<1, 1024, 0, stream>>>(tile_count, ntiles, tile_off, seg_start, n32, sk_out, t->v.slots,
+                                          t->dstate);
+  seg_fill_kernel<<<ntiles, 256, 0, stream>>>(sk_out, n32, tile_off, seg_start);
+  MEEPO_CUDA_TRY(cudaGetLastError());
+
+  ApplyArgs a;
+  a.grads = reinterpret_cast<const uint4*>(grads);
+  a.sorted_slot = sk_out;
+  a.sorted_idx = sv_out;
+  a.seg_start = seg_start;
+  a.ds = t->dstate;
+  a.long_seg = long_seg;
+  a.leaf_desc = leaf_desc;
+  a.partial = partial;
+  uint32_t gl = 1;
+  while (gl * 2 <= t->v.cpr && gl < 32) gl *= 2;
+  a.group_lanes = gl;
+
+  const bool bf16 = t->v.dtype == MEEPO_BF16;
+  const void *k_apply = nullptr, *k_finish = nullptr;
+  if (bf16)
+    pick_apply<true>(t->v.opt, k_apply, k_finish);
+  else
+    pick_apply<false>(t->v.opt, k_apply, k_finish);
+  const void* k_leaf = bf16 ? (const void*)leaf_kernel<true> : (const void*)leaf_kernel<false>;
+  void* args[] = {&t->v, &a};
+  const uint64_t groups_per_block = 256 / gl;
+  {
+    const int grid = grid_for(t, k_apply, 256, 0, (n + groups_per_block - 1) / groups_per_block);
+    MEEPO_CUDA_TRY(cudaLaunchKernel(k_apply, dim3(grid), dim3(256), args, 0, stream));
+  }
+  {
+    const int grid = grid_for(t, k_leaf, 256, 0, (max_leaves + groups_per_block - 1) / groups_per_block);
+    MEEPO_CUDA_TRY(cudaLaunchKernel(k_leaf, dim3(grid), dim3(256), args, 0, stream));
+  }
+  {
+    const int grid = grid_for(t, k_finish, 256, 0, (max_long + groups_per_block - 1) / groups_per_block);
+    MEEPO_CUDA_TRY(cudaLaunchKernel(k_finish, dim3(grid), dim3(256), args, 0, stream));
+  }
+  return MEEPO_OK;
+}
+
+}  // namespace meepo
+
+using namespace meepo;
+
+extern "C" MEEPO_API meepo_status meepo_apply_gradients(meepo_table* t, const uint64_t* keys,
+                                                        const void* grads, uint64_t n, void* stream) {
+  if (!t) return fail(MEEPO_EINVAL, "null table");
+  if (n > 0xFFFFFFFFull) return fail(MEEPO_EINVAL, "batch too large (n must fit in 32 bits)");
+  if (n && (!keys || !grads)) return fail(MEEPO_EINVAL, "null buffer");
+  DeviceGuard guard(t->device);
+  return launch_apply_gradients(t, keys, grads, n, (cudaStream_t)stream);
+}
