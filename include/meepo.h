@@ -175,6 +175,14 @@ MEEPO_API meepo_status meepo_stats(meepo_table* t, meepo_stats_t* out);
 /* thread-local, never NULL */
 MEEPO_API const char* meepo_last_error(void);
 
+/* --- per-kernel timing (bench.py's roofline leg) --------------------------- *
+ * When enabled the library brackets every kernel it launches with CUDA events
+ * on the launch stream. meepo_profile_read drains them and writes one line per
+ * kernel group, "name launches total_ms\n", NUL-terminated, into buf. Enabling
+ * resets the accumulators. The oracle accepts both calls and reports nothing. */
+MEEPO_API meepo_status meepo_profile_enable(meepo_table* t, int32_t on);
+MEEPO_API meepo_status meepo_profile_read(meepo_table* t, char* buf, uint64_t buf_bytes);
+
 /* --- hot path (stream-ordered, asynchronous; device pointers) ------------ */
 /* rows_out: n*dim elements; status_out: n bytes (may be NULL). */
 MEEPO_API meepo_status meepo_find_or_insert(meepo_table* t, const uint64_t* keys, uint64_t n,

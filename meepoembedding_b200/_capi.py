@@ -88,6 +88,8 @@ SIGNATURES = {
     "meepo_destroy": (C.c_int, [_P]),
     "meepo_stats": (C.c_int, [_P, C.POINTER(Stats)]),
     "meepo_last_error": (C.c_char_p, []),
+    "meepo_profile_enable": (C.c_int, [_P, C.c_int32]),
+    "meepo_profile_read": (C.c_int, [_P, C.c_char_p, _U64]),
     "meepo_find_or_insert": (C.c_int, [_P, _P, _U64, _P, _P, _P]),
     "meepo_lookup": (C.c_int, [_P, _P, _U64, _P, _P, _P]),
     "meepo_apply_gradients": (C.c_int, [_P, _P, _P, _U64, _P]),

@@ -14,11 +14,6 @@
 
 namespace meepo {
 
-struct NewList {
-  uint32_t* slots;  // [n] slots claimed in this launch
-  uint32_t* count;
-};
-
 template <int CPR>
 __device__ __forceinline__ void gather_tile_fast(const TableView& t, uint32_t slot, uint32_t tile_keys,
                                                  uint4* __restrict__ out_tile, uint32_t lane) {
@@ -165,33 +160,54 @@ static const void* pick_kernel(uint32_t cpr) {
   }
 }
 
-meepo_status launch_probe_gather(meepo_table* t, const uint64_t* keys, uint64_t n, void* rows_out,
-                                 uint8_t* status_out, bool insert, cudaStream_t stream) {
+// A find_or_insert / lookup call = begin, one or more chunks, end. Chunks of one call share the
+// epoch and (find_or_insert) the claimed-slot list; tags are published once, in end, so a key that
+// is new in the call reports INSERTED in every chunk (meepo.h "Status").
+meepo_status probe_gather_begin(meepo_table* t, uint64_t n_total, bool insert, cudaStream_t stream) {
   t->epoch++;
   t->v.epoch = (uint32_t)t->epoch;
-  if (n == 0) return MEEPO_OK;
-  NewList nl{nullptr, nullptr};
-  uint32_t* next = nullptr;
-  if (insert) {
-    MEEPO_TRY(t->ws.reserve(Workspace::pad(n * 4), stream));
-    nl.slots = t->ws.take<uint32_t>(n);
-    nl.count = &t->dstate->new_count[t->foi_parity];
-    next = &t->dstate->new_count[t->foi_parity ^ 1];
+  t->cur_new.slots = nullptr;
+  t->cur_new.count = nullptr;
+  t->cur_new_next = nullptr;
+  if (insert && n_total) {
+    MEEPO_TRY(t->ws.reserve(Workspace::pad(n_total * 4), stream));
+    t->cur_new.slots = t->ws.take<uint32_t>(n_total);
+    t->cur_new.count = &t->dstate->new_count[t->foi_parity];
+    t->cur_new_next = &t->dstate->new_count[t->foi_parity ^ 1];
     t->foi_parity ^= 1;
   }
+  return MEEPO_OK;
+}
+
+meepo_status probe_gather_chunk(meepo_table* t, const uint64_t* keys, uint64_t n, void* rows_out,
+                                uint8_t* status_out, bool insert, cudaStream_t stream) {
+  if (n == 0) return MEEPO_OK;
   const void* kern = insert ? pick_kernel<true>(t->v.cpr) : pick_kernel<false>(t->v.cpr);
   const uint64_t tiles = (n + 31) / 32;
   const int grid = grid_for(t, kern, 256, 0, (tiles + 7) / 8);
   uint32_t n32 = (uint32_t)n;
   uint4* out = reinterpret_cast<uint4*>(rows_out);
+  NewList nl{t->cur_new.slots, t->cur_new.count};
   void* args[] = {&t->v, &keys, &n32, &out, &status_out, &nl};
+  ProfScope ps(t, insert ? "find_or_insert.probe_gather" : "lookup.probe_gather", stream);
   MEEPO_CUDA_TRY(cudaLaunchKernel(kern, dim3(grid), dim3(256), args, 0, stream));
-  if (insert) {
-    const int pgrid = (int)std::min<uint64_t>((n + 255) / 256, (uint64_t)t->num_sms * 8);
-    publish_kernel<<<pgrid, 256, 0, stream>>>(t->v, nl.slots, nl.count, next);
-    MEEPO_CUDA_TRY(cudaGetLastError());
-  }
   return MEEPO_OK;
+}
+
+meepo_status probe_gather_end(meepo_table* t, uint64_t n_total, bool insert, cudaStream_t stream) {
+  if (!insert || !n_total) return MEEPO_OK;
+  ProfScope ps(t, "find_or_insert.publish", stream);
+  const int pgrid = (int)std::min<uint64_t>((n_total + 255) / 256, (uint64_t)t->num_sms * 8);
+  publish_kernel<<<pgrid, 256, 0, stream>>>(t->v, t->cur_new.slots, t->cur_new.count, t->cur_new_next);
+  MEEPO_CUDA_TRY(cudaGetLastError());
+  return MEEPO_OK;
+}
+
+meepo_status launch_probe_gather(meepo_table* t, const uint64_t* keys, uint64_t n, void* rows_out,
+                                 uint8_t* status_out, bool insert, cudaStream_t stream) {
+  MEEPO_TRY(probe_gather_begin(t, n, insert, stream));
+  MEEPO_TRY(probe_gather_chunk(t, keys, n, rows_out, status_out, insert, stream));
+  return probe_gather_end(t, n, insert, stream);
 }
 
 }  // namespace meepo

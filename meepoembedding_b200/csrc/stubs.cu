@@ -3,11 +3,7 @@
 #include "table.h"
 using namespace meepo;
 #define NOT_YET(name) return fail(MEEPO_EINVAL, name ": not implemented in the CUDA build yet")
-namespace meepo { void destroy_host_pipe(meepo_table*) {} }
 extern "C" {
-MEEPO_API meepo_status meepo_find_or_insert_host(meepo_table*, const uint64_t*, uint64_t, void*, uint8_t*) { NOT_YET("meepo_find_or_insert_host"); }
-MEEPO_API meepo_status meepo_lookup_host(meepo_table*, const uint64_t*, uint64_t, void*, uint8_t*) { NOT_YET("meepo_lookup_host"); }
-MEEPO_API meepo_status meepo_apply_gradients_host(meepo_table*, const uint64_t*, const void*, uint64_t) { NOT_YET("meepo_apply_gradients_host"); }
 MEEPO_API meepo_status meepo_evict(meepo_table*, int32_t, double, uint64_t*, void*) { NOT_YET("meepo_evict"); }
 MEEPO_API meepo_status meepo_spill_readmit(meepo_table*, const uint64_t*, uint64_t, uint8_t*) { NOT_YET("meepo_spill_readmit"); }
 MEEPO_API meepo_status meepo_export_buffers(meepo_table*, uint64_t*, void*, void*, uint64_t*, uint32_t*, uint64_t, uint64_t*) { NOT_YET("meepo_export_buffers"); }

@@ -143,6 +143,7 @@ MEEPO_API meepo_status meepo_destroy(meepo_table* t) {
   DeviceGuard guard(t->device);
   cudaDeviceSynchronize();
   destroy_host_pipe(t);
+  destroy_profiler(t);
   cudaFree(t->v.keys);
   cudaFree(t->v.digests);
   cudaFree(t->v.overflow);

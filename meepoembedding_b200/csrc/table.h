@@ -53,6 +53,13 @@ struct DeviceState {
   unsigned long long scratch64[8];
 };
 
+struct Profiler;
+
+struct NewList {
+  uint32_t* slots;  // slots claimed by the find_or_insert call in flight
+  uint32_t* count;
+};
+
 struct SpillTuple {  // host spill tier bookkeeping (payload lives in the pinned ring)
   uint64_t seq;
   uint64_t ring_index;
@@ -69,7 +76,10 @@ struct meepo_table {
   meepo::DeviceState* dstate = nullptr;
   meepo::Workspace ws;
   uint32_t foi_parity = 0;
+  meepo::NewList cur_new{nullptr, nullptr};
+  uint32_t* cur_new_next = nullptr;
   uint64_t epoch = 0;
+  struct meepo::Profiler* prof = nullptr;  // per-kernel event timing, off unless enabled
   // host-buffer front end (pinned staging + private streams), created lazily
   struct HostPipe* pipe = nullptr;
   // host spill tier
@@ -103,8 +113,24 @@ struct DeviceGuard {
 // kernels' host launchers (defined across the .cu files)
 meepo_status launch_probe_gather(meepo_table* t, const uint64_t* keys, uint64_t n, void* rows_out,
                                  uint8_t* status_out, bool insert, cudaStream_t stream);
+meepo_status probe_gather_begin(meepo_table* t, uint64_t n_total, bool insert, cudaStream_t stream);
+meepo_status probe_gather_chunk(meepo_table* t, const uint64_t* keys, uint64_t n, void* rows_out,
+                                uint8_t* status_out, bool insert, cudaStream_t stream);
+meepo_status probe_gather_end(meepo_table* t, uint64_t n_total, bool insert, cudaStream_t stream);
+// grads_ready (optional): event the reduce kernels wait for, so a caller can overlap the copy of
+// the gradients with the probe / sort / segment passes that only need the keys.
 meepo_status launch_apply_gradients(meepo_table* t, const uint64_t* keys, const void* grads, uint64_t n,
-                                    cudaStream_t stream);
+                                    cudaStream_t stream, cudaEvent_t grads_ready = nullptr);
 int grid_for(const meepo_table* t, const void* kernel, int block, size_t smem, uint64_t blocks_needed);
 void destroy_host_pipe(meepo_table* t);
+void destroy_profiler(meepo_table* t);
+// Times the kernels launched inside its lifetime when profiling is on (profile.cu).
+struct ProfScope {
+  ProfScope(meepo_table* t, const char* name, cudaStream_t s);
+  ~ProfScope();
+  meepo_table* t_;
+  const char* name_;
+  cudaStream_t s_;
+  cudaEvent_t a_ = nullptr;
+};
 }  // namespace meepo

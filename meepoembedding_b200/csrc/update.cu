@@ -403,7 +403,7 @@ static void pick_apply(int opt, const void*& apply, const void*& finish) {
 }
 
 meepo_status launch_apply_gradients(meepo_table* t, const uint64_t* keys, const void* grads, uint64_t n,
-                                    cudaStream_t stream) {
+                                    cudaStream_t stream, cudaEvent_t grads_ready) {
   if (n == 0) return MEEPO_OK;
   const uint32_t n32 = (uint32_t)n;
   const uint32_t ntiles = (n32 + kSegTile - 1) / kSegTile;
@@ -432,17 +432,24 @@ meepo_status launch_apply_gradients(meepo_table* t, const uint64_t* keys, const 
   float* partial = t->ws.take<float>(max_leaves * t->v.dim);
 
   {
+    ProfScope ps(t, "apply.grad_slots", stream);
     const int grid = grid_for(t, (const void*)grad_slots_kernel, 256, 0, (n + 255) / 256);
     grad_slots_kernel<<<grid, 256, 0, stream>>>(t->v, keys, n32, sk_in, sv_in);
     MEEPO_CUDA_TRY(cudaGetLastError());
   }
-  MEEPO_CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, (const uint32_t*)sk_in, sk_out,
-                                                 (const uint32_t*)sv_in, sv_out, (int)n32, 0, end_bit, stream));
-  seg_count_kernel<<<ntiles, 256, 0, stream>>>(sk_out, n32, tile_count);
-  seg_scan_kernel<<<1, 1024, 0, stream>>>(tile_count, ntiles, tile_off, seg_start, n32, sk_out, t->v.slots,
-                                          t->dstate);
-  seg_fill_kernel<<<ntiles, 256, 0, stream>>>(sk_out, n32, tile_off, seg_start);
-  MEEPO_CUDA_TRY(cudaGetLastError());
+  {
+    ProfScope ps(t, "apply.radix_sort(cub)", stream);
+    MEEPO_CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, (const uint32_t*)sk_in, sk_out,
+                                                   (const uint32_t*)sv_in, sv_out, (int)n32, 0, end_bit, stream));
+  }
+  {
+    ProfScope ps(t, "apply.segments(3 kernels)", stream);
+    seg_count_kernel<<<ntiles, 256, 0, stream>>>(sk_out, n32, tile_count);
+    seg_scan_kernel<<<1, 1024, 0, stream>>>(tile_count, ntiles, tile_off, seg_start, n32, sk_out, t->v.slots,
+                                            t->dstate);
+    seg_fill_kernel<<<ntiles, 256, 0, stream>>>(sk_out, n32, tile_off, seg_start);
+    MEEPO_CUDA_TRY(cudaGetLastError());
+  }
 
   ApplyArgs a;
   a.grads = reinterpret_cast<const uint4*>(grads);
@@ -466,17 +473,18 @@ meepo_status launch_apply_gradients(meepo_table* t, const uint64_t* keys, const 
   const void* k_leaf = bf16 ? (const void*)leaf_kernel<true> : (const void*)leaf_kernel<false>;
   void* args[] = {&t->v, &a};
   const uint64_t groups_per_block = 256 / gl;
+  if (grads_ready) MEEPO_CUDA_TRY(cudaStreamWaitEvent(stream, grads_ready, 0));
   {
+    ProfScope ps(t, "apply.reduce_optimizer", stream);
     const int grid = grid_for(t, k_apply, 256, 0, (n + groups_per_block - 1) / groups_per_block);
     MEEPO_CUDA_TRY(cudaLaunchKernel(k_apply, dim3(grid), dim3(256), args, 0, stream));
   }
   {
+    ProfScope ps(t, "apply.long_segments(2 kernels)", stream);
     const int grid = grid_for(t, k_leaf, 256, 0, (max_leaves + groups_per_block - 1) / groups_per_block);
     MEEPO_CUDA_TRY(cudaLaunchKernel(k_leaf, dim3(grid), dim3(256), args, 0, stream));
-  }
-  {
-    const int grid = grid_for(t, k_finish, 256, 0, (max_long + groups_per_block - 1) / groups_per_block);
-    MEEPO_CUDA_TRY(cudaLaunchKernel(k_finish, dim3(grid), dim3(256), args, 0, stream));
+    const int grid2 = grid_for(t, k_finish, 256, 0, (max_long + groups_per_block - 1) / groups_per_block);
+    MEEPO_CUDA_TRY(cudaLaunchKernel(k_finish, dim3(grid2), dim3(256), args, 0, stream));
   }
   return MEEPO_OK;
 }

@@ -127,6 +127,19 @@ class Table:
     def __len__(self):
         return self.stats()["size"]
 
+    def profile(self, on: bool):
+        self.lib.check(self.lib.profile_enable(self._h, 1 if on else 0))
+
+    def profile_read(self) -> dict:
+        """{kernel group: (launches, total_ms)} accumulated since profile(True)."""
+        buf = C.create_string_buffer(1 << 14)
+        self.lib.check(self.lib.profile_read(self._h, buf, len(buf)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, cnt, ms = line.rsplit(" ", 2)
+            out[name] = (int(cnt), float(ms))
+        return out
+
     # -- helpers ------------------------------------------------------------
     def _np_row_dtype(self):
         return np.float32 if self.dtype == capi.F32 else np.uint16  # bf16 carried as raw bits
