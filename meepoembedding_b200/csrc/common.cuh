@@ -172,7 +172,10 @@ __device__ __forceinline__ Probe probe_find_or_insert(const TableView& t, uint64
       }
       free_m &= free_m - 1;
     }
-    if (!overflowed(t, b)) atomicOr(t.overflow + (b >> 5), 1u << (b & 31));
+    if (!overflowed(t, b)) {
+      const uint32_t bit = 1u << (b & 31);
+      if (!(atomicOr(t.overflow + (b >> 5), bit) & bit)) atomicAdd(t.counters + C_OVERFLOW, 1ull);
+    }
     b = (b + 1 == t.num_buckets) ? 0 : b + 1;
   }
   r.status = MEEPO_KEY_FULL;

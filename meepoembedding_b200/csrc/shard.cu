@@ -1,0 +1,336 @@
+// shard.cu — device helpers of the key-hash-sharded table (include/meepo.h "sharding helpers",
+// SURVEY K11 + the dedup-before-exchange rule of section 5):
+//   meepo_shard_partition    stable counting sort of a batch by owner(key, G)
+//   meepo_reduce_duplicates  batch-level dedup (CAS into an L2-resident scratch table) and, for the
+//                            backward path, the fixed-shape pre-reduction of duplicate gradients
+//   meepo_gather_rows        rows_out[i] = rows_in[index[i]], 16-byte vectorised (un-permute/expand)
+#include "table.h"
+
+namespace meepo {
+
+constexpr int kPartTile = 2048;  // keys per CTA in the partition passes
+constexpr int kMaxShards = 32;
+constexpr int kScanTile = 1024;  // elements per CTA in the occupancy passes
+
+// ---------------------------------------------------------------------------------------------
+// single-CTA exclusive scan (n is small: tiles x shards). out[n] = total.
+__global__ void __launch_bounds__(1024) excl_scan_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
+                                                         uint32_t n, unsigned long long* total64) {
+  __shared__ uint32_t warp_sum[32];
+  __shared__ uint32_t carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (uint32_t base = 0; base < n; base += 1024) {
+    const uint32_t i = base + threadIdx.x;
+    const uint32_t v = i < n ? in[i] : 0;
+    uint32_t x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+      if (lane >= d) x += y;
+    }
+    if (lane == 31) warp_sum[w] = x;
+    __syncthreads();
+    if (w == 0) {
+      uint32_t s = warp_sum[lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        uint32_t y = __shfl_up_sync(0xFFFFFFFFu, s, d);
+        if (lane >= d) s += y;
+      }
+      warp_sum[lane] = s;
+    }
+    __syncthreads();
+    const uint32_t carry = carry_s;
+    const uint32_t incl = x + (w ? warp_sum[w - 1] : 0);
+    if (i < n) out[i] = carry + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = carry + incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    out[n] = carry_s;
+    if (total64) *total64 = carry_s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// partition by owner
+__global__ void __launch_bounds__(256) part_hist_kernel(const uint64_t* __restrict__ keys, uint32_t n, uint32_t G,
+                                                        uint32_t ntiles, uint32_t* __restrict__ tile_hist) {
+  __shared__ uint32_t hist[kMaxShards];
+  if (threadIdx.x < kMaxShards) hist[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t base = blockIdx.x * kPartTile;
+#pragma unroll
+  for (int k = 0; k < kPartTile / 256; k++) {
+    const uint32_t i = base + k * 256 + threadIdx.x;
+    const bool ok = i < n;
+    const uint32_t g = ok ? owner_of(__ldg(keys + i), G) : G;  // tail lanes form their own group
+    const unsigned peers = __match_any_sync(0xFFFFFFFFu, g);
+    if (ok && (threadIdx.x & 31) == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&hist[g], (uint32_t)__popc(peers));
+  }
+  __syncthreads();
+  if (threadIdx.x < G) tile_hist[threadIdx.x * ntiles + blockIdx.x] = hist[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(256) part_scatter_kernel(const uint64_t* __restrict__ keys, uint32_t n, uint32_t G,
+                                                           uint32_t ntiles, const uint32_t* __restrict__ tile_off,
+                                                           uint64_t* __restrict__ counts_out,
+                                                           uint32_t* __restrict__ perm_out,
+                                                           uint64_t* __restrict__ keys_sorted_out) {
+  __shared__ uint32_t base_s[kMaxShards];
+  __shared__ uint32_t warp_cnt[8][kMaxShards];
+  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (threadIdx.x < G) base_s[threadIdx.x] = tile_off[threadIdx.x * ntiles + blockIdx.x];
+  if (blockIdx.x == 0 && threadIdx.x < G)
+    counts_out[threadIdx.x] = (uint64_t)(tile_off[(threadIdx.x + 1) * ntiles] - tile_off[threadIdx.x * ntiles]);
+  const uint32_t base = blockIdx.x * kPartTile;
+#pragma unroll 1
+  for (int k = 0; k < kPartTile / 256; k++) {
+    for (uint32_t x = threadIdx.x; x < 8 * kMaxShards; x += 256) (&warp_cnt[0][0])[x] = 0;
+    __syncthreads();
+    const uint32_t i = base + k * 256 + threadIdx.x;
+    const bool ok = i < n;
+    const uint64_t key = ok ? __ldg(keys + i) : 0;
+    const uint32_t g = ok ? owner_of(key, G) : G;
+    const unsigned peers = __match_any_sync(0xFFFFFFFFu, g);
+    const uint32_t rank_in_warp = __popc(peers & ((1u << lane) - 1u));
+    if (ok && rank_in_warp == 0) warp_cnt[w][g] = __popc(peers);
+    __syncthreads();
+    if (ok) {
+      uint32_t before = 0;
+      for (uint32_t j = 0; j < w; j++) before += warp_cnt[j][g];
+      const uint32_t pos = base_s[g] + before + rank_in_warp;
+      if (perm_out) perm_out[pos] = i;
+      if (keys_sorted_out) keys_sorted_out[pos] = key;
+    }
+    __syncthreads();
+    if (threadIdx.x < G) {
+      uint32_t tot = 0;
+      for (int j = 0; j < 8; j++) tot += warp_cnt[j][threadIdx.x];
+      base_s[threadIdx.x] += tot;
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// batch-level dedup
+__global__ void __launch_bounds__(256) dedup_insert_kernel(const uint64_t* __restrict__ keys, uint32_t n,
+                                                           uint64_t* __restrict__ scratch, uint32_t mask,
+                                                           uint32_t* __restrict__ pos) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint64_t key = __ldg(keys + i);
+    uint32_t p = kNil;
+    if (key_valid(key)) {
+      uint32_t h = (uint32_t)(mix64(key ^ 0x5851F42D4C957F2Dull) >> 32) & mask;
+      while (true) {
+        const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(scratch + h),
+                                                 (unsigned long long)MEEPO_KEY_EMPTY, (unsigned long long)key);
+        if (old == MEEPO_KEY_EMPTY || old == key) {
+          p = h;
+          break;
+        }
+        h = (h + 1) & mask;
+      }
+    }
+    pos[i] = p;
+  }
+}
+
+__global__ void __launch_bounds__(256) occ_count_kernel(const uint64_t* __restrict__ scratch, uint32_t m,
+                                                        uint32_t* __restrict__ tile_count) {
+  const uint32_t base = blockIdx.x * kScanTile;
+  int total = 0;
+#pragma unroll
+  for (int k = 0; k < kScanTile / 256; k++) {
+    const uint32_t p = base + k * 256 + threadIdx.x;
+    total += __syncthreads_count(p < m && scratch[p] != MEEPO_KEY_EMPTY);
+  }
+  if (threadIdx.x == 0) tile_count[blockIdx.x] = (uint32_t)total;
+}
+
+__global__ void __launch_bounds__(256) occ_fill_kernel(const uint64_t* __restrict__ scratch, uint32_t m,
+                                                       const uint32_t* __restrict__ tile_off,
+                                                       uint32_t* __restrict__ uid_of_slot,
+                                                       uint64_t* __restrict__ unique_out) {
+  __shared__ uint32_t warp_cnt[8];
+  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint32_t running = tile_off[blockIdx.x];
+  const uint32_t base = blockIdx.x * kScanTile;
+#pragma unroll 1
+  for (int k = 0; k < kScanTile / 256; k++) {
+    const uint32_t p = base + k * 256 + threadIdx.x;
+    const uint64_t key = p < m ? scratch[p] : MEEPO_KEY_EMPTY;
+    const bool occ = key != MEEPO_KEY_EMPTY;
+    const unsigned msk = __ballot_sync(0xFFFFFFFFu, occ);
+    if (lane == 0) warp_cnt[w] = __popc(msk);
+    __syncthreads();
+    uint32_t before = 0, total = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const uint32_t c = warp_cnt[j];
+      before += j < (int)w ? c : 0;
+      total += c;
+    }
+    if (occ) {
+      const uint32_t u = running + before + __popc(msk & ((1u << lane) - 1u));
+      uid_of_slot[p] = u;
+      unique_out[u] = key;
+    }
+    running += total;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) dedup_inverse_kernel(const uint32_t* __restrict__ pos, uint32_t n,
+                                                            const uint32_t* __restrict__ uid_of_slot,
+                                                            uint32_t* __restrict__ inverse_out,
+                                                            uint32_t* __restrict__ sort_key,
+                                                            uint32_t* __restrict__ sort_val) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t p = pos[i];
+    const uint32_t u = p == kNil ? kNil : uid_of_slot[p];
+    if (inverse_out) inverse_out[i] = u;
+    if (sort_key) {
+      sort_key[i] = u == kNil ? n : u;  // invalid keys sort last and are skipped
+      sort_val[i] = i;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// dense row gather: one warp moves 32 rows as a flat array of 16-byte chunks
+__global__ void __launch_bounds__(256) gather_rows_kernel(const uint4* __restrict__ in,
+                                                          const uint32_t* __restrict__ index, uint32_t n,
+                                                          uint32_t cpr, uint4* __restrict__ out) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t ntiles = (n + 31u) >> 5;
+  for (uint32_t tile = warp; tile < ntiles; tile += nwarps) {
+    const uint32_t i = tile * 32u + lane;
+    const uint32_t src = i < n ? __ldg(index + i) : kNil;
+    const uint32_t tile_rows = min(32u, n - tile * 32u);
+    const uint32_t chunks = tile_rows * cpr;
+    uint4* out_tile = out + (size_t)tile * 32u * cpr;
+    for (uint32_t c0 = 0; c0 < chunks; c0 += 128) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const uint32_t c = c0 + u * 32 + lane;
+        const uint32_t j = min(c / cpr, 31u);
+        const uint32_t s = __shfl_sync(0xFFFFFFFFu, src, j);
+        v[u] = make_uint4(0, 0, 0, 0);
+        if (c < chunks && s != kNil) v[u] = ld_nc(in + (size_t)s * cpr + (c - j * cpr));
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const uint32_t c = c0 + u * 32 + lane;
+        if (c < chunks) st_stream(out_tile + c, v[u]);
+      }
+    }
+  }
+}
+
+}  // namespace meepo
+
+using namespace meepo;
+
+extern "C" {
+
+MEEPO_API meepo_status meepo_shard_partition(meepo_table* t, const uint64_t* keys, uint64_t n,
+                                             uint32_t num_shards, uint64_t* counts_out, uint32_t* perm_out,
+                                             uint64_t* keys_sorted_out, void* stream_) {
+  if (!t || !counts_out) return fail(MEEPO_EINVAL, "null argument");
+  if (num_shards == 0 || num_shards > (uint32_t)kMaxShards) return fail(MEEPO_EINVAL, "num_shards must be 1..32");
+  if (n > 0xFFFFFFFFull) return fail(MEEPO_EINVAL, "batch too large (n must fit in 32 bits)");
+  if (n && !keys) return fail(MEEPO_EINVAL, "null buffer");
+  DeviceGuard guard(t->device);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (n == 0) {
+    MEEPO_CUDA_TRY(cudaMemsetAsync(counts_out, 0, 8 * num_shards, stream));
+    return MEEPO_OK;
+  }
+  const uint32_t ntiles = (uint32_t)((n + kPartTile - 1) / kPartTile);
+  const size_t cells = (size_t)ntiles * num_shards;
+  MEEPO_TRY(t->ws.reserve(2 * Workspace::pad((cells + 1) * 4) + 1024, stream));
+  uint32_t* hist = t->ws.take<uint32_t>(cells + 1);
+  uint32_t* off = t->ws.take<uint32_t>(cells + 1);
+  ProfScope ps(t, "shard.partition(3 kernels)", stream);
+  part_hist_kernel<<<ntiles, 256, 0, stream>>>(keys, (uint32_t)n, num_shards, ntiles, hist);
+  excl_scan_kernel<<<1, 1024, 0, stream>>>(hist, off, (uint32_t)cells, nullptr);
+  part_scatter_kernel<<<ntiles, 256, 0, stream>>>(keys, (uint32_t)n, num_shards, ntiles, off, counts_out, perm_out,
+                                                  keys_sorted_out);
+  MEEPO_CUDA_TRY(cudaGetLastError());
+  return MEEPO_OK;
+}
+
+MEEPO_API meepo_status meepo_reduce_duplicates(meepo_table* t, const uint64_t* keys, const void* grads, uint64_t n,
+                                               uint64_t* unique_keys_out, void* grads_out, uint32_t* inverse_out,
+                                               uint64_t* n_unique_out, void* stream_) {
+  if (!t || !n_unique_out) return fail(MEEPO_EINVAL, "null argument");
+  if (n > 0x7FFFFFFFull) return fail(MEEPO_EINVAL, "batch too large");
+  if (n && (!keys || !unique_keys_out)) return fail(MEEPO_EINVAL, "null buffer");
+  if ((grads == nullptr) != (grads_out == nullptr)) return fail(MEEPO_EINVAL, "grads and grads_out go together");
+  DeviceGuard guard(t->device);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (n == 0) {
+    MEEPO_CUDA_TRY(cudaMemsetAsync(n_unique_out, 0, 8, stream));
+    return MEEPO_OK;
+  }
+  uint32_t m = 1024;
+  while (m < 2 * n) m <<= 1;
+  const uint32_t ntiles = m / kScanTile;
+  const int end_bit = bits_for((uint32_t)n);
+  size_t need = Workspace::pad((size_t)m * 8) + Workspace::pad(n * 4) + Workspace::pad((size_t)m * 4) +
+                2 * Workspace::pad((ntiles + 1) * 4) + 4096;
+  if (grads) need += SegWork::bytes(n, t->v.dim, end_bit);
+  MEEPO_TRY(t->ws.reserve(need, stream));
+  uint64_t* scratch = t->ws.take<uint64_t>(m);
+  uint32_t* pos = t->ws.take<uint32_t>(n);
+  uint32_t* uid_of_slot = t->ws.take<uint32_t>(m);
+  uint32_t* tile_count = t->ws.take<uint32_t>(ntiles + 1);
+  uint32_t* tile_off = t->ws.take<uint32_t>(ntiles + 1);
+  SegWork w;
+  if (grads) w.take(t->ws, n, t->v.dim, end_bit);
+  {
+    ProfScope ps(t, "dedup.hash(5 kernels)", stream);
+    MEEPO_CUDA_TRY(cudaMemsetAsync(scratch, 0xFF, (size_t)m * 8, stream));
+    const int grid = grid_for(t, (const void*)dedup_insert_kernel, 256, 0, (n + 255) / 256);
+    dedup_insert_kernel<<<grid, 256, 0, stream>>>(keys, (uint32_t)n, scratch, m - 1, pos);
+    occ_count_kernel<<<ntiles, 256, 0, stream>>>(scratch, m, tile_count);
+    excl_scan_kernel<<<1, 1024, 0, stream>>>(tile_count, tile_off, ntiles, (unsigned long long*)n_unique_out);
+    occ_fill_kernel<<<ntiles, 256, 0, stream>>>(scratch, m, tile_off, uid_of_slot, unique_keys_out);
+    dedup_inverse_kernel<<<grid, 256, 0, stream>>>(pos, (uint32_t)n, uid_of_slot, inverse_out,
+                                                   grads ? w.sk_in : nullptr, grads ? w.sv_in : nullptr);
+    MEEPO_CUDA_TRY(cudaGetLastError());
+  }
+  if (grads) {
+    static const char* const names[4] = {"dedup.radix_sort(cub)", "dedup.segments(3 kernels)", "dedup.reduce_store",
+                                         "dedup.long_segments(2 kernels)"};
+    MEEPO_TRY(run_segmented(t, w, (uint32_t)n, grads, kReduceStoreOnly, grads_out, stream, nullptr, names));
+  }
+  return MEEPO_OK;
+}
+
+MEEPO_API meepo_status meepo_gather_rows(meepo_table* t, const void* rows_in, const uint32_t* index, uint64_t n,
+                                         void* rows_out, void* stream_) {
+  if (!t) return fail(MEEPO_EINVAL, "null table");
+  if (n > 0xFFFFFFFFull) return fail(MEEPO_EINVAL, "batch too large (n must fit in 32 bits)");
+  if (n && (!rows_in || !index || !rows_out)) return fail(MEEPO_EINVAL, "null buffer");
+  if (n == 0) return MEEPO_OK;
+  DeviceGuard guard(t->device);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  ProfScope ps(t, "shard.gather_rows", stream);
+  const uint64_t tiles = (n + 31) / 32;
+  const int grid = grid_for(t, (const void*)gather_rows_kernel, 256, 0, (tiles + 7) / 8);
+  gather_rows_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint4*>(rows_in), index, (uint32_t)n, t->v.cpr,
+                                               reinterpret_cast<uint4*>(rows_out));
+  MEEPO_CUDA_TRY(cudaGetLastError());
+  return MEEPO_OK;
+}
+
+}  // extern "C"

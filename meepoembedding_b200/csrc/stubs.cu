@@ -10,7 +10,4 @@ MEEPO_API meepo_status meepo_export_buffers(meepo_table*, uint64_t*, void*, void
 MEEPO_API meepo_status meepo_import_buffers(meepo_table*, const uint64_t*, const void*, const void*, const uint64_t*, const uint32_t*, uint64_t, uint8_t*) { NOT_YET("meepo_import_buffers"); }
 MEEPO_API meepo_status meepo_export(meepo_table*, const char*) { NOT_YET("meepo_export"); }
 MEEPO_API meepo_status meepo_import(meepo_table*, const char*) { NOT_YET("meepo_import"); }
-MEEPO_API meepo_status meepo_shard_partition(meepo_table*, const uint64_t*, uint64_t, uint32_t, uint64_t*, uint32_t*, uint64_t*, void*) { NOT_YET("meepo_shard_partition"); }
-MEEPO_API meepo_status meepo_reduce_duplicates(meepo_table*, const uint64_t*, const void*, uint64_t, uint64_t*, void*, uint32_t*, uint64_t*, void*) { NOT_YET("meepo_reduce_duplicates"); }
-MEEPO_API meepo_status meepo_gather_rows(meepo_table*, const void*, const uint32_t*, uint64_t, void*, void*) { NOT_YET("meepo_gather_rows"); }
 }

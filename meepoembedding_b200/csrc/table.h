@@ -121,6 +121,23 @@ meepo_status probe_gather_end(meepo_table* t, uint64_t n_total, bool insert, cud
 // the gradients with the probe / sort / segment passes that only need the keys.
 meepo_status launch_apply_gradients(meepo_table* t, const uint64_t* keys, const void* grads, uint64_t n,
                                     cudaStream_t stream, cudaEvent_t grads_ready = nullptr);
+// Scratch of one sort + segment + reduce pipeline (update.cu); carved out of the table workspace.
+struct SegWork {
+  uint32_t *sk_in, *sk_out, *sv_in, *sv_out, *tile_count, *tile_off, *seg_start;
+  char *cub_tmp, *long_seg;
+  uint2* leaf_desc;
+  float* partial;
+  size_t cub_bytes, max_long, max_leaves;
+  uint32_t n, ntiles;
+  int end_bit;
+  static size_t bytes(uint64_t n, uint32_t dim, int end_bit);
+  void take(Workspace& ws, uint64_t n, uint32_t dim, int end_bit);
+};
+constexpr int kReduceStoreOnly = 3;
+int bits_for(uint32_t max_value);
+meepo_status run_segmented(meepo_table* t, SegWork& w, uint32_t limit, const void* grads, int mode,
+                           void* reduce_out, cudaStream_t stream, cudaEvent_t grads_ready,
+                           const char* const* names);
 int grid_for(const meepo_table* t, const void* kernel, int block, size_t smem, uint64_t blocks_needed);
 void destroy_host_pipe(meepo_table* t);
 void destroy_profiler(meepo_table* t);

@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(1024) seg_scan_kernel(const uint32_t* __restri
                                                         uint32_t ntiles, uint32_t* __restrict__ tile_off,
                                                         uint32_t* __restrict__ seg_start, uint32_t n,
                                                         const uint32_t* __restrict__ sk, uint32_t miss_key,
-                                                        DeviceState* ds) {
+                                                        DeviceState* ds, int count_updates) {
   __shared__ uint32_t warp_sum[32];
   __shared__ uint32_t carry_s;
   if (threadIdx.x == 0) carry_s = 0;
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(1024) seg_scan_kernel(const uint32_t* __restri
     ds->num_long = 0;
     ds->num_leaves = 0;
     const uint32_t applied = U - (n && sk[n - 1] == miss_key ? 1u : 0u);
-    if (applied) atomicAdd(ds->counters + C_UPDATES, (unsigned long long)applied);
+    if (applied && count_updates) atomicAdd(ds->counters + C_UPDATES, (unsigned long long)applied);
   }
 }
 
@@ -189,12 +189,30 @@ __device__ __forceinline__ void reduce_positions(const uint4* __restrict__ grads
   }
 }
 
+constexpr int kStoreOnly = 3;  // "optimizer" of meepo_reduce_duplicates: round + store the sum
+
+template <bool BF16>
+__device__ __forceinline__ uint4 narrow(const float (&w)[Chunk<BF16>::E]) {
+  if constexpr (BF16) {
+    return make_uint4(pack_bf16x2(w[0], w[1]), pack_bf16x2(w[2], w[3]), pack_bf16x2(w[4], w[5]),
+                      pack_bf16x2(w[6], w[7]));
+  } else {
+    return make_uint4(__float_as_uint(w[0]), __float_as_uint(w[1]), __float_as_uint(w[2]),
+                      __float_as_uint(w[3]));
+  }
+}
+
 // One optimizer step on chunk q of the row in `slot` (meepo.h "Update"; every op rounded once).
 template <bool BF16, int OPT>
 __device__ __forceinline__ void optimizer_chunk(const TableView& t, uint32_t slot, uint32_t q,
-                                                const float (&g)[Chunk<BF16>::E], float alpha) {
+                                                const float (&g)[Chunk<BF16>::E], float alpha,
+                                                uint4* reduce_out) {
   constexpr int E = Chunk<BF16>::E;
   constexpr int SQ = E / 4;  // state uint4s per chunk
+  if constexpr (OPT == kStoreOnly) {
+    st_stream(reduce_out + (size_t)slot * t.cpr + q, narrow<BF16>(g));
+    return;
+  }
   uint4* rowp = t.rows + (size_t)slot * t.cpr + q;
   float w[E];
   widen<BF16>(ld_stream(rowp), w);
@@ -250,15 +268,7 @@ __device__ __forceinline__ void optimizer_chunk(const TableView& t, uint32_t slo
                                    __float_as_uint(v[4 * k + 2]), __float_as_uint(v[4 * k + 3])));
     }
   }
-  uint4 outv;
-  if constexpr (BF16) {
-    outv = make_uint4(pack_bf16x2(w[0], w[1]), pack_bf16x2(w[2], w[3]), pack_bf16x2(w[4], w[5]),
-                      pack_bf16x2(w[6], w[7]));
-  } else {
-    outv = make_uint4(__float_as_uint(w[0]), __float_as_uint(w[1]), __float_as_uint(w[2]),
-                      __float_as_uint(w[3]));
-  }
-  st_stream(rowp, outv);
+  st_stream(rowp, narrow<BF16>(w));
 }
 
 // Adam: per-row step count -> scalar step size (double math, rounded once). Every lane of the
@@ -284,6 +294,8 @@ struct ApplyArgs {
   uint2* leaf_desc;
   float* partial;  // [leaves][dim]
   uint32_t group_lanes;  // power of two <= min(cpr, 32)
+  uint32_t limit;        // sort keys >= limit form the "absent key" segment and are skipped
+  uint4* reduce_out;     // kStoreOnly: [unique][cpr]
 };
 
 // A4: one group of lanes per segment (unique key)
@@ -301,7 +313,7 @@ __global__ void __launch_bounds__(256) apply_kernel(TableView t, ApplyArgs a) {
   for (uint32_t u = group; u < U; u += ngroups) {
     const uint32_t s0 = a.seg_start[u], s1 = a.seg_start[u + 1];
     const uint32_t slot = a.sorted_slot[s0];
-    if (slot >= t.slots) continue;  // the segment of absent / invalid keys
+    if (slot >= a.limit) continue;  // the segment of absent / invalid keys
     const uint32_t cnt = s1 - s0;
     if (cnt > kLeaf) {  // hand over to the leaf kernels
       const uint32_t nleaf = (cnt + kLeaf - 1) / kLeaf;
@@ -319,7 +331,7 @@ __global__ void __launch_bounds__(256) apply_kernel(TableView t, ApplyArgs a) {
     for (uint32_t q = gl; q < t.cpr; q += GL) {
       float acc[E];
       reduce_positions<BF16>(a.grads, a.sorted_idx, s0, s1, t.cpr, q, acc);
-      optimizer_chunk<BF16, OPT>(t, slot, q, acc, alpha);
+      optimizer_chunk<BF16, OPT>(t, slot, q, acc, alpha, a.reduce_out);
     }
   }
 }
@@ -380,7 +392,7 @@ __global__ void __launch_bounds__(256) long_finish_kernel(TableView t, ApplyArgs
           acc[4 * k + 3] = __fadd_rn(acc[4 * k + 3], x.w);
         }
       }
-      optimizer_chunk<BF16, OPT>(t, slot, q, acc, alpha);
+      optimizer_chunk<BF16, OPT>(t, slot, q, acc, alpha, a.reduce_out);
     }
   }
 }
@@ -396,70 +408,88 @@ static void pick_apply(int opt, const void*& apply, const void*& finish) {
       apply = (const void*)apply_kernel<BF16, MEEPO_ADAGRAD>;
       finish = (const void*)long_finish_kernel<BF16, MEEPO_ADAGRAD>;
       break;
-    default:
+    case MEEPO_ADAM:
       apply = (const void*)apply_kernel<BF16, MEEPO_ADAM>;
       finish = (const void*)long_finish_kernel<BF16, MEEPO_ADAM>;
+      break;
+    default:
+      apply = (const void*)apply_kernel<BF16, kStoreOnly>;
+      finish = (const void*)long_finish_kernel<BF16, kStoreOnly>;
   }
 }
 
-meepo_status launch_apply_gradients(meepo_table* t, const uint64_t* keys, const void* grads, uint64_t n,
-                                    cudaStream_t stream, cudaEvent_t grads_ready) {
-  if (n == 0) return MEEPO_OK;
-  const uint32_t n32 = (uint32_t)n;
-  const uint32_t ntiles = (n32 + kSegTile - 1) / kSegTile;
-  const size_t max_long = n / (kLeaf + 1) + 1;
-  const size_t max_leaves = n / 128 + 2;
-  int end_bit = 1;
-  while (end_bit < 32 && (t->v.slots >> end_bit)) end_bit++;
+// Scratch of one sort + segment + reduce pipeline over n (sort key, batch index) pairs.
+size_t SegWork::bytes(uint64_t n, uint32_t dim, int end_bit_) {
+  size_t cub = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, cub, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                  (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n, 0, end_bit_);
+  const size_t ntiles_ = (n + kSegTile - 1) / kSegTile;
+  const size_t max_long_ = n / (kLeaf + 1) + 1, max_leaves_ = n / 128 + 2;
+  return 4 * Workspace::pad(n * 4) + Workspace::pad(cub) + 2 * Workspace::pad(ntiles_ * 4) +
+         Workspace::pad((n + 2) * 4) + Workspace::pad(max_long_ * sizeof(LongSeg)) +
+         Workspace::pad(max_leaves_ * 8) + Workspace::pad(max_leaves_ * dim * 4) + 4096;
+}
 
-  size_t cub_bytes = 0;
+void SegWork::take(Workspace& ws, uint64_t n_, uint32_t dim, int end_bit_) {
+  n = (uint32_t)n_;
+  end_bit = end_bit_;
+  cub_bytes = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
-                                  (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n32, 0, end_bit, stream);
-  size_t need = 4 * Workspace::pad(n * 4) + Workspace::pad(cub_bytes) + 2 * Workspace::pad(ntiles * 4) +
-                Workspace::pad((n + 2) * 4) + Workspace::pad(max_long * sizeof(LongSeg)) +
-                Workspace::pad(max_leaves * 8) + Workspace::pad(max_leaves * t->v.dim * 4) + 4096;
-  MEEPO_TRY(t->ws.reserve(need, stream));
-  uint32_t* sk_in = t->ws.take<uint32_t>(n);
-  uint32_t* sk_out = t->ws.take<uint32_t>(n);
-  uint32_t* sv_in = t->ws.take<uint32_t>(n);
-  uint32_t* sv_out = t->ws.take<uint32_t>(n);
-  char* cub_tmp = t->ws.take<char>(cub_bytes);
-  uint32_t* tile_count = t->ws.take<uint32_t>(ntiles);
-  uint32_t* tile_off = t->ws.take<uint32_t>(ntiles);
-  uint32_t* seg_start = t->ws.take<uint32_t>(n + 2);
-  LongSeg* long_seg = t->ws.take<LongSeg>(max_long);
-  uint2* leaf_desc = t->ws.take<uint2>(max_leaves);
-  float* partial = t->ws.take<float>(max_leaves * t->v.dim);
+                                  (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n, 0, end_bit);
+  ntiles = (n + kSegTile - 1) / kSegTile;
+  max_long = n_ / (kLeaf + 1) + 1;
+  max_leaves = n_ / 128 + 2;
+  sk_in = ws.take<uint32_t>(n_);
+  sk_out = ws.take<uint32_t>(n_);
+  sv_in = ws.take<uint32_t>(n_);
+  sv_out = ws.take<uint32_t>(n_);
+  cub_tmp = ws.take<char>(cub_bytes);
+  tile_count = ws.take<uint32_t>(ntiles);
+  tile_off = ws.take<uint32_t>(ntiles);
+  seg_start = ws.take<uint32_t>(n_ + 2);
+  long_seg = ws.take<char>(max_long * sizeof(LongSeg));
+  leaf_desc = ws.take<uint2>(max_leaves);
+  partial = ws.take<float>(max_leaves * dim);
+}
 
+int bits_for(uint32_t max_value) {
+  int b = 1;
+  while (b < 32 && (max_value >> b)) b++;
+  return b;
+}
+
+// sort (sk_in, sv_in) by key, find the segments, reduce each segment's gradient rows in the
+// normative order and hand the sum to the optimizer `mode` (MEEPO_SGD/ADAGRAD/ADAM) or store it
+// (kStoreOnly -> reduce_out[sort key]).
+meepo_status run_segmented(meepo_table* t, SegWork& w, uint32_t limit, const void* grads, int mode,
+                           void* reduce_out, cudaStream_t stream, cudaEvent_t grads_ready,
+                           const char* const* names) {
+  const uint32_t n32 = w.n;
   {
-    ProfScope ps(t, "apply.grad_slots", stream);
-    const int grid = grid_for(t, (const void*)grad_slots_kernel, 256, 0, (n + 255) / 256);
-    grad_slots_kernel<<<grid, 256, 0, stream>>>(t->v, keys, n32, sk_in, sv_in);
+    ProfScope ps(t, names[0], stream);
+    MEEPO_CUDA_TRY(cub::DeviceRadixSort::SortPairs(w.cub_tmp, w.cub_bytes, (const uint32_t*)w.sk_in, w.sk_out,
+                                                   (const uint32_t*)w.sv_in, w.sv_out, (int)n32, 0, w.end_bit,
+                                                   stream));
+  }
+  {
+    ProfScope ps(t, names[1], stream);
+    seg_count_kernel<<<w.ntiles, 256, 0, stream>>>(w.sk_out, n32, w.tile_count);
+    seg_scan_kernel<<<1, 1024, 0, stream>>>(w.tile_count, w.ntiles, w.tile_off, w.seg_start, n32, w.sk_out, limit,
+                                            t->dstate, mode != kStoreOnly);
+    seg_fill_kernel<<<w.ntiles, 256, 0, stream>>>(w.sk_out, n32, w.tile_off, w.seg_start);
     MEEPO_CUDA_TRY(cudaGetLastError());
   }
-  {
-    ProfScope ps(t, "apply.radix_sort(cub)", stream);
-    MEEPO_CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, (const uint32_t*)sk_in, sk_out,
-                                                   (const uint32_t*)sv_in, sv_out, (int)n32, 0, end_bit, stream));
-  }
-  {
-    ProfScope ps(t, "apply.segments(3 kernels)", stream);
-    seg_count_kernel<<<ntiles, 256, 0, stream>>>(sk_out, n32, tile_count);
-    seg_scan_kernel<<<1, 1024, 0, stream>>>(tile_count, ntiles, tile_off, seg_start, n32, sk_out, t->v.slots,
-                                            t->dstate);
-    seg_fill_kernel<<<ntiles, 256, 0, stream>>>(sk_out, n32, tile_off, seg_start);
-    MEEPO_CUDA_TRY(cudaGetLastError());
-  }
-
   ApplyArgs a;
   a.grads = reinterpret_cast<const uint4*>(grads);
-  a.sorted_slot = sk_out;
-  a.sorted_idx = sv_out;
-  a.seg_start = seg_start;
+  a.sorted_slot = w.sk_out;
+  a.sorted_idx = w.sv_out;
+  a.seg_start = w.seg_start;
   a.ds = t->dstate;
-  a.long_seg = long_seg;
-  a.leaf_desc = leaf_desc;
-  a.partial = partial;
+  a.long_seg = reinterpret_cast<LongSeg*>(w.long_seg);
+  a.leaf_desc = w.leaf_desc;
+  a.partial = w.partial;
+  a.limit = limit;
+  a.reduce_out = reinterpret_cast<uint4*>(reduce_out);
   uint32_t gl = 1;
   while (gl * 2 <= t->v.cpr && gl < 32) gl *= 2;
   a.group_lanes = gl;
@@ -467,26 +497,44 @@ meepo_status launch_apply_gradients(meepo_table* t, const uint64_t* keys, const 
   const bool bf16 = t->v.dtype == MEEPO_BF16;
   const void *k_apply = nullptr, *k_finish = nullptr;
   if (bf16)
-    pick_apply<true>(t->v.opt, k_apply, k_finish);
+    pick_apply<true>(mode, k_apply, k_finish);
   else
-    pick_apply<false>(t->v.opt, k_apply, k_finish);
+    pick_apply<false>(mode, k_apply, k_finish);
   const void* k_leaf = bf16 ? (const void*)leaf_kernel<true> : (const void*)leaf_kernel<false>;
   void* args[] = {&t->v, &a};
   const uint64_t groups_per_block = 256 / gl;
   if (grads_ready) MEEPO_CUDA_TRY(cudaStreamWaitEvent(stream, grads_ready, 0));
   {
-    ProfScope ps(t, "apply.reduce_optimizer", stream);
-    const int grid = grid_for(t, k_apply, 256, 0, (n + groups_per_block - 1) / groups_per_block);
+    ProfScope ps(t, names[2], stream);
+    const int grid = grid_for(t, k_apply, 256, 0, (n32 + groups_per_block - 1) / groups_per_block);
     MEEPO_CUDA_TRY(cudaLaunchKernel(k_apply, dim3(grid), dim3(256), args, 0, stream));
   }
   {
-    ProfScope ps(t, "apply.long_segments(2 kernels)", stream);
-    const int grid = grid_for(t, k_leaf, 256, 0, (max_leaves + groups_per_block - 1) / groups_per_block);
+    ProfScope ps(t, names[3], stream);
+    const int grid = grid_for(t, k_leaf, 256, 0, (w.max_leaves + groups_per_block - 1) / groups_per_block);
     MEEPO_CUDA_TRY(cudaLaunchKernel(k_leaf, dim3(grid), dim3(256), args, 0, stream));
-    const int grid2 = grid_for(t, k_finish, 256, 0, (max_long + groups_per_block - 1) / groups_per_block);
+    const int grid2 = grid_for(t, k_finish, 256, 0, (w.max_long + groups_per_block - 1) / groups_per_block);
     MEEPO_CUDA_TRY(cudaLaunchKernel(k_finish, dim3(grid2), dim3(256), args, 0, stream));
   }
   return MEEPO_OK;
+}
+
+meepo_status launch_apply_gradients(meepo_table* t, const uint64_t* keys, const void* grads, uint64_t n,
+                                    cudaStream_t stream, cudaEvent_t grads_ready) {
+  if (n == 0) return MEEPO_OK;
+  const int end_bit = bits_for(t->v.slots);
+  MEEPO_TRY(t->ws.reserve(SegWork::bytes(n, t->v.dim, end_bit), stream));
+  SegWork w;
+  w.take(t->ws, n, t->v.dim, end_bit);
+  {
+    ProfScope ps(t, "apply.grad_slots", stream);
+    const int grid = grid_for(t, (const void*)grad_slots_kernel, 256, 0, (n + 255) / 256);
+    grad_slots_kernel<<<grid, 256, 0, stream>>>(t->v, keys, (uint32_t)n, w.sk_in, w.sv_in);
+    MEEPO_CUDA_TRY(cudaGetLastError());
+  }
+  static const char* const names[4] = {"apply.radix_sort(cub)", "apply.segments(3 kernels)",
+                                       "apply.reduce_optimizer", "apply.long_segments(2 kernels)"};
+  return run_segmented(t, w, t->v.slots, grads, t->v.opt, nullptr, stream, grads_ready, names);
 }
 
 }  // namespace meepo
