@@ -81,6 +81,42 @@ def gen_batches(w, nb, dist, rank, world):
     return [keygen.batch_keys(rng, w["batch"], universe, w["seed"], dist=dist) for _ in range(nb)]
 
 
+def _lshr(z, k):
+    return (z >> k) & ((1 << (64 - k)) - 1)
+
+
+def torch_keys_from_ranks(ranks, seed):
+    """keygen.keys_from_ranks on the device (int64 tensors carry the uint64 bit patterns)."""
+    def s64(c):
+        return c - (1 << 64) if c >= (1 << 63) else c
+    z = ranks ^ s64(seed)
+    z = z ^ _lshr(z, 30)
+    z = z * s64(0xBF58476D1CE4E5B9)
+    z = z ^ _lshr(z, 27)
+    z = z * s64(0x94D049BB133111EB)
+    z = z ^ _lshr(z, 31)
+    bad = (z == -1) | (z == -2)
+    return torch_where(bad, z ^ s64(0x8000000000000000), z)
+
+
+def torch_owner(keys, g):
+    def s64(c):
+        return c - (1 << 64) if c >= (1 << 63) else c
+    z = keys ^ s64(0xD6E8FEB86659FD93)
+    z = z ^ _lshr(z, 30)
+    z = z * s64(0xBF58476D1CE4E5B9)
+    z = z ^ _lshr(z, 27)
+    z = z * s64(0x94D049BB133111EB)
+    z = z ^ _lshr(z, 31)
+    hi, lo = _lshr(z, 32), z & 0xFFFFFFFF
+    return _lshr(hi * g + _lshr(lo * g, 32), 32)
+
+
+def torch_where(c, a, b):
+    import torch
+    return torch.where(c, a, b)
+
+
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -93,7 +129,7 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "20", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
@@ -255,12 +291,10 @@ def main():
     pre_rows = torch.empty((chunk, w["dim"]), dtype=tdt, device=dev)
     pre_st = torch.empty(chunk, dtype=torch.uint8, device=dev)
     for lo in range(1, total + 1, chunk):
-        r = np.arange(lo, min(lo + chunk, total + 1), dtype=np.uint64)
-        k = keygen.keys_from_ranks(r, w["seed"])
+        kd = torch_keys_from_ranks(torch.arange(lo, min(lo + chunk, total + 1), dtype=torch.int64, device=dev), w["seed"])
         if world > 1:
-            k = k[sharded.owner_np(k) == rank]
-        kd = torch.from_numpy(k.view(np.int64)).to(dev)
-        table.find_or_insert(kd, pre_rows, pre_st, n=k.size, stream=sp)
+            kd = kd[torch_owner(kd, world) == rank].contiguous()
+        table.find_or_insert(kd, pre_rows, pre_st, n=kd.numel(), stream=sp)
     torch.cuda.synchronize()
     del pre_rows, pre_st
     prefill_s = time.perf_counter() - t0

@@ -230,7 +230,7 @@ MEEPO_API meepo_status meepo_export_buffers(meepo_table* t, uint64_t* keys, void
 MEEPO_API meepo_status meepo_import_buffers(meepo_table* t, const uint64_t* keys, const void* rows,
                                             const void* state, const uint64_t* scores,
                                             const uint32_t* steps, uint64_t n, uint8_t* status_out);
-/* File format "MEEPOTB1": 64-byte header {magic[8], u32 version, dim, dtype,
+/* File format "MEEPOTB1": 56-byte header {magic[8], u32 version, dim, dtype,
  * opt, u64 n, row_bytes, state_bytes, epoch} then keys[n], rows[n], state[n],
  * scores[n], steps[n], tuples sorted by key. Both libraries write identical
  * files for identical tables. */

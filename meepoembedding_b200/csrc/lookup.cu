@@ -194,13 +194,18 @@ meepo_status probe_gather_chunk(meepo_table* t, const uint64_t* keys, uint64_t n
   return MEEPO_OK;
 }
 
+meepo_status publish_slots(meepo_table* t, const uint32_t* slots, const uint32_t* cur, uint32_t* next,
+                           uint64_t n_max, cudaStream_t stream) {
+  const int pgrid = (int)std::max<uint64_t>(1, std::min<uint64_t>((n_max + 255) / 256, (uint64_t)t->num_sms * 8));
+  publish_kernel<<<pgrid, 256, 0, stream>>>(t->v, slots, cur, next);
+  MEEPO_CUDA_TRY(cudaGetLastError());
+  return MEEPO_OK;
+}
+
 meepo_status probe_gather_end(meepo_table* t, uint64_t n_total, bool insert, cudaStream_t stream) {
   if (!insert || !n_total) return MEEPO_OK;
   ProfScope ps(t, "find_or_insert.publish", stream);
-  const int pgrid = (int)std::min<uint64_t>((n_total + 255) / 256, (uint64_t)t->num_sms * 8);
-  publish_kernel<<<pgrid, 256, 0, stream>>>(t->v, t->cur_new.slots, t->cur_new.count, t->cur_new_next);
-  MEEPO_CUDA_TRY(cudaGetLastError());
-  return MEEPO_OK;
+  return publish_slots(t, t->cur_new.slots, t->cur_new.count, t->cur_new_next, n_total, stream);
 }
 
 meepo_status launch_probe_gather(meepo_table* t, const uint64_t* keys, uint64_t n, void* rows_out,

@@ -126,11 +126,10 @@ MEEPO_API meepo_status meepo_create(const meepo_config* cfg, meepo_table** out) 
   if (cfg->host_spill_bytes) {
     t->spill_cap_tuples = cfg->host_spill_bytes / t->tuple_bytes();
     if (t->spill_cap_tuples) {
-      if ((e = cudaHostAlloc(&t->spill_ring, t->spill_cap_tuples * t->tuple_bytes(), cudaHostAllocDefault)) !=
+      if ((e = cudaHostAlloc(&t->spill_ring, t->spill_cap_tuples * t->tuple_bytes(), cudaHostAllocMapped | cudaHostAllocPortable)) !=
           cudaSuccess)
         return bail(e, "cudaHostAlloc(spill)");
-      t->spill_ring_key.assign(t->spill_cap_tuples, MEEPO_KEY_EMPTY);
-      t->spill_ring_seq.assign(t->spill_cap_tuples, 0);
+      for (uint64_t i = t->spill_cap_tuples; i-- > 0;) t->spill_free.push_back((uint32_t)i);
     }
   }
   if ((e = cudaDeviceSynchronize()) != cudaSuccess) return bail(e, "cudaDeviceSynchronize");

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <deque>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -51,6 +52,7 @@ struct DeviceState {
   uint32_t evict_count;
   uint32_t pad[2];
   unsigned long long scratch64[8];
+  unsigned long long hist[256];  // evict: radix-select histogram
 };
 
 struct Profiler;
@@ -87,9 +89,8 @@ struct meepo_table {
   uint64_t spill_cap_tuples = 0;
   uint64_t spill_seq = 0;
   std::unordered_map<uint64_t, meepo::SpillTuple> spill_index;  // key -> newest tuple
-  std::vector<uint64_t> spill_ring_key;                         // ring position -> key (EMPTY = free)
-  std::vector<uint64_t> spill_ring_seq;
-  uint64_t spill_head = 0;  // next ring position to write (FIFO)
+  std::deque<std::pair<uint64_t, uint64_t>> spill_fifo;         // (seq, key), oldest first; stale entries skipped
+  std::vector<uint32_t> spill_free;                             // free slab indices
 
   uint64_t tuple_bytes() const { return 24 + (uint64_t)row_bytes + state_bytes; }
 };
@@ -141,6 +142,13 @@ meepo_status run_segmented(meepo_table* t, SegWork& w, uint32_t limit, const voi
 int grid_for(const meepo_table* t, const void* kernel, int block, size_t smem, uint64_t blocks_needed);
 void destroy_host_pipe(meepo_table* t);
 void destroy_profiler(meepo_table* t);
+// lookup.cu: write the tags of the slots listed in `slots[0..*cur)` and fold the count into the size
+meepo_status publish_slots(meepo_table* t, const uint32_t* slots, const uint32_t* cur, uint32_t* next,
+                           uint64_t n_max, cudaStream_t stream);
+// io.cu
+meepo_status live_size(meepo_table* t, uint64_t* out);
+meepo_status import_probe_launch(meepo_table* t, const uint64_t* keys, uint64_t n, uint32_t* slot_out,
+                                 uint8_t* status_out, NewList nl, cudaStream_t stream);
 // Times the kernels launched inside its lifetime when profiling is on (profile.cu).
 struct ProfScope {
   ProfScope(meepo_table* t, const char* name, cudaStream_t s);

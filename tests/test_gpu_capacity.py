@@ -1,0 +1,154 @@
+"""GPU parity of the rows either side of the hot path: export/import, eviction, spill tier, host verbs."""
+import filecmp
+
+import numpy as np
+import pytest
+
+from meepoembedding_b200 import Table, keygen
+from meepoembedding_b200 import _capi as capi
+
+from util import export_sorted, grads_for, make_keys, table_kwargs
+
+pytestmark = pytest.mark.gpu
+
+
+def run_stream(tables, dtype, dim, seed, steps=4, n=3000, universe=5000, gpu_first=True):
+    """Same find_or_insert / lookup / apply_gradients stream on (gpu, oracle)."""
+    from gpu_util import gpu_apply, gpu_foi
+
+    g, o = tables
+    rng = np.random.default_rng(seed)
+    for _ in range(steps):
+        keys = make_keys(rng, n, universe, dup_frac=0.5)
+        gpu_foi(g, keys, dtype), o.find_or_insert(keys)
+        lk = make_keys(rng, n // 2, universe)
+        gpu_foi(g, lk, dtype, insert=False), o.lookup(lk)
+        gr = grads_for(dtype, rng.normal(0, 0.1, size=(n, dim)))
+        gpu_apply(g, keys, gr, dtype), o.apply_gradients(keys, gr)
+
+
+def assert_tables_equal(g, o):
+    from gpu_util import gpu_export
+
+    for name, a, b in zip(("keys", "rows", "state", "scores", "steps"), gpu_export(g), export_sorted(o)):
+        np.testing.assert_array_equal(a, b, err_msg=name)
+
+
+@pytest.mark.parametrize("dtype,optimizer", [("f32", "adagrad"), ("bf16", "adam"), ("f32", "sgd")])
+def test_export_matches_oracle_and_files_are_identical(oracle_lib, cuda_lib, tmp_path, dtype, optimizer):
+    kw = table_kwargs(dim=32, capacity=8192, dtype=dtype, optimizer=optimizer, track_scores=True)
+    g, o = Table(lib=cuda_lib, **kw), Table(lib=oracle_lib, **kw)
+    run_stream((g, o), dtype, 32, 1)
+    assert_tables_equal(g, o)
+    pg, po = str(tmp_path / "g.meepo"), str(tmp_path / "o.meepo")
+    g.export_file(pg), o.export_file(po)
+    assert filecmp.cmp(pg, po, shallow=False), "GPU and oracle wrote different files for identical tables"
+    # cross-load: oracle file -> fresh GPU table, GPU file -> fresh oracle table
+    g2, o2 = Table(lib=cuda_lib, **kw), Table(lib=oracle_lib, **kw)
+    g2.import_file(po), o2.import_file(pg)
+    assert_tables_equal(g2, o)
+    assert_tables_equal(g, o2)
+    assert g2.stats()["size"] == o.stats()["size"]
+    # and the reloaded table keeps training identically
+    run_stream((g2, o), dtype, 32, 2, steps=2)
+    assert_tables_equal(g2, o)
+
+
+def test_import_buffers_statuses(oracle_lib, cuda_lib):
+    import torch
+    from gpu_util import DEV, dkeys, drows
+
+    kw = table_kwargs(dim=8, capacity=64, optimizer="adagrad")
+    g, o = Table(lib=cuda_lib, **kw), Table(lib=oracle_lib, **kw)
+    rng = np.random.default_rng(0)
+    keys = np.arange(1, 101, dtype=np.uint64) * np.uint64(7919)
+    keys[10] = np.uint64(capi.KEY_EMPTY)
+    rows = rng.normal(size=(100, 8)).astype(np.float32)
+    ost = np.empty(100, dtype=np.uint8)
+    o.import_buffers(keys, rows, status_out=ost)
+    gst = torch.empty(100, dtype=torch.uint8, device=DEV)
+    g.import_buffers(dkeys(keys), drows(rows, "f32"), status_out=gst, n=100)
+    gst = gst.cpu().numpy()
+    assert (gst == capi.KEY_INSERTED).sum() == 64 == (ost == capi.KEY_INSERTED).sum()
+    assert (gst == capi.KEY_FULL).sum() == 35 == (ost == capi.KEY_FULL).sum() and gst[10] == capi.KEY_INVALID
+    # overwrite what is there
+    from gpu_util import gpu_export
+    k2 = gpu_export(g)[0]
+    g.import_buffers(dkeys(k2), drows(np.ones((64, 8), np.float32), "f32"), status_out=(s2 := torch.empty(64, dtype=torch.uint8, device=DEV)), n=64)
+    assert (s2.cpu().numpy() == capi.KEY_FOUND).all()
+    ek, er, es, _, _ = gpu_export(g)
+    assert (er == 1.0).all() and np.allclose(es, 0.1) and (ek == k2).all()
+
+
+@pytest.mark.parametrize("policy", ["lfu", "lru"])
+@pytest.mark.parametrize("dtype,optimizer", [("bf16", "adam"), ("f32", "adagrad")])
+def test_evict_spill_readmit_parity(oracle_lib, cuda_lib, policy, dtype, optimizer):
+    from gpu_util import gpu_foi
+
+    dim = 16
+    probe = Table(lib=oracle_lib, **table_kwargs(dim=dim, capacity=64, dtype=dtype, optimizer=optimizer))
+    tuple_bytes = 24 + probe.row_bytes + probe.state_bytes
+    kw = table_kwargs(dim=dim, capacity=8192, dtype=dtype, optimizer=optimizer, track_scores=True,
+                      host_spill_bytes=1500 * tuple_bytes)
+    g, o = Table(lib=cuda_lib, **kw), Table(lib=oracle_lib, **kw)
+    run_stream((g, o), dtype, dim, 5, steps=5, n=2500, universe=6000)
+    assert_tables_equal(g, o)
+    for target in (0.45, 0.2):  # first: victims fit the spill tier; second: more victims than room
+        ng, no = g.evict(policy, target), o.evict(policy, target)
+        assert ng == no and ng > 0
+        assert_tables_equal(g, o)
+        gs, os_ = g.stats(), o.stats()
+        for k in ("size", "evictions", "spill_keys", "spill_bytes"):
+            assert gs[k] == os_[k], k
+        rng = np.random.default_rng(int(target * 100))
+        probe_keys = make_keys(rng, 1500, 6000, dup_frac=0.2)
+        np.testing.assert_array_equal(g.spill_readmit(probe_keys), o.spill_readmit(probe_keys))
+        assert_tables_equal(g, o)
+        assert g.stats()["spill_keys"] == o.stats()["spill_keys"]
+        # the table keeps working after slots were released without tombstones
+        run_stream((g, o), dtype, dim, 6, steps=2, n=2500, universe=6000)
+        assert_tables_equal(g, o)
+    assert g.evict(policy, 1.0) == 0
+
+
+def test_evict_high_load_chains(oracle_lib, cuda_lib):
+    """90% load (BASELINE config 5 regime): long overflow chains, evict, refill, everything still found."""
+    from gpu_util import gpu_foi
+
+    kw = table_kwargs(dim=8, capacity=1 << 14, dtype="bf16", optimizer="sgd", track_scores=True)
+    g, o = Table(lib=cuda_lib, **kw), Table(lib=oracle_lib, **kw)
+    rng = np.random.default_rng(7)
+    for rnd in range(6):
+        while o.stats()["size"] < 0.85 * (1 << 14):  # +<=2000 new keys per batch: never overfills
+            keys = keygen.batch_keys(rng, 2000, 60000, 5, dist="zipf")
+            r, s = gpu_foi(g, keys, "bf16")
+            orr, os_ = o.find_or_insert(keys)
+            np.testing.assert_array_equal(s, os_)
+            np.testing.assert_array_equal(r, orr)
+        assert g.evict("lfu", 0.7) == o.evict("lfu", 0.7)
+        assert_tables_equal(g, o)
+    assert g.stats()["overflow_buckets"] > 0
+
+
+@pytest.mark.parametrize("dtype,dim", [("f32", 128), ("bf16", 64)])
+def test_host_buffer_verbs(oracle_lib, cuda_lib, dtype, dim):
+    """numpy in / numpy out goes through meepo_*_host (chunked, overlapped): same results, and a key
+    that is new in the call reports INSERTED in every chunk."""
+    kw = table_kwargs(dim=dim, capacity=1 << 19, dtype=dtype, optimizer="adagrad")
+    g, o = Table(lib=cuda_lib, **kw), Table(lib=oracle_lib, **kw)
+    rng = np.random.default_rng(3)
+    n = 300_001  # > 2 chunks of 64 MiB at dim=128 fp32
+    for step in range(2):
+        keys = keygen.batch_keys(rng, n, 200_000, 9, dist="zipf")
+        keys[::50_000] = np.uint64(123456789)  # the same new key in every chunk
+        rows, st = g.find_or_insert(keys)
+        orows, ost = o.find_or_insert(keys)
+        np.testing.assert_array_equal(st, ost)
+        np.testing.assert_array_equal(rows, orows)
+        gr = grads_for(dtype, rng.normal(0, 0.1, size=(n, dim)))
+        g.apply_gradients(keys, gr), o.apply_gradients(keys, gr)
+        rows, st = g.lookup(keys)
+        orows, ost = o.lookup(keys)
+        np.testing.assert_array_equal(st, ost)
+        np.testing.assert_array_equal(rows, orows)
+    assert g.stats()["size"] == o.stats()["size"]
