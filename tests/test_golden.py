@@ -1,0 +1,71 @@
+"""Replays tests/golden/*.npz (made by tests/golden/make_golden.py from the dict model) against the
+authored oracle on the CPU and against libmeepo.so on the GPU. Everything is compared as raw bits."""
+import os
+
+import numpy as np
+import pytest
+
+from meepoembedding_b200 import Table
+from meepoembedding_b200 import _capi as capi
+
+from golden.make_golden import CASES, STEPS
+from util import export_sorted, table_kwargs
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def as_bits(rows, dtype):
+    return rows.view(np.uint32) if dtype == "f32" else rows
+
+
+def from_bits(b, dtype):
+    return b.view(np.float32) if dtype == "f32" else b
+
+
+def replay(name, table, foi, lookup, apply, export):
+    c = CASES[name]
+    d = np.load(os.path.join(GOLD, f"stream_{name}.npz"))
+    for s in range(STEPS):
+        rows, st = foi(d[f"keys{s}"])
+        np.testing.assert_array_equal(st, d[f"status{s}"], err_msg=f"status step {s}")
+        np.testing.assert_array_equal(as_bits(rows, c["dtype"]), d[f"rows{s}"], err_msg=f"rows step {s}")
+        apply(d[f"keys{s}"], from_bits(d[f"grads{s}"], c["dtype"]))
+        rows, st = lookup(d[f"lkeys{s}"])
+        np.testing.assert_array_equal(st, d[f"lstatus{s}"], err_msg=f"lookup status step {s}")
+        np.testing.assert_array_equal(as_bits(rows, c["dtype"]), d[f"lrows{s}"], err_msg=f"lookup rows step {s}")
+    assert table.evict("lfu", 0.2) == int(d["evicted"][0])
+    keys, rows, state, scores, steps = export()
+    np.testing.assert_array_equal(keys, d["final_keys"])
+    np.testing.assert_array_equal(as_bits(rows, c["dtype"]), d["final_rows"])
+    if state.size:
+        np.testing.assert_array_equal(state.view(np.uint32), d["final_state"])
+    np.testing.assert_array_equal(scores, (d["final_epoch"].astype(np.uint64) << np.uint64(32)) | d["final_freq"])
+    if c["optimizer"] == "adam":
+        np.testing.assert_array_equal(steps, d["final_step"])
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_oracle_matches_golden(oracle_lib, name):
+    t = Table(lib=oracle_lib, **table_kwargs(track_scores=True, **CASES[name]))
+    replay(name, t, t.find_or_insert, t.lookup, t.apply_gradients, lambda: export_sorted(t))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_cuda_matches_golden(cuda_lib, name):
+    from gpu_util import gpu_apply, gpu_export, gpu_foi
+
+    dtype = CASES[name]["dtype"]
+    t = Table(lib=cuda_lib, **table_kwargs(track_scores=True, **CASES[name]))
+    replay(name, t, lambda k: gpu_foi(t, k, dtype), lambda k: gpu_foi(t, k, dtype, insert=False),
+           lambda k, g: gpu_apply(t, k, g, dtype), lambda: gpu_export(t))
+
+
+def test_spec_spot_values(oracle_lib):
+    d = np.load(os.path.join(GOLD, "spec_spot_values.npz"))
+    t = Table(lib=oracle_lib, **table_kwargs(dim=8, capacity=64, optimizer="sgd"))  # init_seed 0xC0FFEE, scale 0.05
+    rows, st = t.find_or_insert(d["keys"])
+    assert (st == capi.KEY_INSERTED).all()
+    np.testing.assert_array_equal(rows.view(np.uint32), d["init_bits"])
+    for i, k in enumerate(d["keys"]):
+        assert [oracle_lib.owner(int(k), g) for g in (1, 2, 3, 8)] == d["owner"][i].tolist()
