@@ -4,6 +4,7 @@
 #include "table.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace meepo {
@@ -68,6 +69,10 @@ MEEPO_API meepo_status meepo_create(const meepo_config* cfg, meepo_table** out) 
   DeviceGuard guard(cfg->device);
   if (!guard.ok) return fail(MEEPO_ECUDA, "cudaSetDevice failed");
 
+  if (const char* g = getenv("MEEPO_L2_FETCH_GRANULARITY")) {  // experiment knob: 32 / 64 / 128
+    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
+    cudaGetLastError();
+  }
   meepo_table* t = new meepo_table();
   t->cfg = *cfg;
   t->device = cfg->device;

@@ -127,6 +127,7 @@ struct SegWork {
   uint32_t *sk_in, *sk_out, *sv_in, *sv_out, *tile_count, *tile_off, *seg_start;
   char *cub_tmp, *long_seg;
   uint2* leaf_desc;
+  uint4* seg_desc;
   float* partial;
   size_t cub_bytes, max_long, max_leaves;
   uint32_t n, ntiles;

@@ -63,7 +63,8 @@ __global__ void __launch_bounds__(256) seg_count_kernel(const uint32_t* __restri
 // single CTA: exclusive scan of tile counts; publishes U and resets the long-segment counters
 __global__ void __launch_bounds__(1024) seg_scan_kernel(const uint32_t* __restrict__ tile_count,
                                                         uint32_t ntiles, uint32_t* __restrict__ tile_off,
-                                                        uint32_t* __restrict__ seg_start, uint32_t n,
+                                                        uint32_t* __restrict__ seg_start,
+                                                        uint4* __restrict__ seg_desc, uint32_t n,
                                                         const uint32_t* __restrict__ sk, uint32_t miss_key,
                                                         DeviceState* ds, int count_updates) {
   __shared__ uint32_t warp_sum[32];
@@ -102,6 +103,7 @@ __global__ void __launch_bounds__(1024) seg_scan_kernel(const uint32_t* __restri
   if (threadIdx.x == 0) {
     const uint32_t U = carry_s;
     seg_start[U] = n;
+    seg_desc[U] = make_uint4(n, kNil, 0, 0);
     ds->num_segments = U;
     ds->num_long = 0;
     ds->num_leaves = 0;
@@ -111,8 +113,10 @@ __global__ void __launch_bounds__(1024) seg_scan_kernel(const uint32_t* __restri
 }
 
 __global__ void __launch_bounds__(256) seg_fill_kernel(const uint32_t* __restrict__ sk, uint32_t n,
+                                                       const uint32_t* __restrict__ sv,
                                                        const uint32_t* __restrict__ tile_off,
-                                                       uint32_t* __restrict__ seg_start) {
+                                                       uint32_t* __restrict__ seg_start,
+                                                       uint4* __restrict__ seg_desc) {
   __shared__ uint32_t warp_cnt[8];
   const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   uint32_t running = tile_off[blockIdx.x];
@@ -131,7 +135,11 @@ __global__ void __launch_bounds__(256) seg_fill_kernel(const uint32_t* __restric
       before += j < (int)w ? c : 0;
       total += c;
     }
-    if (head) seg_start[running + before + __popc(m & ((1u << lane) - 1u))] = i;
+    if (head) {
+      const uint32_t u = running + before + __popc(m & ((1u << lane) - 1u));
+      seg_start[u] = i;
+      seg_desc[u] = make_uint4(i, sk[i], sv[i], 0);  // {first sorted position, sort key, first batch index}
+    }
     running += total;
     __syncthreads();
   }
@@ -161,14 +169,27 @@ __device__ __forceinline__ void widen(const uint4& raw, float (&g)[Chunk<BF16>::
   }
 }
 
+template <bool BF16>
+__device__ __forceinline__ void reduce_tail(const uint4* __restrict__ grads, const uint32_t* __restrict__ sidx,
+                                            uint32_t j0, uint32_t s1, uint32_t cpr, uint32_t q,
+                                            float (&acc)[Chunk<BF16>::E]);
+
 // acc = ((g[s0] + g[s0+1]) + ...) over sorted positions [s0, s1), chunk q of every row.
 template <bool BF16>
 __device__ __forceinline__ void reduce_positions(const uint4* __restrict__ grads,
                                                  const uint32_t* __restrict__ sidx, uint32_t s0, uint32_t s1,
                                                  uint32_t cpr, uint32_t q, float (&acc)[Chunk<BF16>::E]) {
-  constexpr int E = Chunk<BF16>::E;
   widen<BF16>(ld_nc(grads + (size_t)sidx[s0] * cpr + q), acc);
-  uint32_t j = s0 + 1;
+  reduce_tail<BF16>(grads, sidx, s0 + 1, s1, cpr, q, acc);
+}
+
+// acc = ((acc + g[j0]) + g[j0+1]) + ... over sorted positions [j0, s1)
+template <bool BF16>
+__device__ __forceinline__ void reduce_tail(const uint4* __restrict__ grads, const uint32_t* __restrict__ sidx,
+                                            uint32_t j0, uint32_t s1, uint32_t cpr, uint32_t q,
+                                            float (&acc)[Chunk<BF16>::E]) {
+  constexpr int E = Chunk<BF16>::E;
+  uint32_t j = j0;
   for (; j + 4 <= s1; j += 4) {
     uint4 raw[4];
 #pragma unroll
@@ -202,20 +223,60 @@ __device__ __forceinline__ uint4 narrow(const float (&w)[Chunk<BF16>::E]) {
   }
 }
 
-// One optimizer step on chunk q of the row in `slot` (meepo.h "Update"; every op rounded once).
+// One optimizer step on chunk q of the row in `slot` (meepo.h "Update"; every op rounded once),
+// split into the loads (opt_issue) and the math + stores (opt_finish) so that a caller can put the
+// loads of several segments in flight before it consumes the first.
 template <bool BF16, int OPT>
-__device__ __forceinline__ void optimizer_chunk(const TableView& t, uint32_t slot, uint32_t q,
-                                                const float (&g)[Chunk<BF16>::E], float alpha,
-                                                uint4* reduce_out) {
+struct OptIn {
+  static constexpr int SQ = Chunk<BF16>::E / 4;  // state uint4s per chunk
+  static constexpr int NS = OPT == MEEPO_ADAGRAD ? SQ : (OPT == MEEPO_ADAM ? 2 * SQ : 1);
+  uint4 row;
+  uint4 st[NS];
+};
+
+template <bool BF16, int OPT>
+__device__ __forceinline__ void opt_issue(const TableView& t, uint32_t slot, uint32_t q, OptIn<BF16, OPT>& in) {
+  constexpr int SQ = OptIn<BF16, OPT>::SQ;
+  if constexpr (OPT == kStoreOnly) return;
+  in.row = ld_stream(t.rows + (size_t)slot * t.cpr + q);
+  if constexpr (OPT == MEEPO_ADAGRAD) {
+    const uint4* sp = t.state + (size_t)slot * t.scpr + (size_t)q * SQ;
+#pragma unroll
+    for (int k = 0; k < SQ; k++) in.st[k] = ld_stream(sp + k);
+  } else if constexpr (OPT == MEEPO_ADAM) {
+    const uint4* mp = t.state + (size_t)slot * t.scpr + (size_t)q * SQ;
+    const uint4* vp = mp + (size_t)t.cpr * SQ;
+#pragma unroll
+    for (int k = 0; k < SQ; k++) {
+      in.st[k] = ld_stream(mp + k);
+      in.st[SQ + k] = ld_stream(vp + k);
+    }
+  }
+}
+
+__device__ __forceinline__ void unpack4(const uint4& raw, float* f) {
+  f[0] = __uint_as_float(raw.x);
+  f[1] = __uint_as_float(raw.y);
+  f[2] = __uint_as_float(raw.z);
+  f[3] = __uint_as_float(raw.w);
+}
+__device__ __forceinline__ uint4 pack4(const float* f) {
+  return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+}
+
+template <bool BF16, int OPT>
+__device__ __forceinline__ void opt_finish(const TableView& t, uint32_t slot, uint32_t q,
+                                           const OptIn<BF16, OPT>& in, const float (&g)[Chunk<BF16>::E],
+                                           float alpha, uint4* reduce_out) {
   constexpr int E = Chunk<BF16>::E;
-  constexpr int SQ = E / 4;  // state uint4s per chunk
+  constexpr int SQ = OptIn<BF16, OPT>::SQ;
   if constexpr (OPT == kStoreOnly) {
     st_stream(reduce_out + (size_t)slot * t.cpr + q, narrow<BF16>(g));
     return;
   }
   uint4* rowp = t.rows + (size_t)slot * t.cpr + q;
   float w[E];
-  widen<BF16>(ld_stream(rowp), w);
+  widen<BF16>(in.row, w);
   if constexpr (OPT == MEEPO_SGD) {
 #pragma unroll
     for (int e = 0; e < E; e++) w[e] = __fsub_rn(w[e], __fmul_rn(t.lr, g[e]));
@@ -223,13 +284,7 @@ __device__ __forceinline__ void optimizer_chunk(const TableView& t, uint32_t slo
     uint4* sp = t.state + (size_t)slot * t.scpr + (size_t)q * SQ;
     float a[E];
 #pragma unroll
-    for (int k = 0; k < SQ; k++) {
-      const uint4 raw = ld_stream(sp + k);
-      a[4 * k] = __uint_as_float(raw.x);
-      a[4 * k + 1] = __uint_as_float(raw.y);
-      a[4 * k + 2] = __uint_as_float(raw.z);
-      a[4 * k + 3] = __uint_as_float(raw.w);
-    }
+    for (int k = 0; k < SQ; k++) unpack4(in.st[k], a + 4 * k);
 #pragma unroll
     for (int e = 0; e < E; e++) {
       a[e] = __fadd_rn(a[e], __fmul_rn(g[e], g[e]));
@@ -237,20 +292,15 @@ __device__ __forceinline__ void optimizer_chunk(const TableView& t, uint32_t slo
       w[e] = __fsub_rn(w[e], __fdiv_rn(__fmul_rn(t.lr, g[e]), den));
     }
 #pragma unroll
-    for (int k = 0; k < SQ; k++)
-      st_stream(sp + k, make_uint4(__float_as_uint(a[4 * k]), __float_as_uint(a[4 * k + 1]),
-                                   __float_as_uint(a[4 * k + 2]), __float_as_uint(a[4 * k + 3])));
+    for (int k = 0; k < SQ; k++) st_stream(sp + k, pack4(a + 4 * k));
   } else {
     uint4* mp = t.state + (size_t)slot * t.scpr + (size_t)q * SQ;
     uint4* vp = mp + (size_t)t.cpr * SQ;
     float m[E], v[E];
 #pragma unroll
     for (int k = 0; k < SQ; k++) {
-      const uint4 a = ld_stream(mp + k), b = ld_stream(vp + k);
-      m[4 * k] = __uint_as_float(a.x), m[4 * k + 1] = __uint_as_float(a.y);
-      m[4 * k + 2] = __uint_as_float(a.z), m[4 * k + 3] = __uint_as_float(a.w);
-      v[4 * k] = __uint_as_float(b.x), v[4 * k + 1] = __uint_as_float(b.y);
-      v[4 * k + 2] = __uint_as_float(b.z), v[4 * k + 3] = __uint_as_float(b.w);
+      unpack4(in.st[k], m + 4 * k);
+      unpack4(in.st[SQ + k], v + 4 * k);
     }
     const float omb1 = __fsub_rn(1.0f, t.beta1), omb2 = __fsub_rn(1.0f, t.beta2);
 #pragma unroll
@@ -262,13 +312,20 @@ __device__ __forceinline__ void optimizer_chunk(const TableView& t, uint32_t slo
     }
 #pragma unroll
     for (int k = 0; k < SQ; k++) {
-      st_stream(mp + k, make_uint4(__float_as_uint(m[4 * k]), __float_as_uint(m[4 * k + 1]),
-                                   __float_as_uint(m[4 * k + 2]), __float_as_uint(m[4 * k + 3])));
-      st_stream(vp + k, make_uint4(__float_as_uint(v[4 * k]), __float_as_uint(v[4 * k + 1]),
-                                   __float_as_uint(v[4 * k + 2]), __float_as_uint(v[4 * k + 3])));
+      st_stream(mp + k, pack4(m + 4 * k));
+      st_stream(vp + k, pack4(v + 4 * k));
     }
   }
   st_stream(rowp, narrow<BF16>(w));
+}
+
+template <bool BF16, int OPT>
+__device__ __forceinline__ void optimizer_chunk(const TableView& t, uint32_t slot, uint32_t q,
+                                                const float (&g)[Chunk<BF16>::E], float alpha,
+                                                uint4* reduce_out) {
+  OptIn<BF16, OPT> in;
+  opt_issue<BF16, OPT>(t, slot, q, in);
+  opt_finish<BF16, OPT>(t, slot, q, in, g, alpha, reduce_out);
 }
 
 // Adam: per-row step count -> scalar step size (double math, rounded once). Every lane of the
@@ -289,6 +346,7 @@ struct ApplyArgs {
   const uint32_t* sorted_slot;
   const uint32_t* sorted_idx;
   const uint32_t* seg_start;
+  const uint4* seg_desc;  // [U+1] {first sorted position, sort key (slot), first batch index, -}
   DeviceState* ds;
   LongSeg* long_seg;
   uint2* leaf_desc;
@@ -333,6 +391,81 @@ __global__ void __launch_bounds__(256) apply_kernel(TableView t, ApplyArgs a) {
       reduce_positions<BF16>(a.grads, a.sorted_idx, s0, s1, t.cpr, q, acc);
       optimizer_chunk<BF16, OPT>(t, slot, q, acc, alpha, a.reduce_out);
     }
+  }
+}
+
+// A4': the same work for rows of <= 512 B (one 16-byte chunk per lane, group_lanes == cpr), software
+// pipelined: each group handles two segments per trip, puts the gradient / row / state loads of
+// both in flight before it consumes the first, and fetches the next trip's descriptors underneath.
+template <bool BF16, int OPT>
+__global__ void __launch_bounds__(256) apply_pipelined_kernel(TableView t, ApplyArgs a) {
+  constexpr int E = Chunk<BF16>::E;
+  const uint32_t GL = a.group_lanes;  // == t.cpr
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t q = lane & (GL - 1);
+  const unsigned gmask = (GL == 32 ? 0xFFFFFFFFu : ((1u << GL) - 1u) << (lane & ~(GL - 1)));
+  const uint32_t groups_per_block = blockDim.x / GL;
+  const uint32_t group = blockIdx.x * groups_per_block + threadIdx.x / GL;
+  const uint32_t stride = gridDim.x * groups_per_block * 2;
+  const uint32_t U = a.ds->num_segments;
+  const uint32_t cpr = t.cpr;
+  const uint4 nil = make_uint4(0, kNil, 0, 0);
+  auto desc = [&](uint32_t i) { return i <= U ? __ldg(a.seg_desc + i) : nil; };
+
+  uint32_t u = group * 2;
+  uint4 da = desc(u), db = desc(u + 1);
+  uint32_t ec = desc(u + 2).x;
+  while (u < U) {
+    const uint32_t un = u + stride;
+    const uint4 na = desc(un), nb = desc(un + 1);
+    const uint32_t nc = desc(un + 2).x;
+    const uint32_t cntA = db.x - da.x, cntB = ec - db.x;
+    const bool liveA = da.y < a.limit, liveB = (u + 1 < U) && db.y < a.limit;
+    const bool okA = liveA && cntA <= kLeaf, okB = liveB && cntB <= kLeaf;
+    uint4 gA = make_uint4(0, 0, 0, 0), gB = gA;
+    OptIn<BF16, OPT> inA, inB;
+    if (okA) {
+      gA = ld_nc(a.grads + (size_t)da.z * cpr + q);
+      opt_issue<BF16, OPT>(t, da.y, q, inA);
+    }
+    if (okB) {
+      gB = ld_nc(a.grads + (size_t)db.z * cpr + q);
+      opt_issue<BF16, OPT>(t, db.y, q, inB);
+    }
+#pragma unroll
+    for (int h = 0; h < 2; h++) {  // segments longer than a leaf go to the leaf kernels
+      const bool live = h ? liveB : liveA;
+      const uint32_t cnt = h ? cntB : cntA;
+      if (live && cnt > kLeaf) {
+        const uint32_t nleaf = (cnt + kLeaf - 1) / kLeaf;
+        uint32_t base = 0;
+        if (q == 0) {
+          const uint32_t li = atomicAdd(&a.ds->num_long, 1u);
+          base = atomicAdd(&a.ds->num_leaves, nleaf);
+          a.long_seg[li] = LongSeg{u + h, base, nleaf, 0};
+        }
+        base = __shfl_sync(gmask, base, lane & ~(GL - 1));
+        for (uint32_t c = q; c < nleaf; c += GL) a.leaf_desc[base + c] = make_uint2(u + h, c);
+      }
+    }
+    if (okA) {
+      const float alpha = adam_alpha<OPT>(t, da.y, gmask, q == 0);
+      float acc[E];
+      widen<BF16>(gA, acc);
+      if (cntA > 1) reduce_tail<BF16>(a.grads, a.sorted_idx, da.x + 1, da.x + cntA, cpr, q, acc);
+      opt_finish<BF16, OPT>(t, da.y, q, inA, acc, alpha, a.reduce_out);
+    }
+    if (okB) {
+      const float alpha = adam_alpha<OPT>(t, db.y, gmask, q == 0);
+      float acc[E];
+      widen<BF16>(gB, acc);
+      if (cntB > 1) reduce_tail<BF16>(a.grads, a.sorted_idx, db.x + 1, db.x + cntB, cpr, q, acc);
+      opt_finish<BF16, OPT>(t, db.y, q, inB, acc, alpha, a.reduce_out);
+    }
+    da = na;
+    db = nb;
+    ec = nc;
+    u = un;
   }
 }
 
@@ -398,24 +531,34 @@ __global__ void __launch_bounds__(256) long_finish_kernel(TableView t, ApplyArgs
 }
 
 template <bool BF16>
-static void pick_apply(int opt, const void*& apply, const void*& finish) {
+static void pick_apply(int opt, bool pipelined, const void*& apply, const void*& finish) {
+  if (pipelined) {
+    switch (opt) {
+      case MEEPO_SGD: apply = (const void*)apply_pipelined_kernel<BF16, MEEPO_SGD>; break;
+      case MEEPO_ADAGRAD: apply = (const void*)apply_pipelined_kernel<BF16, MEEPO_ADAGRAD>; break;
+      case MEEPO_ADAM: apply = (const void*)apply_pipelined_kernel<BF16, MEEPO_ADAM>; break;
+      default: apply = (const void*)apply_pipelined_kernel<BF16, kStoreOnly>;
+    }
+  }
+  const void* plain = nullptr;
   switch (opt) {
     case MEEPO_SGD:
-      apply = (const void*)apply_kernel<BF16, MEEPO_SGD>;
+      plain = (const void*)apply_kernel<BF16, MEEPO_SGD>;
       finish = (const void*)long_finish_kernel<BF16, MEEPO_SGD>;
       break;
     case MEEPO_ADAGRAD:
-      apply = (const void*)apply_kernel<BF16, MEEPO_ADAGRAD>;
+      plain = (const void*)apply_kernel<BF16, MEEPO_ADAGRAD>;
       finish = (const void*)long_finish_kernel<BF16, MEEPO_ADAGRAD>;
       break;
     case MEEPO_ADAM:
-      apply = (const void*)apply_kernel<BF16, MEEPO_ADAM>;
+      plain = (const void*)apply_kernel<BF16, MEEPO_ADAM>;
       finish = (const void*)long_finish_kernel<BF16, MEEPO_ADAM>;
       break;
     default:
-      apply = (const void*)apply_kernel<BF16, kStoreOnly>;
+      plain = (const void*)apply_kernel<BF16, kStoreOnly>;
       finish = (const void*)long_finish_kernel<BF16, kStoreOnly>;
   }
+  if (!pipelined) apply = plain;
 }
 
 // Scratch of one sort + segment + reduce pipeline over n (sort key, batch index) pairs.
@@ -426,7 +569,7 @@ size_t SegWork::bytes(uint64_t n, uint32_t dim, int end_bit_) {
   const size_t ntiles_ = (n + kSegTile - 1) / kSegTile;
   const size_t max_long_ = n / (kLeaf + 1) + 1, max_leaves_ = n / 128 + 2;
   return 4 * Workspace::pad(n * 4) + Workspace::pad(cub) + 2 * Workspace::pad(ntiles_ * 4) +
-         Workspace::pad((n + 2) * 4) + Workspace::pad(max_long_ * sizeof(LongSeg)) +
+         Workspace::pad((n + 2) * 4) + Workspace::pad((n + 2) * 16) + Workspace::pad(max_long_ * sizeof(LongSeg)) +
          Workspace::pad(max_leaves_ * 8) + Workspace::pad(max_leaves_ * dim * 4) + 4096;
 }
 
@@ -447,6 +590,7 @@ void SegWork::take(Workspace& ws, uint64_t n_, uint32_t dim, int end_bit_) {
   tile_count = ws.take<uint32_t>(ntiles);
   tile_off = ws.take<uint32_t>(ntiles);
   seg_start = ws.take<uint32_t>(n_ + 2);
+  seg_desc = ws.take<uint4>(n_ + 2);
   long_seg = ws.take<char>(max_long * sizeof(LongSeg));
   leaf_desc = ws.take<uint2>(max_leaves);
   partial = ws.take<float>(max_leaves * dim);
@@ -474,9 +618,9 @@ meepo_status run_segmented(meepo_table* t, SegWork& w, uint32_t limit, const voi
   {
     ProfScope ps(t, names[1], stream);
     seg_count_kernel<<<w.ntiles, 256, 0, stream>>>(w.sk_out, n32, w.tile_count);
-    seg_scan_kernel<<<1, 1024, 0, stream>>>(w.tile_count, w.ntiles, w.tile_off, w.seg_start, n32, w.sk_out, limit,
-                                            t->dstate, mode != kStoreOnly);
-    seg_fill_kernel<<<w.ntiles, 256, 0, stream>>>(w.sk_out, n32, w.tile_off, w.seg_start);
+    seg_scan_kernel<<<1, 1024, 0, stream>>>(w.tile_count, w.ntiles, w.tile_off, w.seg_start, w.seg_desc, n32, w.sk_out,
+                                            limit, t->dstate, mode != kStoreOnly);
+    seg_fill_kernel<<<w.ntiles, 256, 0, stream>>>(w.sk_out, n32, w.sv_out, w.tile_off, w.seg_start, w.seg_desc);
     MEEPO_CUDA_TRY(cudaGetLastError());
   }
   ApplyArgs a;
@@ -484,6 +628,7 @@ meepo_status run_segmented(meepo_table* t, SegWork& w, uint32_t limit, const voi
   a.sorted_slot = w.sk_out;
   a.sorted_idx = w.sv_out;
   a.seg_start = w.seg_start;
+  a.seg_desc = w.seg_desc;
   a.ds = t->dstate;
   a.long_seg = reinterpret_cast<LongSeg*>(w.long_seg);
   a.leaf_desc = w.leaf_desc;
@@ -496,17 +641,19 @@ meepo_status run_segmented(meepo_table* t, SegWork& w, uint32_t limit, const voi
 
   const bool bf16 = t->v.dtype == MEEPO_BF16;
   const void *k_apply = nullptr, *k_finish = nullptr;
+  const bool pipelined = gl == t->v.cpr && !getenv("MEEPO_APPLY_PLAIN");
   if (bf16)
-    pick_apply<true>(mode, k_apply, k_finish);
+    pick_apply<true>(mode, pipelined, k_apply, k_finish);
   else
-    pick_apply<false>(mode, k_apply, k_finish);
+    pick_apply<false>(mode, pipelined, k_apply, k_finish);
   const void* k_leaf = bf16 ? (const void*)leaf_kernel<true> : (const void*)leaf_kernel<false>;
   void* args[] = {&t->v, &a};
   const uint64_t groups_per_block = 256 / gl;
   if (grads_ready) MEEPO_CUDA_TRY(cudaStreamWaitEvent(stream, grads_ready, 0));
   {
     ProfScope ps(t, names[2], stream);
-    const int grid = grid_for(t, k_apply, 256, 0, (n32 + groups_per_block - 1) / groups_per_block);
+    const uint64_t per_block = groups_per_block * (pipelined ? 2 : 1);
+    const int grid = grid_for(t, k_apply, 256, 0, (n32 + per_block - 1) / per_block);
     MEEPO_CUDA_TRY(cudaLaunchKernel(k_apply, dim3(grid), dim3(256), args, 0, stream));
   }
   {
