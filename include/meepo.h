@@ -106,6 +106,7 @@ extern "C" {
 #define MEEPO_KEY_EMPTY 0xFFFFFFFFFFFFFFFFull
 #define MEEPO_KEY_RESERVED 0xFFFFFFFFFFFFFFFEull
 #define MEEPO_REDUCE_LEAF 256u
+#define MEEPO_BUCKET_SLOTS 14u /* slots per 128-byte bucket line; capacity is rounded up to it */
 #define MEEPO_OWNER_SALT 0xD6E8FEB86659FD93ull
 
 typedef struct meepo_table meepo_table; /* opaque */
@@ -137,7 +138,7 @@ enum { MEEPO_FLAG_TRACK_SCORES = 1u };
 typedef struct {
   uint32_t dim;          /* elements per row */
   uint32_t flags;        /* MEEPO_FLAG_* */
-  uint64_t capacity;     /* number of key slots (rounded up to a multiple of 32) */
+  uint64_t capacity;     /* number of key slots (rounded up to a multiple of MEEPO_BUCKET_SLOTS) */
   int32_t dtype;         /* meepo_dtype */
   int32_t opt;           /* meepo_opt */
   float lr, eps, beta1, beta2, init_accum;

@@ -1,14 +1,17 @@
 // common.cuh — table layout in HBM, hashing, probing and row helpers shared by every kernel.
 //
-// Layout (DESIGN.md "Data layout"): open addressing over BUCKETS of 32 slots.
-//   keys     u64[slots]           EMPTY = ~0; bucket b owns slots [32b, 32b+32)
-//   digests  u8[slots]            one 32-byte sector per bucket; 0 = free slot, else an 8-bit tag
-//                                 of the key's hash (1..255). A probe reads ONE sector of tags,
-//                                 SIMD-compares them in registers and then touches only the
-//                                 8-byte key(s) whose tag matched.
-//   overflow u32 bitmap[buckets]  bit b set once any insertion has skipped past bucket b because
-//                                 it was full; lookups follow the chain only while it is set, so
-//                                 eviction can free slots without tombstones.
+// Layout (DESIGN.md "Data layout"): open addressing over BUCKETS that are exactly one 128-byte line
+// — the DRAM fetch granule measured on B200 (a random 8-byte read costs 128 B of HBM traffic, ncu
+// dram__bytes_read; cudaLimitMaxL2FetchGranularity has no effect). One probe = one line:
+//   bytes   0..13   14 one-byte tags of the bucket's 14 slots: 0 = free slot, else an 8-bit tag of
+//                   the key's hash (1..255). The probe loads these 16 bytes, SIMD-compares all tags
+//                   in registers and then touches only the 8-byte key(s) whose tag matched — which
+//                   sit in the SAME line, i.e. an L2 hit, not a second HBM access.
+//   bytes  14..15   per-bucket metadata: bit 0 = overflow (set once any insertion has skipped past
+//                   this bucket because it was full; lookups follow the chain only while it is set,
+//                   so eviction can free slots without tombstones)
+//   bytes 16..127   14 keys (u64, EMPTY = ~0), claimed with one 64-bit CAS
+// Slot s = 14*bucket + index addresses the other arrays:
 //   rows     16-byte chunks [slots * cpr]     value arena
 //   state    16-byte chunks [slots * scpr]    optimizer-state arena (fp32)
 //   scores   uint2[slots] {freq, last_epoch}  only with MEEPO_FLAG_TRACK_SCORES; 0 for free slots
@@ -22,17 +25,22 @@
 
 namespace meepo {
 
-constexpr uint32_t kBucket = 32;
+constexpr uint32_t kBucket = MEEPO_BUCKET_SLOTS;  // 14
 constexpr uint32_t kNil = 0xFFFFFFFFu;
 
 enum Counter : int {
   C_SIZE = 0, C_INSERTS, C_HITS, C_MISSES, C_FULL, C_EVICTIONS, C_UPDATES, C_DROPPED, C_OVERFLOW, C_COUNT
 };
 
+struct __align__(128) BucketLine {
+  uint8_t tag[kBucket];
+  uint16_t meta;  // bit 0: overflow
+  uint64_t key[kBucket];
+};
+static_assert(sizeof(BucketLine) == 128, "a bucket is one 128-byte line");
+
 struct TableView {
-  uint64_t* keys;
-  uint8_t* digests;
-  uint32_t* overflow;
+  BucketLine* buckets;
   uint4* rows;
   uint4* state;
   uint2* scores;
@@ -91,49 +99,62 @@ __device__ __forceinline__ void st_stream(uint4* p, uint4 v) {
                : "memory");
 }
 
-// --- digest line -------------------------------------------------------------------------------
+// --- bucket line -------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t* key_ptr(const TableView& t, uint32_t slot) {
+  return &t.buckets[slot / kBucket].key[slot % kBucket];
+}
+__device__ __forceinline__ uint8_t* tag_ptr(const TableView& t, uint32_t slot) {
+  return &t.buckets[slot / kBucket].tag[slot % kBucket];
+}
 // 4 tag bytes -> 4 mask bits (bit i set if byte i of `w` equals the tag replicated in `pat`).
 __device__ __forceinline__ uint32_t bytes_eq4(uint32_t w, uint32_t pat) {
   uint32_t m = __vcmpeq4(w, pat) & 0x80808080u;  // bit 7 of each matching byte
   return ((m >> 7) * 0x10204080u) >> 28;           // gather bits 0,8,16,24 into a nibble
 }
-struct DigestLine {
-  uint4 lo, hi;
-};
-__device__ __forceinline__ DigestLine load_digests(const TableView& t, uint32_t b) {
-  const uint4* p = reinterpret_cast<const uint4*>(t.digests + (size_t)b * kBucket);
-  DigestLine d;
-  d.lo = __ldg(p);
-  d.hi = __ldg(p + 1);
-  return d;
+// Load policy of the probe. kCoherent (ld.global.cg, L2): find_or_insert, where other threads CAS
+// keys / OR the overflow bit in the same line (tags and published keys never change in a kernel).
+// kReadOnly (ld.global.nc, L1-cached): lookup / apply_gradients / evict probes — nothing in the
+// bucket array is written while they run, and hot Zipf keys are served by L1.
+enum : int { kCoherent = 0, kReadOnly = 1 };
+template <int LD>
+__device__ __forceinline__ uint4 load_header(const TableView& t, uint32_t b) {
+  const uint4* p = reinterpret_cast<const uint4*>(&t.buckets[b]);
+  return LD == kReadOnly ? __ldg(p) : __ldcg(p);
 }
-__device__ __forceinline__ uint32_t match_mask(const DigestLine& d, uint32_t tag) {
-  uint32_t pat = tag * 0x01010101u;
-  return bytes_eq4(d.lo.x, pat) | (bytes_eq4(d.lo.y, pat) << 4) | (bytes_eq4(d.lo.z, pat) << 8) |
-         (bytes_eq4(d.lo.w, pat) << 12) | (bytes_eq4(d.hi.x, pat) << 16) | (bytes_eq4(d.hi.y, pat) << 20) |
-         (bytes_eq4(d.hi.z, pat) << 24) | (bytes_eq4(d.hi.w, pat) << 28);
+template <int LD>
+__device__ __forceinline__ uint64_t load_key(const TableView& t, uint32_t b, uint32_t i) {
+  const uint64_t* p = &t.buckets[b].key[i];
+  return LD == kReadOnly ? __ldg(p) : __ldcg(p);
 }
-__device__ __forceinline__ bool overflowed(const TableView& t, uint32_t b) {
-  return (__ldcg(t.overflow + (b >> 5)) >> (b & 31)) & 1u;
+__device__ __forceinline__ uint32_t match_mask(const uint4& h, uint32_t tag) {
+  const uint32_t pat = tag * 0x01010101u;
+  return bytes_eq4(h.x, pat) | (bytes_eq4(h.y, pat) << 4) | (bytes_eq4(h.z, pat) << 8) |
+         ((bytes_eq4(h.w, pat) & 3u) << 12);
 }
+__device__ __forceinline__ bool overflowed(const uint4& h) { return (h.w >> 16) & 1u; }
 
-// Read-only probe: slot of `key` or kNil. Keys whose tag is published never move, so plain loads.
-__device__ __forceinline__ uint32_t probe_find(const TableView& t, uint64_t key) {
-  const uint64_t h = mix64(key);
-  uint32_t b = bucket_of(h, t.num_buckets);
-  const uint32_t tag = digest_of(h);
+// Slot of `key` or kNil, starting at bucket b with the header already in registers.
+template <int LD>
+__device__ __forceinline__ uint32_t probe_from(const TableView& t, uint64_t key, uint32_t tag, uint32_t b, uint4 hdr) {
   for (uint32_t p = 0; p < t.num_buckets; ++p) {
-    DigestLine d = load_digests(t, b);
-    uint32_t m = match_mask(d, tag);
+    uint32_t m = match_mask(hdr, tag);
     while (m) {
-      uint32_t s = b * kBucket + (__ffs(m) - 1);
-      if (__ldg(t.keys + s) == key) return s;
+      const uint32_t i = __ffs(m) - 1;
+      if (load_key<LD>(t, b, i) == key) return b * kBucket + i;
       m &= m - 1;
     }
-    if (!overflowed(t, b)) return kNil;
+    if (!overflowed(hdr)) return kNil;
     b = (b + 1 == t.num_buckets) ? 0 : b + 1;
+    hdr = load_header<LD>(t, b);
   }
   return kNil;
+}
+// Probe without insertion. One HBM line per bucket visited.
+template <int LD = kCoherent>
+__device__ __forceinline__ uint32_t probe_find(const TableView& t, uint64_t key) {
+  const uint64_t h = mix64(key);
+  const uint32_t b = bucket_of(h, t.num_buckets);
+  return probe_from<LD>(t, key, digest_of(h), b, load_header<LD>(t, b));
 }
 
 struct Probe {
@@ -149,7 +170,7 @@ struct Probe {
 __device__ __forceinline__ Probe probe_find_or_insert(const TableView& t, uint64_t key) {
   Probe r{kNil, MEEPO_KEY_INVALID, false};
   if (!key_valid(key)) return r;
-  uint32_t s = probe_find(t, key);
+  uint32_t s = probe_find<kCoherent>(t, key);
   if (s != kNil) {
     r.slot = s;
     r.status = MEEPO_KEY_FOUND;
@@ -158,23 +179,23 @@ __device__ __forceinline__ Probe probe_find_or_insert(const TableView& t, uint64
   const uint64_t h = mix64(key);
   uint32_t b = bucket_of(h, t.num_buckets);
   for (uint32_t p = 0; p < t.num_buckets; ++p) {
-    DigestLine d = load_digests(t, b);
-    uint32_t free_m = match_mask(d, 0);
+    const uint4 hdr = load_header<kCoherent>(t, b);
+    uint32_t free_m = match_mask(hdr, 0);
     while (free_m) {
-      uint32_t slot = b * kBucket + (__ffs(free_m) - 1);
-      unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(t.keys + slot),
+      const uint32_t i = __ffs(free_m) - 1;
+      unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(&t.buckets[b].key[i]),
                                          (unsigned long long)MEEPO_KEY_EMPTY, (unsigned long long)key);
       if (old == MEEPO_KEY_EMPTY || old == key) {
-        r.slot = slot;
+        r.slot = b * kBucket + i;
         r.status = MEEPO_KEY_INSERTED;
         r.winner = (old == MEEPO_KEY_EMPTY);
         return r;
       }
       free_m &= free_m - 1;
     }
-    if (!overflowed(t, b)) {
-      const uint32_t bit = 1u << (b & 31);
-      if (!(atomicOr(t.overflow + (b >> 5), bit) & bit)) atomicAdd(t.counters + C_OVERFLOW, 1ull);
+    if (!overflowed(hdr)) {  // tags 12,13 and the metadata share one 32-bit word of the header
+      uint32_t* w = reinterpret_cast<uint32_t*>(&t.buckets[b]) + 3;
+      if (!(atomicOr(w, 1u << 16) & (1u << 16))) atomicAdd(t.counters + C_OVERFLOW, 1ull);
     }
     b = (b + 1 == t.num_buckets) ? 0 : b + 1;
   }

@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(256) score_hist_kernel(TableView t, int policy
   sh[threadIdx.x] = 0;
   __syncthreads();
   for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < t.slots; s += gridDim.x * blockDim.x) {
-    if (t.keys[s] == MEEPO_KEY_EMPTY) continue;
+    if (*key_ptr(t, s) == MEEPO_KEY_EMPTY) continue;
     const uint32_t sc = score_of(t, s, policy);
     if ((sc & mask) == prefix) atomicAdd(&sh[(sc >> shift) & 0xFFu], 1u);
   }
@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(256) candidates_kernel(TableView t, int policy
     uint64_t key = MEEPO_KEY_EMPTY;
     bool take = false;
     if (s < t.slots) {
-      key = t.keys[s];
+      key = *key_ptr(t, s);
       take = key != MEEPO_KEY_EMPTY && score_of(t, s, policy) <= threshold;
     }
     const unsigned m = __ballot_sync(0xFFFFFFFFu, take);
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(256) spill_copy_kernel(TableView t, SpillView 
     for (uint32_t q = lane; q < t.cpr; q += 32) sp.rows[(size_t)d * t.cpr + q] = t.rows[(size_t)s * t.cpr + q];
     for (uint32_t q = lane; q < t.scpr; q += 32) sp.state[(size_t)d * t.scpr + q] = t.state[(size_t)s * t.scpr + q];
     if (lane == 0) {
-      const uint64_t key = t.keys[s];
+      const uint64_t key = *key_ptr(t, s);
       const uint2 sc = t.scores[s];
       sp.meta[d] = make_uint4((uint32_t)key, (uint32_t)(key >> 32), sc.x, sc.y);
       sp.steps[d] = t.steps ? t.steps[s] : 0u;
@@ -111,8 +111,8 @@ __global__ void __launch_bounds__(256) spill_copy_kernel(TableView t, SpillView 
 __global__ void release_kernel(TableView t, const uint32_t* __restrict__ vslot, uint32_t k) {
   for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < k; j += gridDim.x * blockDim.x) {
     const uint32_t s = vslot[j];
-    t.keys[s] = MEEPO_KEY_EMPTY;
-    t.digests[s] = 0;
+    *key_ptr(t, s) = MEEPO_KEY_EMPTY;
+    *tag_ptr(t, s) = 0;
     t.scores[s] = make_uint2(0, 0);
     if (t.steps) t.steps[s] = 0;
   }
@@ -145,7 +145,7 @@ __global__ void found_flags_kernel(TableView t, const uint64_t* __restrict__ key
                                    uint8_t* __restrict__ found) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint64_t k = keys[i];
-    found[i] = key_valid(k) && probe_find(t, k) != kNil;
+    found[i] = key_valid(k) && probe_find<kReadOnly>(t, k) != kNil;
   }
 }
 
@@ -213,6 +213,7 @@ MEEPO_API meepo_status meepo_evict(meepo_table* t, int32_t policy, double target
   const uint64_t target = (uint64_t)std::floor(target_load * (double)t->v.slots);
   if (size <= target) return MEEPO_OK;
   const uint64_t k = size - target;
+  t->cache_valid = false;  // slots are about to change owners
 
   // --- radix select: threshold T = score of the k-th smallest, need `remaining` of the ties
   unsigned long long* d_hist = t->dstate->hist;
@@ -348,6 +349,7 @@ MEEPO_API meepo_status meepo_spill_readmit(meepo_table* t, const uint64_t* keys,
   }
   const uint64_t m = ins_keys.size();
   if (m) {
+    t->cache_valid = false;
     MEEPO_CUDA_TRY(cudaMemcpyAsync(d_keys, ins_keys.data(), m * 8, cudaMemcpyHostToDevice, stream));
     MEEPO_CUDA_TRY(cudaMemcpyAsync(d_slab, ins_slab.data(), m * 4, cudaMemcpyHostToDevice, stream));
     NewList nl{d_new, &t->dstate->new_count[t->foi_parity]};

@@ -14,14 +14,14 @@ namespace meepo {
 
 constexpr int kLiveTile = 1024;
 
-__global__ void __launch_bounds__(256) live_count_kernel(const uint64_t* __restrict__ keys, uint32_t m,
+__global__ void __launch_bounds__(256) live_count_kernel(TableView t, uint32_t m,
                                                          uint32_t* __restrict__ tile_count) {
   const uint32_t base = blockIdx.x * kLiveTile;
   int total = 0;
 #pragma unroll
   for (int k = 0; k < kLiveTile / 256; k++) {
     const uint32_t p = base + k * 256 + threadIdx.x;
-    total += __syncthreads_count(p < m && keys[p] != MEEPO_KEY_EMPTY);
+    total += __syncthreads_count(p < m && *key_ptr(t, p) != MEEPO_KEY_EMPTY);
   }
   if (threadIdx.x == 0) tile_count[blockIdx.x] = (uint32_t)total;
 }
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(1024) scan_tiles_kernel(const uint32_t* __rest
   if (threadIdx.x == 0) out[n] = carry_s;
 }
 
-__global__ void __launch_bounds__(256) live_fill_kernel(const uint64_t* __restrict__ keys, uint32_t m,
+__global__ void __launch_bounds__(256) live_fill_kernel(TableView t, uint32_t m,
                                                         const uint32_t* __restrict__ tile_off,
                                                         uint64_t* __restrict__ live_key,
                                                         uint32_t* __restrict__ live_slot) {
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(256) live_fill_kernel(const uint64_t* __restri
 #pragma unroll 1
   for (int k = 0; k < kLiveTile / 256; k++) {
     const uint32_t p = base + k * 256 + threadIdx.x;
-    const uint64_t key = p < m ? keys[p] : MEEPO_KEY_EMPTY;
+    const uint64_t key = p < m ? *key_ptr(t, p) : MEEPO_KEY_EMPTY;
     const bool occ = key != MEEPO_KEY_EMPTY;
     const unsigned msk = __ballot_sync(0xFFFFFFFFu, occ);
     if (lane == 0) warp_cnt[w] = __popc(msk);
@@ -201,9 +201,9 @@ meepo_status sorted_live(meepo_table* t, uint64_t n, uint64_t** keys_sorted, uin
   char* tmp = t->ws.take<char>(cub_bytes);
   uint32_t* tile_count = t->ws.take<uint32_t>(ntiles + 1);
   uint32_t* tile_off = t->ws.take<uint32_t>(ntiles + 1);
-  live_count_kernel<<<ntiles, 256, 0, stream>>>(t->v.keys, m, tile_count);
+  live_count_kernel<<<ntiles, 256, 0, stream>>>(t->v, m, tile_count);
   scan_tiles_kernel<<<1, 1024, 0, stream>>>(tile_count, tile_off, ntiles);
-  live_fill_kernel<<<ntiles, 256, 0, stream>>>(t->v.keys, m, tile_off, k_in, s_in);
+  live_fill_kernel<<<ntiles, 256, 0, stream>>>(t->v, m, tile_off, k_in, s_in);
   MEEPO_CUDA_TRY(cudaGetLastError());
   if (n)
     MEEPO_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, cub_bytes, (const uint64_t*)k_in, k_out, (const uint32_t*)s_in,
@@ -223,6 +223,7 @@ meepo_status import_device(meepo_table* t, const uint64_t* keys, const void* row
                            const uint64_t* scores, const uint32_t* steps, uint64_t n, uint8_t* status_out,
                            cudaStream_t stream, uint32_t* slot_buf, uint32_t* new_slots) {
   if (n == 0) return MEEPO_OK;
+  t->cache_valid = false;
   NewList nl{new_slots, &t->dstate->new_count[t->foi_parity]};
   uint32_t* next = &t->dstate->new_count[t->foi_parity ^ 1];
   t->foi_parity ^= 1;

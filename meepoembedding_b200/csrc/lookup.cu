@@ -70,7 +70,7 @@ __device__ __forceinline__ void gather_tile_slow(const TableView& t, uint64_t ke
 template <int CPR, bool INSERT>
 __global__ void __launch_bounds__(256) probe_gather_kernel(TableView t, const uint64_t* __restrict__ keys,
                                                            uint32_t n, uint4* __restrict__ out,
-                                                           uint8_t* __restrict__ status, NewList nl) {
+                                                           uint8_t* __restrict__ status, NewList nl, SlotCache sc) {
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -85,11 +85,15 @@ __global__ void __launch_bounds__(256) probe_gather_kernel(TableView t, const ui
     if (INSERT) {
       pr = probe_find_or_insert(t, key);
     } else if (key_valid(key)) {
-      pr.slot = probe_find(t, key);
+      pr.slot = probe_find<kReadOnly>(t, key);
       pr.status = pr.slot != kNil ? MEEPO_KEY_FOUND : MEEPO_KEY_MISS;
     }
     if (i < n) {
       if (status) status[i] = (uint8_t)pr.status;
+      if (sc.slots) {
+        sc.slots[i] = pr.slot;
+        sc.keys[i] = key;
+      }
       c_hit += pr.status == MEEPO_KEY_FOUND;
       c_miss += pr.status == MEEPO_KEY_MISS;
       c_full += pr.status == MEEPO_KEY_FULL;
@@ -135,7 +139,7 @@ __global__ void publish_kernel(TableView t, const uint32_t* __restrict__ new_slo
   const uint32_t n = *cur;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint32_t s = new_slots[i];
-    t.digests[s] = (uint8_t)digest_of(mix64(t.keys[s]));
+    *tag_ptr(t, s) = (uint8_t)digest_of(mix64(*key_ptr(t, s)));
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     *next = 0;
@@ -169,6 +173,23 @@ meepo_status probe_gather_begin(meepo_table* t, uint64_t n_total, bool insert, c
   t->cur_new.slots = nullptr;
   t->cur_new.count = nullptr;
   t->cur_new_next = nullptr;
+  t->cache_valid = false;
+  t->cache_off = 0;
+  t->cache_n = 0;
+  if (t->cache_enabled && n_total) {
+    if (n_total > t->cache_cap) {
+      MEEPO_CUDA_TRY(cudaStreamSynchronize(stream));
+      cudaFree(t->cache.keys);
+      cudaFree(t->cache.slots);
+      t->cache = SlotCache{nullptr, nullptr};
+      t->cache_cap = 0;
+      const uint64_t cap = n_total + n_total / 8;
+      MEEPO_CUDA_TRY(cudaMalloc(&t->cache.keys, cap * 8));
+      MEEPO_CUDA_TRY(cudaMalloc(&t->cache.slots, cap * 4));
+      t->cache_cap = cap;
+    }
+    t->cache_n = n_total;
+  }
   if (insert && n_total) {
     MEEPO_TRY(t->ws.reserve(Workspace::pad(n_total * 4), stream));
     t->cur_new.slots = t->ws.take<uint32_t>(n_total);
@@ -188,7 +209,14 @@ meepo_status probe_gather_chunk(meepo_table* t, const uint64_t* keys, uint64_t n
   uint32_t n32 = (uint32_t)n;
   uint4* out = reinterpret_cast<uint4*>(rows_out);
   NewList nl{t->cur_new.slots, t->cur_new.count};
-  void* args[] = {&t->v, &keys, &n32, &out, &status_out, &nl};
+  SlotCache sc{nullptr, nullptr};
+  if (t->cache_n) {  // chunks of one call fill consecutive ranges
+    sc.keys = t->cache.keys + t->cache_off;
+    sc.slots = t->cache.slots + t->cache_off;
+    t->cache_off += n;
+    t->cache_valid = t->cache_off == t->cache_n;
+  }
+  void* args[] = {&t->v, &keys, &n32, &out, &status_out, &nl, &sc};
   ProfScope ps(t, insert ? "find_or_insert.probe_gather" : "lookup.probe_gather", stream);
   MEEPO_CUDA_TRY(cudaLaunchKernel(kern, dim3(grid), dim3(256), args, 0, stream));
   return MEEPO_OK;

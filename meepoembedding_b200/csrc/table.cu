@@ -75,6 +75,7 @@ MEEPO_API meepo_status meepo_create(const meepo_config* cfg, meepo_table** out) 
   }
   meepo_table* t = new meepo_table();
   t->cfg = *cfg;
+  t->cache_enabled = getenv("MEEPO_NO_SLOT_CACHE") == nullptr;
   t->device = cfg->device;
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) {
@@ -108,10 +109,8 @@ MEEPO_API meepo_status meepo_create(const meepo_config* cfg, meepo_table** out) 
     return fail(e == cudaErrorMemoryAllocation ? MEEPO_ENOMEM : MEEPO_ECUDA, m);
   };
   cudaError_t e;
-  const size_t ovf_words = (v.num_buckets + 31) / 32;
-  if ((e = cudaMalloc(&v.keys, slots * 8)) != cudaSuccess) return bail(e, "cudaMalloc(keys)");
-  if ((e = cudaMalloc(&v.digests, slots)) != cudaSuccess) return bail(e, "cudaMalloc(digests)");
-  if ((e = cudaMalloc(&v.overflow, ovf_words * 4)) != cudaSuccess) return bail(e, "cudaMalloc(overflow)");
+  const size_t bucket_bytes = (size_t)v.num_buckets * sizeof(BucketLine);
+  if ((e = cudaMalloc(&v.buckets, bucket_bytes)) != cudaSuccess) return bail(e, "cudaMalloc(buckets)");
   if ((e = cudaMalloc(&v.rows, slots * (size_t)t->row_bytes)) != cudaSuccess) return bail(e, "cudaMalloc(rows)");
   if (t->state_bytes &&
       (e = cudaMalloc(&v.state, slots * (size_t)t->state_bytes)) != cudaSuccess)
@@ -122,9 +121,9 @@ MEEPO_API meepo_status meepo_create(const meepo_config* cfg, meepo_table** out) 
     return bail(e, "cudaMalloc(steps)");
   if ((e = cudaMalloc(&t->dstate, sizeof(DeviceState))) != cudaSuccess) return bail(e, "cudaMalloc(dstate)");
   v.counters = t->dstate->counters;
-  if ((e = cudaMemset(v.keys, 0xFF, slots * 8)) != cudaSuccess) return bail(e, "memset");
-  if ((e = cudaMemset(v.digests, 0, slots)) != cudaSuccess) return bail(e, "memset");
-  if ((e = cudaMemset(v.overflow, 0, ovf_words * 4)) != cudaSuccess) return bail(e, "memset");
+  // keys = EMPTY (all ones), then the 16-byte headers (tags + metadata) = 0
+  if ((e = cudaMemset(v.buckets, 0xFF, bucket_bytes)) != cudaSuccess) return bail(e, "memset");
+  if ((e = cudaMemset2D(v.buckets, sizeof(BucketLine), 0, 16, v.num_buckets)) != cudaSuccess) return bail(e, "memset2D");
   if (v.scores && (e = cudaMemset(v.scores, 0, slots * 8)) != cudaSuccess) return bail(e, "memset");
   if (v.steps && (e = cudaMemset(v.steps, 0, slots * 4)) != cudaSuccess) return bail(e, "memset");
   if ((e = cudaMemset(t->dstate, 0, sizeof(DeviceState))) != cudaSuccess) return bail(e, "memset");
@@ -148,15 +147,15 @@ MEEPO_API meepo_status meepo_destroy(meepo_table* t) {
   cudaDeviceSynchronize();
   destroy_host_pipe(t);
   destroy_profiler(t);
-  cudaFree(t->v.keys);
-  cudaFree(t->v.digests);
-  cudaFree(t->v.overflow);
+  cudaFree(t->v.buckets);
   cudaFree(t->v.rows);
   cudaFree(t->v.state);
   cudaFree(t->v.scores);
   cudaFree(t->v.steps);
   cudaFree(t->dstate);
   cudaFree(t->ws.base);
+  cudaFree(t->cache.keys);
+  cudaFree(t->cache.slots);
   if (t->spill_ring) cudaFreeHost(t->spill_ring);
   delete t;
   return MEEPO_OK;

@@ -57,6 +57,15 @@ struct DeviceState {
 
 struct Profiler;
 
+// (key, slot) of every element of the last find_or_insert / lookup batch. apply_gradients on the
+// same keys (the training loop) reuses the slots instead of probing again: one HBM line per key
+// saved. Entries are validated per element (keys[i] == cache.keys[i]); any mutation other than
+// find_or_insert / lookup / apply_gradients invalidates the whole cache.
+struct SlotCache {
+  uint64_t* keys;
+  uint32_t* slots;
+};
+
 struct NewList {
   uint32_t* slots;  // slots claimed by the find_or_insert call in flight
   uint32_t* count;
@@ -80,6 +89,9 @@ struct meepo_table {
   uint32_t foi_parity = 0;
   meepo::NewList cur_new{nullptr, nullptr};
   uint32_t* cur_new_next = nullptr;
+  meepo::SlotCache cache{nullptr, nullptr};
+  uint64_t cache_cap = 0, cache_n = 0, cache_off = 0;
+  bool cache_valid = false, cache_enabled = true;
   uint64_t epoch = 0;
   struct meepo::Profiler* prof = nullptr;  // per-kernel event timing, off unless enabled
   // host-buffer front end (pinned staging + private streams), created lazily

@@ -23,14 +23,21 @@ struct LongSeg {
 };
 
 // ---------------------------------------------------------------------------------------------
-// A1: slot of every key (sort key) + iota (sort value)
+// A1: slot of every key (sort key) + iota (sort value). Keys that the preceding find_or_insert /
+// lookup already resolved (same batch: keys[i] == cache.keys[i]) reuse the cached slot; everything
+// else is probed (one 128-byte bucket line per key).
 __global__ void __launch_bounds__(256) grad_slots_kernel(TableView t, const uint64_t* __restrict__ keys,
                                                          uint32_t n, uint32_t* __restrict__ sort_key,
-                                                         uint32_t* __restrict__ sort_val) {
+                                                         uint32_t* __restrict__ sort_val, SlotCache sc,
+                                                         uint32_t cache_n) {
   uint32_t dropped = 0;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint64_t key = __ldg(keys + i);
-    uint32_t s = key_valid(key) ? probe_find(t, key) : kNil;
+    uint32_t s;
+    if (i < cache_n && __ldg(sc.keys + i) == key)
+      s = __ldg(sc.slots + i);
+    else
+      s = key_valid(key) ? probe_find<kReadOnly>(t, key) : kNil;
     if (s == kNil) {
       s = t.slots;  // sorts after every real slot
       dropped++;
@@ -676,7 +683,8 @@ meepo_status launch_apply_gradients(meepo_table* t, const uint64_t* keys, const 
   {
     ProfScope ps(t, "apply.grad_slots", stream);
     const int grid = grid_for(t, (const void*)grad_slots_kernel, 256, 0, (n + 255) / 256);
-    grad_slots_kernel<<<grid, 256, 0, stream>>>(t->v, keys, (uint32_t)n, w.sk_in, w.sv_in);
+    const uint32_t cache_n = t->cache_valid ? (uint32_t)std::min<uint64_t>(t->cache_n, n) : 0u;
+    grad_slots_kernel<<<grid, 256, 0, stream>>>(t->v, keys, (uint32_t)n, w.sk_in, w.sv_in, t->cache, cache_n);
     MEEPO_CUDA_TRY(cudaGetLastError());
   }
   static const char* const names[4] = {"apply.radix_sort(cub)", "apply.segments(3 kernels)",

@@ -42,7 +42,7 @@ class Model:
     def __init__(self, dim, capacity, dtype=capi.F32, opt=capi.ADAGRAD, lr=0.01, eps=1e-8, beta1=0.9,
                  beta2=0.999, init_accum=0.1, init_scale=0.01, init_seed=0, track=False, spill_tuples=0):
         self.dim, self.dtype, self.opt = dim, dtype, opt
-        self.capacity = (capacity + 31) // 32 * 32
+        self.capacity = (capacity + 13) // 14 * 14
         self.lr, self.eps, self.b1, self.b2 = F(lr), F(eps), F(beta1), F(beta2)
         self.init_accum, self.init_scale, self.seed = F(init_accum), init_scale, init_seed
         self.track = track

@@ -58,7 +58,7 @@ def test_import_buffers_statuses(oracle_lib, cuda_lib):
     import torch
     from gpu_util import DEV, dkeys, drows
 
-    kw = table_kwargs(dim=8, capacity=64, optimizer="adagrad")
+    kw = table_kwargs(dim=8, capacity=70, optimizer="adagrad")
     g, o = Table(lib=cuda_lib, **kw), Table(lib=oracle_lib, **kw)
     rng = np.random.default_rng(0)
     keys = np.arange(1, 101, dtype=np.uint64) * np.uint64(7919)
@@ -69,12 +69,12 @@ def test_import_buffers_statuses(oracle_lib, cuda_lib):
     gst = torch.empty(100, dtype=torch.uint8, device=DEV)
     g.import_buffers(dkeys(keys), drows(rows, "f32"), status_out=gst, n=100)
     gst = gst.cpu().numpy()
-    assert (gst == capi.KEY_INSERTED).sum() == 64 == (ost == capi.KEY_INSERTED).sum()
-    assert (gst == capi.KEY_FULL).sum() == 35 == (ost == capi.KEY_FULL).sum() and gst[10] == capi.KEY_INVALID
+    assert (gst == capi.KEY_INSERTED).sum() == 70 == (ost == capi.KEY_INSERTED).sum()
+    assert (gst == capi.KEY_FULL).sum() == 29 == (ost == capi.KEY_FULL).sum() and gst[10] == capi.KEY_INVALID
     # overwrite what is there
     from gpu_util import gpu_export
     k2 = gpu_export(g)[0]
-    g.import_buffers(dkeys(k2), drows(np.ones((64, 8), np.float32), "f32"), status_out=(s2 := torch.empty(64, dtype=torch.uint8, device=DEV)), n=64)
+    g.import_buffers(dkeys(k2), drows(np.ones((70, 8), np.float32), "f32"), status_out=(s2 := torch.empty(70, dtype=torch.uint8, device=DEV)), n=70)
     assert (s2.cpu().numpy() == capi.KEY_FOUND).all()
     ek, er, es, _, _ = gpu_export(g)
     assert (er == 1.0).all() and np.allclose(es, 0.1) and (ek == k2).all()

@@ -107,15 +107,15 @@ def test_full_table_counts(oracle_lib, cuda_lib):
     from gpu_util import gpu_foi
 
     rng = np.random.default_rng(3)
-    g, o = pair(oracle_lib, cuda_lib, dim=4, capacity=256, optimizer="sgd")
+    g, o = pair(oracle_lib, cuda_lib, dim=4, capacity=252, optimizer="sgd")
     keys = make_keys(rng, 2000, 100000, dup_frac=0.3)
     rows, st = gpu_foi(g, keys, "f32")
     _, ost = o.find_or_insert(keys)
-    assert g.stats()["size"] == 256 == o.stats()["size"]
+    assert g.stats()["size"] == 252 == o.stats()["size"]
     assert (st == capi.KEY_INVALID).sum() == (ost == capi.KEY_INVALID).sum()
     # every distinct valid key got one consistent status; exactly 256 distinct keys are INSERTED
     ins = np.unique(keys[st == capi.KEY_INSERTED])
-    assert ins.size == 256 and not np.isin(keys[st == capi.KEY_FULL], ins).any()
+    assert ins.size == 252 and not np.isin(keys[st == capi.KEY_FULL], ins).any()
     assert (rows[st == capi.KEY_FULL] == 0).all()
     rows2, st2 = gpu_foi(g, keys, "f32")
     assert ((st2 == capi.KEY_FOUND) == (st == capi.KEY_INSERTED)).all()
@@ -137,3 +137,44 @@ def test_two_runs_identical(oracle_lib, cuda_lib):
         outs.append(gpu_foi(g, uk, "f32", insert=False))
     np.testing.assert_array_equal(outs[0][0], outs[1][0])
     np.testing.assert_array_equal(outs[0][1], outs[1][1])
+
+
+def test_slot_cache_paths(oracle_lib, cuda_lib):
+    """apply_gradients reuses the slots of the preceding find_or_insert when keys[i] matches; a
+    permuted / different / longer batch, an intervening lookup or an eviction must all fall back
+    to probing and still give the oracle's result."""
+    from gpu_util import gpu_apply, gpu_foi
+
+    rng = np.random.default_rng(8)
+    dim = 32
+    g, o = pair(oracle_lib, cuda_lib, dim=dim, capacity=1 << 14, dtype="f32", optimizer="adagrad", track_scores=True)
+    universe = keygen.keys_from_ranks(np.arange(1, 6001, dtype=np.uint64), 7)
+
+    def both_apply(k):
+        gr = rng.normal(0, 0.1, size=(k.size, dim)).astype(np.float32)
+        gpu_apply(g, k, gr, "f32"), o.apply_gradients(k, gr)
+
+    for variant in ("same", "permuted", "other", "longer", "after_lookup", "after_evict"):
+        keys = make_keys(rng, 3000, 6000, dup_frac=0.4)
+        gpu_foi(g, keys, "f32"), o.find_or_insert(keys)
+        if variant == "same":
+            both_apply(keys)
+        elif variant == "permuted":
+            both_apply(rng.permutation(keys))
+        elif variant == "other":
+            both_apply(make_keys(rng, 3000, 9000, dup_frac=0.4))
+        elif variant == "longer":
+            both_apply(np.concatenate([keys, make_keys(rng, 500, 6000)]))
+        elif variant == "after_lookup":
+            lk = make_keys(rng, 100, 9000)
+            gpu_foi(g, lk, "f32", insert=False), o.lookup(lk)
+            both_apply(keys)
+        else:
+            assert g.evict("lfu", 0.2) == o.evict("lfu", 0.2)
+            both_apply(keys)  # many of these keys are gone now
+        rows, st = gpu_foi(g, universe, "f32", insert=False)
+        orows, ost = o.lookup(universe)
+        np.testing.assert_array_equal(st, ost, err_msg=variant)
+        np.testing.assert_array_equal(rows, orows, err_msg=variant)
+    gs, os_ = g.stats(), o.stats()
+    assert gs["updates"] == os_["updates"] and gs["grad_dropped"] == os_["grad_dropped"]

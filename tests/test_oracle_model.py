@@ -92,7 +92,7 @@ def test_known_answers(oracle_lib):
 
 
 def test_full_table_and_sentinels(oracle_lib):
-    t, m = make_pair(oracle_lib, dim=4, capacity=64, optimizer="sgd")
+    t, m = make_pair(oracle_lib, dim=4, capacity=70, optimizer="sgd")
     rng = np.random.default_rng(5)
     keys = make_keys(rng, 200, 10_000, dup_frac=0.2)
     rows, st_ = t.find_or_insert(keys)
@@ -100,7 +100,7 @@ def test_full_table_and_sentinels(oracle_lib):
     np.testing.assert_array_equal(st_, mst)
     np.testing.assert_array_equal(rows, mrows)
     assert (st_ == capi.KEY_FULL).any() and (st_ == capi.KEY_INVALID).sum() == 2
-    assert t.stats()["size"] == 64
+    assert t.stats()["size"] == 70
     # empty batch is legal
     t.find_or_insert(np.empty(0, dtype=np.uint64))
     m.find_or_insert(np.empty(0, dtype=np.uint64))
