@@ -100,10 +100,14 @@ __device__ __forceinline__ void st_stream(uint4* p, uint4 v) {
 }
 
 // --- bucket line -------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t* key_ptr(const TableView& t, uint32_t slot) {
+// TB = anything with {BucketLine* buckets; uint32_t num_buckets; unsigned long long* counters;}: the
+// local TableView, or a peer shard reached over NVLink (peer.cu).
+template <typename TB>
+__device__ __forceinline__ uint64_t* key_ptr(const TB& t, uint32_t slot) {
   return &t.buckets[slot / kBucket].key[slot % kBucket];
 }
-__device__ __forceinline__ uint8_t* tag_ptr(const TableView& t, uint32_t slot) {
+template <typename TB>
+__device__ __forceinline__ uint8_t* tag_ptr(const TB& t, uint32_t slot) {
   return &t.buckets[slot / kBucket].tag[slot % kBucket];
 }
 // 4 tag bytes -> 4 mask bits (bit i set if byte i of `w` equals the tag replicated in `pat`).
@@ -116,13 +120,13 @@ __device__ __forceinline__ uint32_t bytes_eq4(uint32_t w, uint32_t pat) {
 // kReadOnly (ld.global.nc, L1-cached): lookup / apply_gradients / evict probes — nothing in the
 // bucket array is written while they run, and hot Zipf keys are served by L1.
 enum : int { kCoherent = 0, kReadOnly = 1 };
-template <int LD>
-__device__ __forceinline__ uint4 load_header(const TableView& t, uint32_t b) {
+template <int LD, typename TB>
+__device__ __forceinline__ uint4 load_header(const TB& t, uint32_t b) {
   const uint4* p = reinterpret_cast<const uint4*>(&t.buckets[b]);
   return LD == kReadOnly ? __ldg(p) : __ldcg(p);
 }
-template <int LD>
-__device__ __forceinline__ uint64_t load_key(const TableView& t, uint32_t b, uint32_t i) {
+template <int LD, typename TB>
+__device__ __forceinline__ uint64_t load_key(const TB& t, uint32_t b, uint32_t i) {
   const uint64_t* p = &t.buckets[b].key[i];
   return LD == kReadOnly ? __ldg(p) : __ldcg(p);
 }
@@ -134,8 +138,8 @@ __device__ __forceinline__ uint32_t match_mask(const uint4& h, uint32_t tag) {
 __device__ __forceinline__ bool overflowed(const uint4& h) { return (h.w >> 16) & 1u; }
 
 // Slot of `key` or kNil, starting at bucket b with the header already in registers.
-template <int LD>
-__device__ __forceinline__ uint32_t probe_from(const TableView& t, uint64_t key, uint32_t tag, uint32_t b, uint4 hdr) {
+template <int LD, typename TB>
+__device__ __forceinline__ uint32_t probe_from(const TB& t, uint64_t key, uint32_t tag, uint32_t b, uint4 hdr) {
   for (uint32_t p = 0; p < t.num_buckets; ++p) {
     uint32_t m = match_mask(hdr, tag);
     while (m) {
@@ -150,8 +154,8 @@ __device__ __forceinline__ uint32_t probe_from(const TableView& t, uint64_t key,
   return kNil;
 }
 // Probe without insertion. One HBM line per bucket visited.
-template <int LD = kCoherent>
-__device__ __forceinline__ uint32_t probe_find(const TableView& t, uint64_t key) {
+template <int LD = kCoherent, typename TB>
+__device__ __forceinline__ uint32_t probe_find(const TB& t, uint64_t key) {
   const uint64_t h = mix64(key);
   const uint32_t b = bucket_of(h, t.num_buckets);
   return probe_from<LD>(t, key, digest_of(h), b, load_header<LD>(t, b));
@@ -167,7 +171,8 @@ struct Probe {
 // written here (publish_kernel does it afterwards), so every thread sees the same free-slot set
 // per bucket and walks it in the same order: a key can only ever land in one slot, and "found by
 // tag" == "was present when the call started" (meepo.h "Status").
-__device__ __forceinline__ Probe probe_find_or_insert(const TableView& t, uint64_t key) {
+template <typename TB>
+__device__ __forceinline__ Probe probe_find_or_insert(const TB& t, uint64_t key) {
   Probe r{kNil, MEEPO_KEY_INVALID, false};
   if (!key_valid(key)) return r;
   uint32_t s = probe_find<kCoherent>(t, key);
