@@ -218,6 +218,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N>1: fused peer-memory verbs (csrc/peer.cu) or the NCCL all-to-all composition")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "meepo" else args.warmup
 
@@ -270,7 +272,7 @@ def main():
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
     if world > 1:
-        from meepoembedding_b200.sharded import ShardedTable
+        from meepoembedding_b200.sharded import PeerShardedTable, ShardedTable
 
     R = w["dim"] * esize(w["dtype"])
     B = w["batch"]
@@ -280,7 +282,15 @@ def main():
     stream = torch.cuda.current_stream()
     sp = stream.cuda_stream
     if world > 1:
-        sharded = ShardedTable(table, dist_.group.WORLD, dev)
+        if args.exchange == "peer":
+            # one (sender, owner) lane holds the unique keys one rank sends one owner: B/world on average
+            region = min(w["batch"], int(w["batch"] / world * 1.25) + 4096)
+            sharded = PeerShardedTable(table, dist_.group.WORLD, dev, max_batch=w["batch"], region_keys=region)
+            config["exchange"] = ("fused peer-memory verbs over NVLink (cudaIpc windows, device-side barriers, "
+                                  f"no NCCL on the data path); region_keys={region}")
+        else:
+            sharded = ShardedTable(table, dist_.group.WORLD, dev)
+            config["exchange"] = "NCCL all_to_all_single (torch.distributed)"
 
     # prefill: ranks 1..table_keys*world, each rank inserts the keys it owns
     rows_out = torch.empty((B, w["dim"]), dtype=tdt, device=dev)
@@ -328,7 +338,8 @@ def main():
     for i in range(args.warmup):
         step(i)
     barrier()
-    upd0 = table.stats()["updates"]
+    st0 = table.stats()
+    upd0 = st0["updates"]
     table.profile(True)
     clocks = ClockSampler(local_rank)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -355,6 +366,13 @@ def main():
     # ---- roofline of the dominant kernel group (CUDA events on the launch stream, inside the timed region)
     peak, peak_src = load_peaks()
     alg = algorithmic_bytes(w, B, U_avg)
+    if world > 1:  # owner-side kernels of the sharded verbs: entries actually received by this rank
+        kr = (st1["peer_keys_received"] - st0["peer_keys_received"]) / args.steps
+        gr = (st1["peer_grads_received"] - st0["peer_grads_received"]) / args.steps
+        alg["sharded.owner_find_or_insert"] = kr * (16 + 2 * R)
+        alg["sharded.owner_apply"] = gr * R + U_avg * (2 * R + 2 * w["dim"] * 4)
+        alg["sharded.push_grads"] = gr * 2 * R
+        alg["sharded.expand"] = B * 2 * R
     kernels = {}
     for name, (cnt, ms) in prof.items():
         avg = ms / max(cnt, 1)
@@ -430,6 +448,8 @@ def main():
                           "unique_per_batch": U_avg, "inserted_during_bench": st1["size"] - size0}}
         print(json.dumps(line))
     if world > 1:
+        if args.exchange == "peer":
+            sharded.close()
         dist_.destroy_process_group()
     return 0
 

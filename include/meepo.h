@@ -108,6 +108,8 @@ extern "C" {
 #define MEEPO_REDUCE_LEAF 256u
 #define MEEPO_BUCKET_SLOTS 14u /* slots per 128-byte bucket line; capacity is rounded up to it */
 #define MEEPO_OWNER_SALT 0xD6E8FEB86659FD93ull
+#define MEEPO_MAX_PEERS 8u        /* shards of one sharded table (the GPUs of one NVSwitch box) */
+#define MEEPO_PEER_BLOB_BYTES 256u /* size of the opaque per-rank blob of meepo_peer_prepare */
 
 typedef struct meepo_table meepo_table; /* opaque */
 
@@ -164,6 +166,8 @@ typedef struct {
   uint64_t epoch;        /* batch epoch */
   uint64_t overflow_buckets; /* buckets whose overflow flag is set */
   uint64_t row_bytes, state_bytes; /* per slot */
+  uint64_t peer_keys_received;  /* sharded forward verbs: (sender, key) entries this owner served */
+  uint64_t peer_grads_received; /* sharded apply_gradients: (sender, key) gradient rows received */
 } meepo_stats_t;
 
 /* --- life cycle (synchronous) ------------------------------------------- */
@@ -270,6 +274,48 @@ MEEPO_API meepo_status meepo_reduce_duplicates(meepo_table* t, const uint64_t* k
  * 0xFFFFFFFF writes a zero row. */
 MEEPO_API meepo_status meepo_gather_rows(meepo_table* t, const void* rows_in, const uint32_t* index,
                                          uint64_t n, void* rows_out, void* stream);
+
+/* --- sharded verbs fused with their exchange over NVLink peer memory ------- *
+ * One table per GPU (one process per GPU, or several tables driven by one
+ * process), rank r owns the keys with meepo_owner(key, world) == r. Set-up:
+ *   1. every rank: meepo_peer_prepare(t, rank, world, max_batch, region_keys,
+ *      blob) allocates this rank's exchange window and fills `blob`
+ *      (MEEPO_PEER_BLOB_BYTES, opaque; carries a CUDA IPC handle);
+ *   2. the caller all-gathers the blobs (any transport; they are plain bytes);
+ *   3. every rank: meepo_peer_attach(t, blobs) with the world blobs in rank
+ *      order maps the peers' windows.
+ * The three verbs are COLLECTIVE: every rank calls the same verb in the same
+ * order (n may differ per rank and may be 0). They are stream-ordered and
+ * asynchronous like the single-table verbs and do not synchronise with the
+ * host; ranks meet in device-side flag barriers. Semantics are those of ONE
+ * table fed the concatenation of all ranks' batches: a key that is new in the
+ * collective call reports MEEPO_KEY_INSERTED on every rank; apply_gradients
+ * first sums each rank's duplicate gradients (fixed-shape tree, rounded to the
+ * table dtype — meepo_reduce_duplicates), then adds the ranks' partial sums in
+ * rank order and performs one optimizer step per key.
+ *   max_batch    largest n any call will pass on this rank
+ *   region_keys  capacity of one (sender, owner) lane of the window in unique
+ *                keys; 0 = max_batch (always sufficient). A smaller value
+ *                (e.g. 1.25 * max_batch / world) saves window memory
+ *                (2 * world * region_keys * row_bytes); exceeding it is
+ *                reported by meepo_stats as MEEPO_ENCCL, never a memory error.
+ * A rank that does not reach a barrier within MEEPO_PEER_TIMEOUT_MS (env,
+ * default 20000) makes its peers give up and report MEEPO_ENCCL from
+ * meepo_stats instead of hanging the GPU. All ranks must have finished (e.g. a
+ * host barrier) before any of them calls meepo_peer_detach / meepo_destroy.
+ * The oracle library exports these symbols and returns MEEPO_EINVAL: the
+ * checker for the sharded verbs is ONE oracle table fed the concatenated
+ * batches (tests/test_gpu_peer.py). */
+MEEPO_API meepo_status meepo_peer_prepare(meepo_table* t, uint32_t rank, uint32_t world, uint64_t max_batch,
+                                          uint64_t region_keys, void* blob_out);
+MEEPO_API meepo_status meepo_peer_attach(meepo_table* t, const void* blobs);
+MEEPO_API meepo_status meepo_peer_detach(meepo_table* t);
+MEEPO_API meepo_status meepo_sharded_find_or_insert(meepo_table* t, const uint64_t* keys, uint64_t n,
+                                                    void* rows_out, uint8_t* status_out, void* stream);
+MEEPO_API meepo_status meepo_sharded_lookup(meepo_table* t, const uint64_t* keys, uint64_t n,
+                                            void* rows_out, uint8_t* found_out, void* stream);
+MEEPO_API meepo_status meepo_sharded_apply_gradients(meepo_table* t, const uint64_t* keys,
+                                                     const void* grads, uint64_t n, void* stream);
 
 #ifdef __cplusplus
 }

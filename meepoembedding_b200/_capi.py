@@ -27,6 +27,8 @@ FLAG_TRACK_SCORES = 1
 KEY_EMPTY = 0xFFFFFFFFFFFFFFFF
 KEY_RESERVED = 0xFFFFFFFFFFFFFFFE
 REDUCE_LEAF = 256
+MAX_PEERS = 8
+PEER_BLOB_BYTES = 256
 ABI_VERSION = 1
 
 
@@ -69,6 +71,8 @@ class Stats(C.Structure):
             "overflow_buckets",
             "row_bytes",
             "state_bytes",
+            "peer_keys_received",
+            "peer_grads_received",
         )
     ]
 
@@ -106,6 +110,12 @@ SIGNATURES = {
     "meepo_shard_partition": (C.c_int, [_P, _P, _U64, _U32, _P, _P, _P, _P]),
     "meepo_reduce_duplicates": (C.c_int, [_P, _P, _P, _U64, _P, _P, _P, _P, _P]),
     "meepo_gather_rows": (C.c_int, [_P, _P, _P, _U64, _P, _P]),
+    "meepo_peer_prepare": (C.c_int, [_P, _U32, _U32, _U64, _U64, _P]),
+    "meepo_peer_attach": (C.c_int, [_P, _P]),
+    "meepo_peer_detach": (C.c_int, [_P]),
+    "meepo_sharded_find_or_insert": (C.c_int, [_P, _P, _U64, _P, _P, _P]),
+    "meepo_sharded_lookup": (C.c_int, [_P, _P, _U64, _P, _P, _P]),
+    "meepo_sharded_apply_gradients": (C.c_int, [_P, _P, _P, _U64, _P]),
 }
 
 

@@ -29,7 +29,7 @@ constexpr uint32_t kBucket = MEEPO_BUCKET_SLOTS;  // 14
 constexpr uint32_t kNil = 0xFFFFFFFFu;
 
 enum Counter : int {
-  C_SIZE = 0, C_INSERTS, C_HITS, C_MISSES, C_FULL, C_EVICTIONS, C_UPDATES, C_DROPPED, C_OVERFLOW, C_COUNT
+  C_SIZE = 0, C_INSERTS, C_HITS, C_MISSES, C_FULL, C_EVICTIONS, C_UPDATES, C_DROPPED, C_OVERFLOW, C_PEER_KEYS, C_PEER_GRADS, C_COUNT
 };
 
 struct __align__(128) BucketLine {

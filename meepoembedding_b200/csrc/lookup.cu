@@ -1,71 +1,8 @@
-// lookup.cu — find_or_insert / lookup: fused probe + row gather.
-//
-// One warp owns a tile of 32 consecutive batch keys.
-//   probe   lane i resolves key i on its own: one 32-byte tag sector, SIMD compare in registers,
-//           one 8-byte key compare per tag hit; on a miss (find_or_insert only) a 64-bit CAS on
-//           the first free slot of the bucket. 32 independent probes in flight per warp.
-//   gather  the warp then streams the 32 rows as one flat array of 16-byte chunks: chunk c of the
-//           tile belongs to key c / CPR, so every warp instruction moves 512 contiguous-per-row
-//           bytes, fully coalesced on both the arena and the output side, UNROLL loads in flight
-//           per lane before the first store.
-// Rows of keys that are new in this batch are never read from the arena: every duplicate
-// computes init_chunk(key) itself (pure function), only the CAS winner writes it back.
-#include "table.h"
+// lookup.cu — find_or_insert / lookup: fused probe + row gather. The per-tile body
+// lives in probe_gather.cuh; this file is the single-table kernel, the tag publish pass and the verbs.
+#include "probe_gather.cuh"
 
 namespace meepo {
-
-template <int CPR>
-__device__ __forceinline__ void gather_tile_fast(const TableView& t, uint32_t slot, uint32_t tile_keys,
-                                                 uint4* __restrict__ out_tile, uint32_t lane) {
-  constexpr int UNROLL = CPR >= 8 ? 8 : CPR;
-  // chunk c = it*32 + lane; key j = c / CPR; offset = c % CPR
-#pragma unroll 1
-  for (int it0 = 0; it0 < CPR; it0 += UNROLL) {
-    uint4 v[UNROLL];
-    uint32_t jj[UNROLL];
-#pragma unroll
-    for (int u = 0; u < UNROLL; u++) {
-      const uint32_t c = (uint32_t)(it0 + u) * 32u + lane;
-      const uint32_t j = c / CPR, off = c % CPR;
-      const uint32_t s = __shfl_sync(0xFFFFFFFFu, slot, j);
-      jj[u] = j;
-      v[u] = make_uint4(0, 0, 0, 0);
-      if (s != kNil) v[u] = ld_stream(t.rows + (size_t)s * CPR + off);
-    }
-#pragma unroll
-    for (int u = 0; u < UNROLL; u++) {
-      const uint32_t c = (uint32_t)(it0 + u) * 32u + lane;
-      if (jj[u] < tile_keys) st_stream(out_tile + c, v[u]);
-    }
-  }
-}
-
-// Generic-width version (any cpr), also the path for tiles that contain freshly inserted keys.
-__device__ __forceinline__ void gather_tile_slow(const TableView& t, uint64_t key, const Probe& pr,
-                                                 uint32_t tile_keys, uint4* __restrict__ out_tile,
-                                                 uint32_t lane) {
-  const uint32_t cpr = t.cpr;
-  for (uint32_t j = 0; j < tile_keys; j++) {
-    const uint32_t s = __shfl_sync(0xFFFFFFFFu, pr.slot, j);
-    const uint32_t st = __shfl_sync(0xFFFFFFFFu, pr.status, j);
-    const bool win = __shfl_sync(0xFFFFFFFFu, (int)pr.winner, j);
-    const uint64_t kj = __shfl_sync(0xFFFFFFFFu, key, j);
-    for (uint32_t off = lane; off < cpr; off += 32) {
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (st == MEEPO_KEY_INSERTED) {
-        v = init_chunk(t, kj, off);
-        if (win) t.rows[(size_t)s * cpr + off] = v;
-      } else if (s != kNil) {
-        v = ld_stream(t.rows + (size_t)s * cpr + off);
-      }
-      st_stream(out_tile + (size_t)j * cpr + off, v);
-    }
-    if (win) {
-      const uint4 sv = init_state_chunk(t);
-      for (uint32_t off = lane; off < t.scpr; off += 32) t.state[(size_t)s * t.scpr + off] = sv;
-    }
-  }
-}
 
 template <int CPR, bool INSERT>
 __global__ void __launch_bounds__(256) probe_gather_kernel(TableView t, const uint64_t* __restrict__ keys,
@@ -76,59 +13,16 @@ __global__ void __launch_bounds__(256) probe_gather_kernel(TableView t, const ui
   const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
   const uint32_t ntiles = (n + 31u) >> 5;
   const uint32_t cpr = CPR > 0 ? (uint32_t)CPR : t.cpr;
-  uint32_t c_hit = 0, c_miss = 0, c_full = 0;
+  TileCounts cnt;
   for (uint32_t tile = warp; tile < ntiles; tile += nwarps) {
     const uint32_t i = tile * 32u + lane;
     const uint32_t tile_keys = min(32u, n - tile * 32u);
     const uint64_t key = i < n ? __ldg(keys + i) : MEEPO_KEY_EMPTY;
-    Probe pr{kNil, MEEPO_KEY_INVALID, false};
-    if (INSERT) {
-      pr = probe_find_or_insert(t, key);
-    } else if (key_valid(key)) {
-      pr.slot = probe_find<kReadOnly>(t, key);
-      pr.status = pr.slot != kNil ? MEEPO_KEY_FOUND : MEEPO_KEY_MISS;
-    }
-    if (i < n) {
-      if (status) status[i] = (uint8_t)pr.status;
-      if (sc.slots) {
-        sc.slots[i] = pr.slot;
-        sc.keys[i] = key;
-      }
-      c_hit += pr.status == MEEPO_KEY_FOUND;
-      c_miss += pr.status == MEEPO_KEY_MISS;
-      c_full += pr.status == MEEPO_KEY_FULL;
-      if (t.scores && pr.slot != kNil) {  // meepo.h "Evict": freq += 1, last_epoch = epoch
-        atomicAdd(&t.scores[pr.slot].x, 1u);
-        t.scores[pr.slot].y = t.epoch;
-      }
-    }
-    uint4* out_tile = out + (size_t)tile * 32u * cpr;
-    bool fresh = false;
-    if (INSERT) {
-      const unsigned wm = __ballot_sync(0xFFFFFFFFu, pr.winner);
-      if (wm) {  // list the claimed slots for publish_kernel (one atomic per warp)
-        const int leader = __ffs(wm) - 1;
-        uint32_t base = 0;
-        if ((int)lane == leader) base = atomicAdd(nl.count, (uint32_t)__popc(wm));
-        base = __shfl_sync(0xFFFFFFFFu, base, leader);
-        if (pr.winner) nl.slots[base + __popc(wm & ((1u << lane) - 1u))] = pr.slot;
-      }
-      fresh = __any_sync(0xFFFFFFFFu, pr.status == MEEPO_KEY_INSERTED);
-    }
-    if (CPR > 0 && !fresh)
-      gather_tile_fast<(CPR > 0 ? CPR : 1)>(t, pr.slot, tile_keys, out_tile, lane);
-    else
-      gather_tile_slow(t, key, pr, tile_keys, out_tile, lane);
+    probe_gather_tile<CPR, INSERT>(t, key, i < n, tile_keys, out + (size_t)tile * 32u * cpr,
+                                   status ? status + i : nullptr, sc.slots ? sc.slots + i : nullptr,
+                                   sc.keys ? sc.keys + i : nullptr, 1u, nl, cnt, lane);
   }
-  // stats: one atomic per warp per counter for the whole launch
-  c_hit = __reduce_add_sync(0xFFFFFFFFu, c_hit);
-  c_miss = __reduce_add_sync(0xFFFFFFFFu, c_miss);
-  c_full = __reduce_add_sync(0xFFFFFFFFu, c_full);
-  if (lane == 0) {
-    if (c_hit) atomicAdd(t.counters + C_HITS, (unsigned long long)c_hit);
-    if (c_miss) atomicAdd(t.counters + C_MISSES, (unsigned long long)c_miss);
-    if (c_full) atomicAdd(t.counters + C_FULL, (unsigned long long)c_full);
-  }
+  flush_tile_counts(t, cnt, lane);
 }
 
 // Writes the tags of the slots claimed by the preceding probe_gather_kernel<.., true> and folds the

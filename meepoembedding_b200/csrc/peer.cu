@@ -1,0 +1,851 @@
+// peer.cu — the key-hash-sharded verbs fused with their exchange over NVLink peer memory
+// (SURVEY rows a4 / e; include/meepo.h "sharded verbs"). One process per GPU; every rank owns the
+// keys with owner(key, world) == rank and exposes ONE exchange window (cudaIpc) that its peers
+// store into directly. No NCCL call, no host synchronisation and no staging copy on the data path:
+//
+//   find_or_insert / lookup (requester r, owner o)
+//     r: dedup the batch                              -> unique keys, inverse, occurrences
+//     r: push_keys      key -> o.recv_keys[r][p]      8 B per unique key over NVLink (p = arrival order)
+//     barrier (delivers the per-pair counts)
+//     o: owner_probe_gather  probe the LOCAL table (same tile body as the single-table kernel) and
+//                            store each row straight into r.ret_rows[o][p] over NVLink; tags of the
+//                            slots claimed in this call are published afterwards, locally
+//     barrier
+//     r: expand         rows_out[i] = ret_rows[loc[inverse[i]]]
+//   apply_gradients
+//     r: dedup + fixed-shape pre-reduction of duplicate gradients (rounded to the table dtype)
+//     r: push_grads     (key, summed gradient row) -> o.recv_*[r][p], rows stored over NVLink
+//     barrier
+//     o: group the received entries by slot in an L2-resident scratch table (one cell per key, a
+//        bitmask of contributing senders, contrib[cell][sender] = entry) and apply ONE optimizer
+//        step per key with the senders' partial sums added in rank order — deterministic, no sort
+//     barrier
+//
+// Only bulk stores and the barrier flags cross NVLink: every table mutation (CAS insert, tag
+// publish, optimizer step) is done by the owner on its own HBM. Every count that depends on the
+// data (unique keys, keys per owner, received entries) stays on the device: grids are persistent
+// and read their bounds from device memory, so a verb is one uninterrupted stream of launches.
+#include <unistd.h>
+
+#include <cstring>
+
+#include "optimizer.cuh"
+#include "probe_gather.cuh"
+
+namespace meepo {
+
+constexpr uint32_t kMaxPeers = MEEPO_MAX_PEERS;
+constexpr uint32_t kBlobMagic = 0x4D50454Bu;  // "MPEK"
+constexpr size_t kWindowHeader = 4096;
+
+enum PeerError : uint32_t { PE_TIMEOUT = 1u, PE_REGION_OVERFLOW = 2u };
+
+// A rank's exchange window as seen through a (peer or local) mapping.
+struct PeerWindow {
+  unsigned long long* flags;  // [kMaxPeers] barrier sequence number last signalled by each source
+  uint32_t* recv_cnt;         // [kMaxPeers] entries source s pushed in the current phase
+  uint32_t* error;            // sticky PeerError bits
+  uint64_t* recv_keys;        // [world][region]      keys pushed by source s
+  uint32_t* recv_occ;         // [world][region]      batch occurrences behind each pushed key
+  uint4* recv_grads;          // [world][region][cpr] pre-reduced gradient rows pushed by source s
+  uint4* ret_rows;            // [world][region][cpr] rows returned by owner o for my p-th key to it
+  uint8_t* ret_status;        // [world][region]
+};
+
+struct PeerSet {
+  PeerWindow w[kMaxPeers];
+  uint32_t world, rank, region, cpr;
+};
+
+// Device-resident bookkeeping of the owner side of one phase (filled by the barrier kernel).
+struct PeerWork {
+  uint32_t cnt[kMaxPeers];           // entries received from source s
+  uint32_t recv_off[kMaxPeers + 1];  // exclusive prefix of cnt
+  uint32_t tile_off[kMaxPeers + 1];  // exclusive prefix of ceil(cnt / 32)
+  uint32_t mask;                     // group table size - 1 (power of two >= 2 * received entries)
+  uint32_t n_groups;                 // unique keys among the received entries
+  uint32_t pad[2];
+};
+
+struct PeerBlob {  // what ranks hand each other (opaque to the caller, MEEPO_PEER_BLOB_BYTES)
+  uint32_t magic, abi;
+  int32_t pid, device;
+  uint32_t rank, world;
+  uint64_t region, max_batch;
+  uint32_t dim, dtype, opt, flags;
+  uint64_t window_bytes;
+  uint64_t raw_ptr;
+  cudaIpcMemHandle_t handle;
+};
+static_assert(sizeof(PeerBlob) <= MEEPO_PEER_BLOB_BYTES, "blob too large");
+
+struct PeerState {
+  bool attached = false;
+  uint32_t world = 0, rank = 0;
+  uint64_t max_batch = 0, region = 0;
+  char* window = nullptr;  // this rank's exchange window (IPC-exported)
+  size_t window_bytes = 0;
+  char* local = nullptr;   // private scratch
+  uint32_t* send_cnt = nullptr;
+  PeerWork* work = nullptr;
+  uint32_t* loc = nullptr;         // [max_batch]     window position of unique key u: owner * region + p
+  uint2* cells = nullptr;          // [m_max]         {slot, sender bitmask}
+  uint32_t* contrib = nullptr;     // [m_max][world]  entry index of sender s for this cell
+  uint32_t* group_list = nullptr;  // [world*region]  occupied cells
+  uint64_t m_max = 0;
+  PeerSet ps{};
+  void* opened[kMaxPeers] = {};
+  unsigned long long seq = 0;
+  unsigned long long timeout_ns = 20ull * 1000000000ull;
+};
+
+static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// Offsets are a pure function of (world, region, cpr), hence identical on every rank.
+static void carve_window(char* base, uint32_t world, uint64_t region, uint32_t cpr, PeerWindow& w, size_t* total) {
+  size_t off = 0;
+  w.flags = reinterpret_cast<unsigned long long*>(base + off);
+  w.recv_cnt = reinterpret_cast<uint32_t*>(base + off + 128);
+  w.error = reinterpret_cast<uint32_t*>(base + off + 256);
+  off += kWindowHeader;
+  const size_t cells = (size_t)world * region;
+  w.recv_keys = reinterpret_cast<uint64_t*>(base + off);
+  off += align_up(cells * 8);
+  w.recv_occ = reinterpret_cast<uint32_t*>(base + off);
+  off += align_up(cells * 4);
+  w.recv_grads = reinterpret_cast<uint4*>(base + off);
+  off += align_up(cells * cpr * 16);
+  w.ret_rows = reinterpret_cast<uint4*>(base + off);
+  off += align_up(cells * cpr * 16);
+  w.ret_status = reinterpret_cast<uint8_t*>(base + off);
+  off += align_up(cells);
+  if (total) *total = off;
+}
+
+// --- system-scope flag accesses ----------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// data another GPU stored into this rank's window: read at L2 (the point of coherence), never L1
+__device__ __forceinline__ uint64_t ld_window(const uint64_t* p) { return __ldcg(p); }
+__device__ __forceinline__ uint32_t ld_window(const uint32_t* p) { return __ldcg(p); }
+
+// --- barrier -----------------------------------------------------------------------------------
+// All-to-all flag barrier between kernels: thread j delivers this rank's count for peer j, releases
+// sequence number `seq` into j's window and then waits until j's number has arrived here. Bounded:
+// a peer that never shows up sets PE_TIMEOUT instead of hanging the GPU.
+__global__ void __launch_bounds__(32) peer_barrier_kernel(const __grid_constant__ PeerSet ps, unsigned long long seq,
+                                                          const uint32_t* send_cnt, PeerWork* work, int for_apply,
+                                                          unsigned long long* counters,
+                                                          unsigned long long timeout_ns) {
+  const uint32_t j = threadIdx.x;
+  if (j < ps.world) {
+    if (send_cnt) ps.w[j].recv_cnt[ps.rank] = min(send_cnt[j], ps.region);
+    __threadfence_system();
+    st_release_sys(ps.w[j].flags + ps.rank, seq);
+    const unsigned long long* mine = ps.w[ps.rank].flags + j;
+    const unsigned long long t0 = global_timer_ns();
+    while (ld_acquire_sys(mine) < seq) {
+      if (global_timer_ns() - t0 > timeout_ns) {
+        atomicOr(ps.w[ps.rank].error, (uint32_t)PE_TIMEOUT);
+        break;
+      }
+      __nanosleep(64);
+    }
+  }
+  __syncthreads();
+  if (work && threadIdx.x == 0) {
+    uint32_t ro = 0, to = 0;
+    for (uint32_t s = 0; s < ps.world; s++) {
+      const uint32_t c = send_cnt ? ld_window(ps.w[ps.rank].recv_cnt + s) : 0u;
+      work->cnt[s] = c;
+      work->recv_off[s] = ro;
+      work->tile_off[s] = to;
+      ro += c;
+      to += (c + 31u) >> 5;
+    }
+    work->recv_off[ps.world] = ro;
+    work->tile_off[ps.world] = to;
+    uint32_t m = 1024;
+    while (m < 2u * ro) m <<= 1;
+    work->mask = for_apply ? m - 1 : 0u;
+    work->n_groups = 0;
+    if (ro) atomicAdd(counters + (for_apply ? C_PEER_GRADS : C_PEER_KEYS), (unsigned long long)ro);
+  }
+}
+
+// --- requester: push -----------------------------------------------------------------------------
+// p = arrival position of this lane's key at owner o (one atomic per distinct owner per warp)
+__device__ __forceinline__ uint32_t claim_position(uint32_t* send_cnt, uint32_t o, unsigned active, uint32_t lane) {
+  const unsigned peers = __match_any_sync(active, o);
+  const int leader = __ffs(peers) - 1;
+  uint32_t base = 0;
+  if ((int)lane == leader) base = atomicAdd(send_cnt + o, (uint32_t)__popc(peers));
+  base = __shfl_sync(peers, base, leader);
+  return base + __popc(peers & ((1u << lane) - 1u));
+}
+
+__global__ void __launch_bounds__(256) push_keys_kernel(const __grid_constant__ PeerSet ps,
+                                                        const uint64_t* __restrict__ ukeys,
+                                                        const uint32_t* __restrict__ uocc,
+                                                        const unsigned long long* __restrict__ n_unique,
+                                                        uint32_t* __restrict__ send_cnt, uint32_t* __restrict__ loc) {
+  const uint32_t n = (uint32_t)*n_unique;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
+    const uint32_t u = base + lane;
+    const bool act = u < n;
+    const unsigned am = __ballot_sync(0xFFFFFFFFu, act);
+    if (!act) continue;
+    const uint64_t key = __ldg(ukeys + u);
+    const uint32_t o = owner_of(key, ps.world);
+    const uint32_t p = claim_position(send_cnt, o, am, lane);
+    if (p >= ps.region) {
+      atomicOr(ps.w[ps.rank].error, (uint32_t)PE_REGION_OVERFLOW);
+      loc[u] = kNil;
+      continue;
+    }
+    const size_t e = (size_t)ps.rank * ps.region + p;
+    ps.w[o].recv_keys[e] = key;
+    ps.w[o].recv_occ[e] = uocc ? __ldg(uocc + u) : 1u;
+    loc[u] = o * ps.region + p;
+  }
+}
+
+// (key, pre-reduced gradient row) of every unique key -> the owner's window. A warp owns 32
+// consecutive unique keys: the source rows are one contiguous block, the destination rows are
+// whole rows in the owner's region; 4 x 16-byte loads in flight per lane.
+__global__ void __launch_bounds__(256) push_grads_kernel(const __grid_constant__ PeerSet ps,
+                                                         const uint64_t* __restrict__ ukeys,
+                                                         const uint4* __restrict__ ugrads,
+                                                         const unsigned long long* __restrict__ n_unique,
+                                                         uint32_t* __restrict__ send_cnt) {
+  const uint32_t n = (uint32_t)*n_unique;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t ntiles = (n + 31u) >> 5;
+  const uint32_t cpr = ps.cpr;
+  for (uint32_t tile = warp; tile < ntiles; tile += nwarps) {
+    const uint32_t u = tile * 32u + lane;
+    const bool act = u < n;
+    const unsigned am = __ballot_sync(0xFFFFFFFFu, act);
+    unsigned long long dst = 0;
+    if (act) {
+      const uint64_t key = __ldg(ukeys + u);
+      const uint32_t o = owner_of(key, ps.world);
+      const uint32_t p = claim_position(send_cnt, o, am, lane);
+      if (p < ps.region) {
+        const size_t e = (size_t)ps.rank * ps.region + p;
+        ps.w[o].recv_keys[e] = key;
+        dst = reinterpret_cast<unsigned long long>(ps.w[o].recv_grads + e * cpr);
+      } else {
+        atomicOr(ps.w[ps.rank].error, (uint32_t)PE_REGION_OVERFLOW);
+      }
+    }
+    const uint32_t chunks = min(32u, n - tile * 32u) * cpr;
+    const uint4* src = ugrads + (size_t)tile * 32u * cpr;
+    for (uint32_t c0 = 0; c0 < chunks; c0 += 128) {
+      uint4 v[4];
+      uint4* d[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const uint32_t c = c0 + k * 32 + lane;
+        const uint32_t j = min(c / cpr, 31u);
+        uint4* row = reinterpret_cast<uint4*>(__shfl_sync(0xFFFFFFFFu, dst, j));
+        d[k] = (c < chunks && row) ? row + (c - j * cpr) : nullptr;
+        if (d[k]) v[k] = ld_nc(src + c);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        if (d[k]) st_stream(d[k], v[k]);
+    }
+  }
+}
+
+// --- owner: probe + gather + peer store ------------------------------------------------------------
+// Tile t of the received keys = 32 consecutive positions of ONE source's region, so the rows of a
+// tile go to one contiguous block of that requester's ret_rows and the tile body is exactly the
+// single-table one with a peer pointer as its output.
+template <int CPR, bool INSERT>
+__global__ void __launch_bounds__(256) owner_probe_gather_kernel(TableView t, const __grid_constant__ PeerSet ps,
+                                                                 const PeerWork* __restrict__ work, NewList nl) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t cpr = CPR > 0 ? (uint32_t)CPR : t.cpr;
+  const PeerWindow& me = ps.w[ps.rank];
+  const uint32_t ntiles = work->tile_off[ps.world];
+  TileCounts cnt;
+  for (uint32_t tile = warp; tile < ntiles; tile += nwarps) {
+    uint32_t s = 0;
+#pragma unroll
+    for (uint32_t k = 1; k < kMaxPeers; k++) s += (k < ps.world && __ldg(work->tile_off + k) <= tile) ? 1u : 0u;
+    const uint32_t p0 = (tile - __ldg(work->tile_off + s)) * 32u;
+    const uint32_t cnt_s = work->cnt[s];
+    const uint32_t tile_keys = min(32u, cnt_s - p0);
+    const bool valid = lane < tile_keys;
+    const size_t e = (size_t)s * ps.region + p0 + lane;  // in my window: [source][position]
+    const uint64_t key = valid ? ld_window(me.recv_keys + e) : MEEPO_KEY_EMPTY;
+    const uint32_t occ = valid ? ld_window(me.recv_occ + e) : 0u;
+    const size_t r = (size_t)ps.rank * ps.region + p0;    // in the requester's window: [owner][position]
+    probe_gather_tile<CPR, INSERT>(t, key, valid, tile_keys, ps.w[s].ret_rows + r * cpr,
+                                   valid ? ps.w[s].ret_status + r + lane : nullptr, nullptr, nullptr, occ, nl, cnt,
+                                   lane);
+  }
+  flush_tile_counts(t, cnt, lane);
+}
+
+template <bool INSERT>
+static const void* pick_owner_kernel(uint32_t cpr) {
+  switch (cpr) {
+    case 1: return (const void*)owner_probe_gather_kernel<1, INSERT>;
+    case 2: return (const void*)owner_probe_gather_kernel<2, INSERT>;
+    case 4: return (const void*)owner_probe_gather_kernel<4, INSERT>;
+    case 8: return (const void*)owner_probe_gather_kernel<8, INSERT>;
+    case 16: return (const void*)owner_probe_gather_kernel<16, INSERT>;
+    case 32: return (const void*)owner_probe_gather_kernel<32, INSERT>;
+    case 64: return (const void*)owner_probe_gather_kernel<64, INSERT>;
+    default: return (const void*)owner_probe_gather_kernel<0, INSERT>;
+  }
+}
+
+// --- requester: expand ---------------------------------------------------------------------------
+// rows_out[i] = ret_rows[loc[inverse[i]]]: one warp moves 32 output rows as a flat chunk array.
+__global__ void __launch_bounds__(256) expand_kernel(const uint4* __restrict__ ret_rows,
+                                                     const uint8_t* __restrict__ ret_status,
+                                                     const uint32_t* __restrict__ loc,
+                                                     const uint32_t* __restrict__ inverse, uint32_t n, uint32_t cpr,
+                                                     uint4* __restrict__ out, uint8_t* __restrict__ status_out) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t ntiles = (n + 31u) >> 5;
+  for (uint32_t tile = warp; tile < ntiles; tile += nwarps) {
+    const uint32_t i = tile * 32u + lane;
+    uint32_t src = kNil;
+    if (i < n) {
+      const uint32_t u = __ldg(inverse + i);
+      uint8_t st = MEEPO_KEY_INVALID;
+      if (u != kNil) {
+        src = __ldg(loc + u);
+        st = src != kNil ? __ldcg(ret_status + src) : (uint8_t)MEEPO_KEY_FULL;
+      }
+      if (status_out) status_out[i] = st;
+    }
+    const uint32_t chunks = min(32u, n - tile * 32u) * cpr;
+    uint4* out_tile = out + (size_t)tile * 32u * cpr;
+    for (uint32_t c0 = 0; c0 < chunks; c0 += 128) {
+      uint4 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const uint32_t c = c0 + k * 32 + lane;
+        const uint32_t j = min(c / cpr, 31u);
+        const uint32_t s = __shfl_sync(0xFFFFFFFFu, src, j);
+        v[k] = make_uint4(0, 0, 0, 0);
+        if (c < chunks && s != kNil) v[k] = ld_stream(ret_rows + (size_t)s * cpr + (c - j * cpr));
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const uint32_t c = c0 + k * 32 + lane;
+        if (c < chunks) st_stream(out_tile + c, v[k]);
+      }
+    }
+  }
+}
+
+// --- owner: group received gradient entries by key, then one optimizer step per key ---------------
+__global__ void __launch_bounds__(256) owner_clear_kernel(uint2* __restrict__ cells, const PeerWork* __restrict__ work) {
+  const uint32_t m = work->mask + 1u;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x)
+    cells[i] = make_uint2(kNil, 0u);
+}
+
+__device__ __forceinline__ uint32_t hash_slot(uint32_t s) {
+  s ^= s >> 16;
+  s *= 0x7FEB352Du;
+  s ^= s >> 15;
+  s *= 0x846CA68Bu;
+  s ^= s >> 16;
+  return s;
+}
+
+__global__ void __launch_bounds__(256) owner_group_kernel(TableView t, const __grid_constant__ PeerSet ps,
+                                                          PeerWork* __restrict__ work, uint2* __restrict__ cells,
+                                                          uint32_t* __restrict__ contrib,
+                                                          uint32_t* __restrict__ group_list) {
+  const uint32_t n = work->recv_off[ps.world];
+  const uint32_t mask = work->mask;
+  const uint32_t lane = threadIdx.x & 31u;
+  const PeerWindow& me = ps.w[ps.rank];
+  uint32_t dropped = 0;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
+    const uint32_t i = base + lane;
+    bool winner = false;
+    uint32_t h = 0;
+    if (i < n) {
+      uint32_t s = 0;
+      for (uint32_t k = 1; k < ps.world; k++) s += work->recv_off[k] <= i ? 1u : 0u;
+      const uint32_t e = s * ps.region + (i - work->recv_off[s]);
+      const uint64_t key = ld_window(me.recv_keys + e);
+      const uint32_t slot = key_valid(key) ? probe_find<kReadOnly>(t, key) : kNil;
+      if (slot == kNil) {
+        dropped++;
+      } else {
+        h = hash_slot(slot) & mask;
+        while (true) {
+          const uint32_t old = atomicCAS(&cells[h].x, kNil, slot);
+          if (old == kNil) winner = true;
+          if (old == kNil || old == slot) break;
+          h = (h + 1) & mask;
+        }
+        atomicOr(&cells[h].y, 1u << s);
+        contrib[(size_t)h * ps.world + s] = e;
+      }
+    }
+    const unsigned wm = __ballot_sync(0xFFFFFFFFu, winner);
+    if (wm) {
+      const int leader = __ffs(wm) - 1;
+      uint32_t b = 0;
+      if ((int)lane == leader) b = atomicAdd(&work->n_groups, (uint32_t)__popc(wm));
+      b = __shfl_sync(0xFFFFFFFFu, b, leader);
+      if (winner) group_list[b + __popc(wm & ((1u << lane) - 1u))] = h;
+    }
+  }
+  dropped = __reduce_add_sync(0xFFFFFFFFu, dropped);
+  if (lane == 0 && dropped) atomicAdd(t.counters + C_DROPPED, (unsigned long long)dropped);
+}
+
+// One group of lanes per key: the senders' partial sums (each already rounded to the table dtype)
+// are added in rank order — a single leaf of the normative tree, <= world terms — and the optimizer
+// is applied to row + state in the same registers. All loads of a key are issued before the math.
+template <bool BF16, int OPT>
+__global__ void __launch_bounds__(256) owner_apply_kernel(TableView t, const __grid_constant__ PeerSet ps,
+                                                          const PeerWork* __restrict__ work,
+                                                          const uint2* __restrict__ cells,
+                                                          const uint32_t* __restrict__ contrib,
+                                                          const uint32_t* __restrict__ group_list,
+                                                          uint32_t group_lanes) {
+  constexpr int E = Chunk<BF16>::E;
+  const uint32_t GL = group_lanes;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t gl = lane & (GL - 1);
+  const unsigned gmask = (GL == 32 ? 0xFFFFFFFFu : ((1u << GL) - 1u) << (lane & ~(GL - 1)));
+  const uint32_t groups_per_block = blockDim.x / GL;
+  const uint32_t group = blockIdx.x * groups_per_block + threadIdx.x / GL;
+  const uint32_t ngroups = gridDim.x * groups_per_block;
+  const uint32_t U = work->n_groups;
+  const uint4* grads = ps.w[ps.rank].recv_grads;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && U) atomicAdd(t.counters + C_UPDATES, (unsigned long long)U);
+  for (uint32_t g = group; g < U; g += ngroups) {
+    const uint32_t h = __ldg(group_list + g);
+    const uint2 cell = cells[h];
+    const uint32_t slot = cell.x, senders = cell.y;
+    uint32_t ent[kMaxPeers];
+#pragma unroll
+    for (uint32_t s = 0; s < kMaxPeers; s++)
+      ent[s] = ((senders >> s) & 1u) ? __ldg(contrib + (size_t)h * ps.world + s) : kNil;
+    const float alpha = adam_alpha<OPT>(t, slot, gmask, gl == 0);
+    for (uint32_t q = gl; q < t.cpr; q += GL) {
+      OptIn<BF16, OPT> in;
+      opt_issue<BF16, OPT>(t, slot, q, in);
+      uint4 raw[kMaxPeers];
+#pragma unroll
+      for (uint32_t s = 0; s < kMaxPeers; s++)
+        if (ent[s] != kNil) raw[s] = ld_stream(grads + (size_t)ent[s] * t.cpr + q);
+      float acc[E];
+      bool first = true;
+#pragma unroll
+      for (uint32_t s = 0; s < kMaxPeers; s++) {
+        if (ent[s] == kNil) continue;
+        float x[E];
+        widen<BF16>(raw[s], x);
+        if (first) {
+#pragma unroll
+          for (int k = 0; k < E; k++) acc[k] = x[k];
+          first = false;
+        } else {
+#pragma unroll
+          for (int k = 0; k < E; k++) acc[k] = __fadd_rn(acc[k], x[k]);
+        }
+      }
+      opt_finish<BF16, OPT>(t, slot, q, in, acc, alpha, nullptr);
+    }
+  }
+}
+
+template <bool BF16>
+static const void* pick_owner_apply(int opt) {
+  switch (opt) {
+    case MEEPO_SGD: return (const void*)owner_apply_kernel<BF16, MEEPO_SGD>;
+    case MEEPO_ADAGRAD: return (const void*)owner_apply_kernel<BF16, MEEPO_ADAGRAD>;
+    default: return (const void*)owner_apply_kernel<BF16, MEEPO_ADAM>;
+  }
+}
+
+// --- host side ---------------------------------------------------------------------------------
+static size_t forward_ws_bytes(const meepo_table* t, const PeerState* p) {
+  const uint64_t n = p->max_batch;
+  return dedup_bytes(t, n, false) + Workspace::pad(n * 8) + 2 * Workspace::pad(n * 4) + 256 +
+         Workspace::pad((size_t)p->world * p->region * 4) + 4096;
+}
+static size_t backward_ws_bytes(const meepo_table* t, const PeerState* p) {
+  const uint64_t n = p->max_batch;
+  return dedup_bytes(t, n, true) + Workspace::pad(n * 8) + Workspace::pad(n * (size_t)t->row_bytes) + 256 + 4096;
+}
+
+void destroy_peer(meepo_table* t) {
+  PeerState* p = t->peer;
+  if (!p) return;
+  for (uint32_t j = 0; j < kMaxPeers; j++)
+    if (p->opened[j]) cudaIpcCloseMemHandle(p->opened[j]);
+  cudaFree(p->window);
+  cudaFree(p->local);
+  delete p;
+  t->peer = nullptr;
+}
+
+meepo_status peer_error_check(meepo_table* t) {
+  PeerState* p = t->peer;
+  if (!p || !p->window) return MEEPO_OK;
+  uint32_t err = 0;
+  PeerWindow w;
+  carve_window(p->window, p->world, p->region, t->v.cpr, w, nullptr);
+  MEEPO_CUDA_TRY(cudaMemcpy(&err, w.error, 4, cudaMemcpyDeviceToHost));
+  if (err & PE_TIMEOUT) return fail(MEEPO_ENCCL, "sharded verb: a peer did not reach the barrier (timeout)");
+  if (err & PE_REGION_OVERFLOW)
+    return fail(MEEPO_ENCCL, "sharded verb: more keys for one owner than region_keys; results are incomplete");
+  return MEEPO_OK;
+}
+
+static meepo_status barrier(meepo_table* t, const uint32_t* send_cnt, bool for_apply, cudaStream_t stream) {
+  PeerState* p = t->peer;
+  ProfScope ps(t, "sharded.barrier", stream);
+  p->seq++;
+  peer_barrier_kernel<<<1, 32, 0, stream>>>(p->ps, p->seq, send_cnt, send_cnt ? p->work : nullptr, for_apply ? 1 : 0,
+                                            t->v.counters, p->timeout_ns);
+  MEEPO_CUDA_TRY(cudaGetLastError());
+  return MEEPO_OK;
+}
+
+static meepo_status check_sharded(meepo_table* t, const void* keys, uint64_t n, const void* buf) {
+  if (!t) return fail(MEEPO_EINVAL, "null table");
+  if (!t->peer || !t->peer->attached) return fail(MEEPO_EINVAL, "meepo_peer_attach has not been called");
+  if (n > t->peer->max_batch) return fail(MEEPO_EINVAL, "batch larger than the max_batch given to meepo_peer_prepare");
+  if (n && (!keys || !buf)) return fail(MEEPO_EINVAL, "null buffer");
+  return MEEPO_OK;
+}
+
+static meepo_status sharded_forward(meepo_table* t, const uint64_t* keys, uint64_t n, void* rows_out,
+                                    uint8_t* status_out, bool insert, cudaStream_t stream) {
+  MEEPO_TRY(check_sharded(t, keys, n, rows_out));
+  DeviceGuard guard(t->device);
+  PeerState* p = t->peer;
+  t->cache_valid = false;
+  t->epoch++;
+  t->v.epoch = (uint32_t)t->epoch;
+  MEEPO_TRY(t->ws.reserve(forward_ws_bytes(t, p), stream));
+  uint64_t* ukeys = t->ws.take<uint64_t>(std::max<uint64_t>(n, 1));
+  uint32_t* inverse = t->ws.take<uint32_t>(std::max<uint64_t>(n, 1));
+  uint32_t* uocc = t->ws.take<uint32_t>(std::max<uint64_t>(n, 1));  // hit/miss stats and LFU scores count occurrences
+  uint64_t* n_unique = t->ws.take<uint64_t>(1);
+  NewList nl{t->ws.take<uint32_t>((size_t)p->world * p->region), &t->dstate->new_count[t->foi_parity]};
+  uint32_t* nl_next = &t->dstate->new_count[t->foi_parity ^ 1];
+  if (insert) t->foi_parity ^= 1;
+  MEEPO_TRY(dedup_run(t, keys, nullptr, n, DedupOut{ukeys, nullptr, inverse, n_unique, uocc}, stream));
+  {
+    ProfScope ps(t, "sharded.push_keys", stream);
+    MEEPO_CUDA_TRY(cudaMemsetAsync(p->send_cnt, 0, kMaxPeers * 4, stream));
+    const int grid = grid_for(t, (const void*)push_keys_kernel, 256, 0, (std::max<uint64_t>(n, 1) + 255) / 256);
+    push_keys_kernel<<<grid, 256, 0, stream>>>(p->ps, ukeys, uocc, (const unsigned long long*)n_unique, p->send_cnt,
+                                               p->loc);
+    MEEPO_CUDA_TRY(cudaGetLastError());
+  }
+  MEEPO_TRY(barrier(t, p->send_cnt, false, stream));
+  {
+    ProfScope ps(t, insert ? "sharded.owner_find_or_insert" : "sharded.owner_lookup", stream);
+    const void* kern = insert ? pick_owner_kernel<true>(t->v.cpr) : pick_owner_kernel<false>(t->v.cpr);
+    const uint64_t tiles = ((uint64_t)p->world * p->region + 31) / 32 + p->world;
+    const int grid = grid_for(t, kern, 256, 0, (tiles + 7) / 8);
+    const PeerWork* work = p->work;
+    void* args[] = {&t->v, &p->ps, &work, &nl};
+    MEEPO_CUDA_TRY(cudaLaunchKernel(kern, dim3(grid), dim3(256), args, 0, stream));
+  }
+  if (insert) {
+    ProfScope ps(t, "find_or_insert.publish", stream);
+    MEEPO_TRY(publish_slots(t, nl.slots, nl.count, nl_next, (uint64_t)p->world * p->region, stream));
+  }
+  MEEPO_TRY(barrier(t, nullptr, false, stream));
+  if (n) {
+    ProfScope ps(t, "sharded.expand", stream);
+    const PeerWindow& me = p->ps.w[p->rank];
+    const uint64_t tiles = (n + 31) / 32;
+    const int grid = grid_for(t, (const void*)expand_kernel, 256, 0, (tiles + 7) / 8);
+    expand_kernel<<<grid, 256, 0, stream>>>(me.ret_rows, me.ret_status, p->loc, inverse, (uint32_t)n, t->v.cpr,
+                                            reinterpret_cast<uint4*>(rows_out), status_out);
+    MEEPO_CUDA_TRY(cudaGetLastError());
+  }
+  return MEEPO_OK;
+}
+
+static meepo_status sharded_apply(meepo_table* t, const uint64_t* keys, const void* grads, uint64_t n,
+                                  cudaStream_t stream) {
+  MEEPO_TRY(check_sharded(t, keys, n, grads));
+  DeviceGuard guard(t->device);
+  PeerState* p = t->peer;
+  MEEPO_TRY(t->ws.reserve(backward_ws_bytes(t, p), stream));
+  uint64_t* ukeys = t->ws.take<uint64_t>(std::max<uint64_t>(n, 1));
+  uint4* ugrads = reinterpret_cast<uint4*>(t->ws.take<char>(std::max<uint64_t>(n, 1) * t->row_bytes));
+  uint64_t* n_unique = t->ws.take<uint64_t>(1);
+  MEEPO_TRY(dedup_run(t, keys, n ? grads : nullptr, n, DedupOut{ukeys, ugrads, nullptr, n_unique, nullptr}, stream));
+  {
+    ProfScope ps(t, "sharded.push_grads", stream);
+    MEEPO_CUDA_TRY(cudaMemsetAsync(p->send_cnt, 0, kMaxPeers * 4, stream));
+    const uint64_t tiles = (std::max<uint64_t>(n, 1) + 31) / 32;
+    const int grid = grid_for(t, (const void*)push_grads_kernel, 256, 0, (tiles + 7) / 8);
+    push_grads_kernel<<<grid, 256, 0, stream>>>(p->ps, ukeys, ugrads, (const unsigned long long*)n_unique, p->send_cnt);
+    MEEPO_CUDA_TRY(cudaGetLastError());
+  }
+  MEEPO_TRY(barrier(t, p->send_cnt, true, stream));
+  const uint64_t max_recv = (uint64_t)p->world * p->region;
+  {
+    ProfScope ps(t, "sharded.owner_group(2 kernels)", stream);
+    const int g1 = grid_for(t, (const void*)owner_clear_kernel, 256, 0, (p->m_max + 255) / 256);
+    owner_clear_kernel<<<g1, 256, 0, stream>>>(p->cells, p->work);
+    const int g2 = grid_for(t, (const void*)owner_group_kernel, 256, 0, (max_recv + 255) / 256);
+    owner_group_kernel<<<g2, 256, 0, stream>>>(t->v, p->ps, p->work, p->cells, p->contrib, p->group_list);
+    MEEPO_CUDA_TRY(cudaGetLastError());
+  }
+  {
+    ProfScope ps(t, "sharded.owner_apply", stream);
+    uint32_t gl = 1;
+    while (gl * 2 <= t->v.cpr && gl < 32) gl *= 2;
+    const void* kern = t->v.dtype == MEEPO_BF16 ? pick_owner_apply<true>(t->v.opt) : pick_owner_apply<false>(t->v.opt);
+    const uint64_t groups_per_block = 256 / gl;
+    const int grid = grid_for(t, kern, 256, 0, (max_recv + groups_per_block - 1) / groups_per_block);
+    const PeerWork* work = p->work;
+    const uint2* cells = p->cells;
+    const uint32_t* contrib = p->contrib;
+    const uint32_t* group_list = p->group_list;
+    void* args[] = {&t->v, &p->ps, &work, &cells, &contrib, &group_list, &gl};
+    MEEPO_CUDA_TRY(cudaLaunchKernel(kern, dim3(grid), dim3(256), args, 0, stream));
+  }
+  return barrier(t, nullptr, false, stream);
+}
+
+// CUDA loads kernels lazily, and the first launch of a kernel may synchronise the whole context: a
+// rank whose barrier kernel is already spinning would then wait for a launch that cannot start (a
+// deadlock when one process drives several shards, a stall otherwise). So every kernel of the three
+// verbs is launched once here, on this rank alone (world 1), over a batch of invalid keys: no key is
+// touched, no counter moves, and the window header and sequence numbers are reset afterwards.
+static meepo_status warm_up(meepo_table* t) {
+  PeerState* p = t->peer;
+  const PeerSet saved = p->ps;
+  PeerSet self{};
+  self.world = 1;
+  self.rank = 0;
+  self.region = (uint32_t)p->region;
+  self.cpr = t->v.cpr;
+  carve_window(p->window, p->world, p->region, t->v.cpr, self.w[0], nullptr);
+  p->ps = self;
+  p->attached = true;
+  const uint64_t epoch = t->epoch;
+  meepo_status rc = MEEPO_OK;
+  const uint64_t sizes[2] = {std::min<uint64_t>(p->max_batch, 1024), std::min<uint64_t>(p->max_batch, 65536)};
+  void* keys = nullptr;
+  void* rows = nullptr;
+  if (cudaMalloc(&keys, sizes[1] * 8) != cudaSuccess || cudaMalloc(&rows, sizes[1] * (size_t)t->row_bytes) != cudaSuccess) {
+    cudaFree(keys);
+    rc = fail(MEEPO_ENOMEM, "cudaMalloc(warm-up)");
+  } else {
+    cudaMemset(keys, 0xFF, sizes[1] * 8);  // MEEPO_KEY_EMPTY: invalid, dropped by the dedup
+    cudaMemset(rows, 0, sizes[1] * (size_t)t->row_bytes);
+    for (int k = 0; k < 2 && rc == MEEPO_OK; k++) {
+      rc = sharded_forward(t, (const uint64_t*)keys, sizes[k], rows, nullptr, false, nullptr);
+      if (rc == MEEPO_OK) rc = sharded_forward(t, (const uint64_t*)keys, sizes[k], rows, nullptr, true, nullptr);
+      if (rc == MEEPO_OK) rc = sharded_apply(t, (const uint64_t*)keys, rows, sizes[k], nullptr);
+    }
+    if (rc == MEEPO_OK && cudaDeviceSynchronize() != cudaSuccess) rc = fail(MEEPO_ECUDA, "warm-up failed");
+    cudaFree(keys);
+    cudaFree(rows);
+  }
+  cudaMemset(p->window, 0, kWindowHeader);
+  cudaDeviceSynchronize();
+  p->seq = 0;
+  p->ps = saved;
+  p->attached = false;
+  t->epoch = epoch;
+  t->v.epoch = (uint32_t)epoch;
+  return rc;
+}
+
+}  // namespace meepo
+
+using namespace meepo;
+
+extern "C" {
+
+MEEPO_API meepo_status meepo_peer_prepare(meepo_table* t, uint32_t rank, uint32_t world, uint64_t max_batch,
+                                          uint64_t region_keys, void* blob_out) {
+  if (!t || !blob_out) return fail(MEEPO_EINVAL, "null argument");
+  if (world == 0 || world > kMaxPeers || rank >= world) return fail(MEEPO_EINVAL, "need rank < world <= MEEPO_MAX_PEERS");
+  if (max_batch == 0 || max_batch > 0x7FFFFFFFull) return fail(MEEPO_EINVAL, "bad max_batch");
+  if (region_keys == 0 || region_keys > max_batch) region_keys = max_batch;
+  if ((uint64_t)world * region_keys > 0x7FFFFFFFull) return fail(MEEPO_EINVAL, "world * region_keys must fit in 31 bits");
+  if (t->peer) return fail(MEEPO_EINVAL, "meepo_peer_prepare was already called on this table");
+  DeviceGuard guard(t->device);
+  PeerState* p = new PeerState();
+  t->peer = p;
+  p->world = world;
+  p->rank = rank;
+  p->max_batch = max_batch;
+  p->region = region_keys;
+  if (const char* e = getenv("MEEPO_PEER_TIMEOUT_MS")) p->timeout_ns = strtoull(e, nullptr, 10) * 1000000ull;
+  PeerWindow w;
+  carve_window(nullptr, world, region_keys, t->v.cpr, w, &p->window_bytes);
+  auto bail = [&](cudaError_t e, const char* what) {
+    std::string m = std::string(what) + ": " + cudaGetErrorString(e);
+    destroy_peer(t);
+    return fail(e == cudaErrorMemoryAllocation ? MEEPO_ENOMEM : MEEPO_ECUDA, m);
+  };
+  cudaError_t e;
+  if ((e = cudaMalloc(&p->window, p->window_bytes)) != cudaSuccess) return bail(e, "cudaMalloc(exchange window)");
+  if ((e = cudaMemset(p->window, 0, kWindowHeader)) != cudaSuccess) return bail(e, "cudaMemset");
+  // private scratch
+  const uint64_t max_recv = (uint64_t)world * region_keys;
+  uint64_t m = 1024;
+  while (m < 2 * max_recv) m <<= 1;
+  p->m_max = m;
+  size_t off = 0;
+  const size_t o_cnt = off;
+  off += align_up(kMaxPeers * 4);
+  const size_t o_work = off;
+  off += align_up(sizeof(PeerWork));
+  const size_t o_loc = off;
+  off += align_up(max_batch * 4);
+  const size_t o_cells = off;
+  off += align_up(m * 8);
+  const size_t o_contrib = off;
+  off += align_up(m * (size_t)world * 4);
+  const size_t o_list = off;
+  off += align_up(max_recv * 4);
+  if ((e = cudaMalloc(&p->local, off)) != cudaSuccess) return bail(e, "cudaMalloc(peer scratch)");
+  if ((e = cudaMemset(p->local, 0, o_loc)) != cudaSuccess) return bail(e, "cudaMemset");
+  p->send_cnt = reinterpret_cast<uint32_t*>(p->local + o_cnt);
+  p->work = reinterpret_cast<PeerWork*>(p->local + o_work);
+  p->loc = reinterpret_cast<uint32_t*>(p->local + o_loc);
+  p->cells = reinterpret_cast<uint2*>(p->local + o_cells);
+  p->contrib = reinterpret_cast<uint32_t*>(p->local + o_contrib);
+  p->group_list = reinterpret_cast<uint32_t*>(p->local + o_list);
+  // the workspace never grows (cudaFree = device-wide sync) once the verbs are in flight
+  if (t->ws.reserve(std::max(forward_ws_bytes(t, p), backward_ws_bytes(t, p)), nullptr) != MEEPO_OK) {
+    destroy_peer(t);
+    return MEEPO_ENOMEM;
+  }
+  if (meepo_status rc = warm_up(t); rc != MEEPO_OK) {
+    destroy_peer(t);
+    return rc;
+  }
+  PeerBlob b;
+  memset(&b, 0, sizeof b);
+  b.magic = kBlobMagic;
+  b.abi = MEEPO_ABI_VERSION;
+  b.pid = (int32_t)getpid();
+  b.device = t->device;
+  b.rank = rank;
+  b.world = world;
+  b.region = region_keys;
+  b.max_batch = max_batch;
+  b.dim = t->v.dim;
+  b.dtype = (uint32_t)t->v.dtype;
+  b.opt = (uint32_t)t->v.opt;
+  b.flags = t->cfg.flags;
+  b.window_bytes = p->window_bytes;
+  b.raw_ptr = (uint64_t)(uintptr_t)p->window;
+  if ((e = cudaIpcGetMemHandle(&b.handle, p->window)) != cudaSuccess) return bail(e, "cudaIpcGetMemHandle");
+  if ((e = cudaDeviceSynchronize()) != cudaSuccess) return bail(e, "cudaDeviceSynchronize");
+  memset(blob_out, 0, MEEPO_PEER_BLOB_BYTES);
+  memcpy(blob_out, &b, sizeof b);
+  return MEEPO_OK;
+}
+
+MEEPO_API meepo_status meepo_peer_attach(meepo_table* t, const void* blobs) {
+  if (!t || !blobs) return fail(MEEPO_EINVAL, "null argument");
+  PeerState* p = t->peer;
+  if (!p) return fail(MEEPO_EINVAL, "call meepo_peer_prepare first");
+  if (p->attached) return fail(MEEPO_EINVAL, "already attached");
+  DeviceGuard guard(t->device);
+  p->ps.world = p->world;
+  p->ps.rank = p->rank;
+  p->ps.region = (uint32_t)p->region;
+  p->ps.cpr = t->v.cpr;
+  for (uint32_t j = 0; j < p->world; j++) {
+    PeerBlob b;
+    memcpy(&b, (const char*)blobs + (size_t)j * MEEPO_PEER_BLOB_BYTES, sizeof b);
+    if (b.magic != kBlobMagic || b.abi != MEEPO_ABI_VERSION) return fail(MEEPO_EINVAL, "peer blob: bad magic / ABI");
+    if (b.rank != j || b.world != p->world) return fail(MEEPO_EINVAL, "peer blobs must be ordered by rank");
+    if (b.region != p->region || b.dim != t->v.dim || b.dtype != (uint32_t)t->v.dtype || b.opt != (uint32_t)t->v.opt ||
+        b.flags != t->cfg.flags || b.window_bytes != p->window_bytes)
+      return fail(MEEPO_EINVAL, "peer blob: table geometry differs between ranks");
+    char* base = nullptr;
+    if (j == p->rank) {
+      base = p->window;
+    } else if (b.pid == (int32_t)getpid()) {  // several tables driven by one process
+      base = reinterpret_cast<char*>((uintptr_t)b.raw_ptr);
+      if (b.device != t->device) {
+        int can = 0;
+        MEEPO_CUDA_TRY(cudaDeviceCanAccessPeer(&can, t->device, b.device));
+        if (!can) return fail(MEEPO_ECUDA, "no peer access between the devices of two shards");
+        cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+          return fail(MEEPO_ECUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+        cudaGetLastError();
+      }
+    } else {
+      void* ptr = nullptr;
+      cudaError_t e = cudaIpcOpenMemHandle(&ptr, b.handle, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess)
+        return fail(MEEPO_ECUDA, std::string("cudaIpcOpenMemHandle(rank ") + std::to_string(j) + "): " + cudaGetErrorString(e));
+      p->opened[j] = ptr;
+      base = reinterpret_cast<char*>(ptr);
+    }
+    carve_window(base, p->world, p->region, t->v.cpr, p->ps.w[j], nullptr);
+  }
+  p->attached = true;
+  return MEEPO_OK;
+}
+
+MEEPO_API meepo_status meepo_peer_detach(meepo_table* t) {
+  if (!t) return fail(MEEPO_EINVAL, "null table");
+  DeviceGuard guard(t->device);
+  cudaDeviceSynchronize();
+  destroy_peer(t);
+  return MEEPO_OK;
+}
+
+MEEPO_API meepo_status meepo_sharded_find_or_insert(meepo_table* t, const uint64_t* keys, uint64_t n, void* rows_out,
+                                                    uint8_t* status_out, void* stream) {
+  return sharded_forward(t, keys, n, rows_out, status_out, true, (cudaStream_t)stream);
+}
+MEEPO_API meepo_status meepo_sharded_lookup(meepo_table* t, const uint64_t* keys, uint64_t n, void* rows_out,
+                                            uint8_t* found_out, void* stream) {
+  return sharded_forward(t, keys, n, rows_out, found_out, false, (cudaStream_t)stream);
+}
+MEEPO_API meepo_status meepo_sharded_apply_gradients(meepo_table* t, const uint64_t* keys, const void* grads,
+                                                     uint64_t n, void* stream) {
+  return sharded_apply(t, keys, grads, n, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -189,11 +189,13 @@ __global__ void __launch_bounds__(256) dedup_inverse_kernel(const uint32_t* __re
                                                             const uint32_t* __restrict__ uid_of_slot,
                                                             uint32_t* __restrict__ inverse_out,
                                                             uint32_t* __restrict__ sort_key,
-                                                            uint32_t* __restrict__ sort_val) {
+                                                            uint32_t* __restrict__ sort_val,
+                                                            uint32_t* __restrict__ occurrences) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint32_t p = pos[i];
     const uint32_t u = p == kNil ? kNil : uid_of_slot[p];
     if (inverse_out) inverse_out[i] = u;
+    if (occurrences && u != kNil) atomicAdd(occurrences + u, 1u);
     if (sort_key) {
       sort_key[i] = u == kNil ? n : u;  // invalid keys sort last and are skipped
       sort_val[i] = i;
@@ -233,6 +235,58 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const uint4* __restric
       }
     }
   }
+}
+
+// batch-level dedup (+ optional pre-reduction of the duplicate gradients); scratch comes out of the
+// table workspace, which the caller has reserved for at least dedup_bytes().
+size_t dedup_bytes(const meepo_table* t, uint64_t n, bool with_grads) {
+  if (n == 0) return 256;
+  uint64_t m = 1024;
+  while (m < 2 * n) m <<= 1;
+  const uint64_t ntiles = m / kScanTile;
+  size_t need = Workspace::pad((size_t)m * 8) + Workspace::pad(n * 4) + Workspace::pad((size_t)m * 4) +
+                2 * Workspace::pad((ntiles + 1) * 4) + 4096;
+  if (with_grads) need += SegWork::bytes(n, t->v.dim, bits_for((uint32_t)n));
+  return need;
+}
+
+meepo_status dedup_run(meepo_table* t, const uint64_t* keys, const void* grads, uint64_t n, const DedupOut& o,
+                       cudaStream_t stream) {
+  if (n == 0) {
+    MEEPO_CUDA_TRY(cudaMemsetAsync(o.n_unique, 0, 8, stream));
+    return MEEPO_OK;
+  }
+  uint32_t m = 1024;
+  while (m < 2 * n) m <<= 1;
+  const uint32_t ntiles = m / kScanTile;
+  const int end_bit = bits_for((uint32_t)n);
+  uint64_t* scratch = t->ws.take<uint64_t>(m);
+  uint32_t* pos = t->ws.take<uint32_t>(n);
+  uint32_t* uid_of_slot = t->ws.take<uint32_t>(m);
+  uint32_t* tile_count = t->ws.take<uint32_t>(ntiles + 1);
+  uint32_t* tile_off = t->ws.take<uint32_t>(ntiles + 1);
+  SegWork w;
+  if (grads) w.take(t->ws, n, t->v.dim, end_bit);
+  {
+    ProfScope ps(t, "dedup.hash(5 kernels)", stream);
+    MEEPO_CUDA_TRY(cudaMemsetAsync(scratch, 0xFF, (size_t)m * 8, stream));
+    if (o.occurrences) MEEPO_CUDA_TRY(cudaMemsetAsync(o.occurrences, 0, n * 4, stream));
+    const int grid = grid_for(t, (const void*)dedup_insert_kernel, 256, 0, (n + 255) / 256);
+    dedup_insert_kernel<<<grid, 256, 0, stream>>>(keys, (uint32_t)n, scratch, m - 1, pos);
+    occ_count_kernel<<<ntiles, 256, 0, stream>>>(scratch, m, tile_count);
+    excl_scan_kernel<<<1, 1024, 0, stream>>>(tile_count, tile_off, ntiles, (unsigned long long*)o.n_unique);
+    occ_fill_kernel<<<ntiles, 256, 0, stream>>>(scratch, m, tile_off, uid_of_slot, o.unique_keys);
+    dedup_inverse_kernel<<<grid, 256, 0, stream>>>(pos, (uint32_t)n, uid_of_slot, o.inverse,
+                                                   grads ? w.sk_in : nullptr, grads ? w.sv_in : nullptr,
+                                                   o.occurrences);
+    MEEPO_CUDA_TRY(cudaGetLastError());
+  }
+  if (grads) {
+    static const char* const names[4] = {"dedup.radix_sort(cub)", "dedup.segments(3 kernels)", "dedup.reduce_store",
+                                         "dedup.long_segments(2 kernels)"};
+    MEEPO_TRY(run_segmented(t, w, (uint32_t)n, grads, kReduceStoreOnly, o.grads_out, stream, nullptr, names));
+  }
+  return MEEPO_OK;
 }
 
 }  // namespace meepo
@@ -277,43 +331,8 @@ MEEPO_API meepo_status meepo_reduce_duplicates(meepo_table* t, const uint64_t* k
   if ((grads == nullptr) != (grads_out == nullptr)) return fail(MEEPO_EINVAL, "grads and grads_out go together");
   DeviceGuard guard(t->device);
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (n == 0) {
-    MEEPO_CUDA_TRY(cudaMemsetAsync(n_unique_out, 0, 8, stream));
-    return MEEPO_OK;
-  }
-  uint32_t m = 1024;
-  while (m < 2 * n) m <<= 1;
-  const uint32_t ntiles = m / kScanTile;
-  const int end_bit = bits_for((uint32_t)n);
-  size_t need = Workspace::pad((size_t)m * 8) + Workspace::pad(n * 4) + Workspace::pad((size_t)m * 4) +
-                2 * Workspace::pad((ntiles + 1) * 4) + 4096;
-  if (grads) need += SegWork::bytes(n, t->v.dim, end_bit);
-  MEEPO_TRY(t->ws.reserve(need, stream));
-  uint64_t* scratch = t->ws.take<uint64_t>(m);
-  uint32_t* pos = t->ws.take<uint32_t>(n);
-  uint32_t* uid_of_slot = t->ws.take<uint32_t>(m);
-  uint32_t* tile_count = t->ws.take<uint32_t>(ntiles + 1);
-  uint32_t* tile_off = t->ws.take<uint32_t>(ntiles + 1);
-  SegWork w;
-  if (grads) w.take(t->ws, n, t->v.dim, end_bit);
-  {
-    ProfScope ps(t, "dedup.hash(5 kernels)", stream);
-    MEEPO_CUDA_TRY(cudaMemsetAsync(scratch, 0xFF, (size_t)m * 8, stream));
-    const int grid = grid_for(t, (const void*)dedup_insert_kernel, 256, 0, (n + 255) / 256);
-    dedup_insert_kernel<<<grid, 256, 0, stream>>>(keys, (uint32_t)n, scratch, m - 1, pos);
-    occ_count_kernel<<<ntiles, 256, 0, stream>>>(scratch, m, tile_count);
-    excl_scan_kernel<<<1, 1024, 0, stream>>>(tile_count, tile_off, ntiles, (unsigned long long*)n_unique_out);
-    occ_fill_kernel<<<ntiles, 256, 0, stream>>>(scratch, m, tile_off, uid_of_slot, unique_keys_out);
-    dedup_inverse_kernel<<<grid, 256, 0, stream>>>(pos, (uint32_t)n, uid_of_slot, inverse_out,
-                                                   grads ? w.sk_in : nullptr, grads ? w.sv_in : nullptr);
-    MEEPO_CUDA_TRY(cudaGetLastError());
-  }
-  if (grads) {
-    static const char* const names[4] = {"dedup.radix_sort(cub)", "dedup.segments(3 kernels)", "dedup.reduce_store",
-                                         "dedup.long_segments(2 kernels)"};
-    MEEPO_TRY(run_segmented(t, w, (uint32_t)n, grads, kReduceStoreOnly, grads_out, stream, nullptr, names));
-  }
-  return MEEPO_OK;
+  MEEPO_TRY(t->ws.reserve(dedup_bytes(t, n, grads != nullptr), stream));
+  return dedup_run(t, keys, grads, n, DedupOut{unique_keys_out, grads_out, inverse_out, n_unique_out, nullptr}, stream);
 }
 
 MEEPO_API meepo_status meepo_gather_rows(meepo_table* t, const void* rows_in, const uint32_t* index, uint64_t n,

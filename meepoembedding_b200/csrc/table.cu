@@ -145,6 +145,7 @@ MEEPO_API meepo_status meepo_destroy(meepo_table* t) {
   if (!t) return MEEPO_OK;
   DeviceGuard guard(t->device);
   cudaDeviceSynchronize();
+  destroy_peer(t);
   destroy_host_pipe(t);
   destroy_profiler(t);
   cudaFree(t->v.buckets);
@@ -178,12 +179,14 @@ MEEPO_API meepo_status meepo_stats(meepo_table* t, meepo_stats_t* out) {
   out->updates = c[C_UPDATES];
   out->grad_dropped = c[C_DROPPED];
   out->overflow_buckets = c[C_OVERFLOW];
+  out->peer_keys_received = c[C_PEER_KEYS];
+  out->peer_grads_received = c[C_PEER_GRADS];
   out->spill_keys = t->spill_index.size();
   out->spill_bytes = t->spill_index.size() * t->tuple_bytes();
   out->epoch = t->epoch;
   out->row_bytes = t->row_bytes;
   out->state_bytes = t->state_bytes;
-  return MEEPO_OK;
+  return peer_error_check(t);
 }
 
 }  // extern "C"

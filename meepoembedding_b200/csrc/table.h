@@ -56,6 +56,7 @@ struct DeviceState {
 };
 
 struct Profiler;
+struct PeerState;  // peer.cu: exchange window + peer mappings of the sharded verbs
 
 // (key, slot) of every element of the last find_or_insert / lookup batch. apply_gradients on the
 // same keys (the training loop) reuses the slots instead of probing again: one HBM line per key
@@ -96,6 +97,7 @@ struct meepo_table {
   struct meepo::Profiler* prof = nullptr;  // per-kernel event timing, off unless enabled
   // host-buffer front end (pinned staging + private streams), created lazily
   struct HostPipe* pipe = nullptr;
+  struct meepo::PeerState* peer = nullptr;
   // host spill tier
   char* spill_ring = nullptr;       // pinned
   uint64_t spill_cap_tuples = 0;
@@ -152,9 +154,25 @@ int bits_for(uint32_t max_value);
 meepo_status run_segmented(meepo_table* t, SegWork& w, uint32_t limit, const void* grads, int mode,
                            void* reduce_out, cudaStream_t stream, cudaEvent_t grads_ready,
                            const char* const* names);
+// shard.cu: batch-level dedup. unique_keys[U] (order unspecified), inverse[n] (kNil for invalid
+// keys), *n_unique = U (device), occurrences[U] = duplicates per unique key (optional), grads_out[U] =
+// fixed-shape sum of each key's gradient rows rounded to the table dtype (with grads only).
+struct DedupOut {
+  uint64_t* unique_keys;
+  void* grads_out;
+  uint32_t* inverse;
+  uint64_t* n_unique;
+  uint32_t* occurrences;
+};
+size_t dedup_bytes(const meepo_table* t, uint64_t n, bool with_grads);
+meepo_status dedup_run(meepo_table* t, const uint64_t* keys, const void* grads, uint64_t n, const DedupOut& o,
+                       cudaStream_t stream);
 int grid_for(const meepo_table* t, const void* kernel, int block, size_t smem, uint64_t blocks_needed);
 void destroy_host_pipe(meepo_table* t);
 void destroy_profiler(meepo_table* t);
+void destroy_peer(meepo_table* t);
+// sticky device-side errors of the sharded verbs (barrier timeout, region overflow) -> status
+meepo_status peer_error_check(meepo_table* t);
 // lookup.cu: write the tags of the slots listed in `slots[0..*cur)` and fold the count into the size
 meepo_status publish_slots(meepo_table* t, const uint32_t* slots, const uint32_t* cur, uint32_t* next,
                            uint64_t n_max, cudaStream_t stream);

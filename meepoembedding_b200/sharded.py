@@ -123,3 +123,46 @@ class ShardedTable:
         self._a2a(rgrads, gsorted, rc, sc)
         self.t.apply_gradients(rkeys, rgrads, n=nr, stream=s)
         self.last_exchange = {"unique": U, "sent_keys": U - sc[self.rank], "recv_keys": nr - rc[self.rank], "local": nr}
+
+
+class PeerShardedTable:
+    """The sharded verbs fused with their exchange over NVLink peer memory (csrc/peer.cu).
+
+    torch.distributed is used ONCE, to all-gather the 256-byte window blobs at construction; after
+    that every verb is a single stream of libmeepo.so kernels per rank — no NCCL call, no host
+    synchronisation, no staging copy. Verbs are collective: every rank calls them in the same order.
+    """
+
+    def __init__(self, table, group=None, device=None, max_batch=1 << 20, region_keys=0):
+        self.t = table
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.device = torch.device(device) if device is not None else torch.device("cuda", table.device)
+        blob = table.peer_prepare(self.rank, self.world, max_batch, region_keys)
+        mine = torch.frombuffer(bytearray(blob), dtype=torch.uint8)
+        backend = dist.get_backend(self.group)
+        if backend == "nccl":
+            mine = mine.to(self.device)
+        every = torch.empty(self.world * mine.numel(), dtype=torch.uint8, device=mine.device)
+        dist.all_gather_into_tensor(every, mine, group=self.group)
+        table.peer_attach(bytes(every.cpu().numpy().tobytes()))
+        dist.barrier(group=self.group)
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def find_or_insert(self, keys, rows_out, status_out=None):
+        return self.t.sharded_find_or_insert(keys, rows_out, status_out, n=keys.numel(), stream=self._stream())
+
+    def lookup(self, keys, rows_out, found_out=None):
+        return self.t.sharded_lookup(keys, rows_out, found_out, n=keys.numel(), stream=self._stream())
+
+    def apply_gradients(self, keys, grads):
+        self.t.sharded_apply_gradients(keys, grads, n=keys.numel(), stream=self._stream())
+
+    def close(self):
+        """All ranks must be done with the table: synchronise, meet, then unmap."""
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
+        self.t.peer_detach()

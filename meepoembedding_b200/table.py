@@ -279,3 +279,31 @@ class Table:
     def gather_rows(self, rows_in, index, rows_out, n=None, stream=None):
         n = self._n(index, n)
         self.lib.check(self.lib.gather_rows(self._h, _ptr(rows_in), _ptr(index), n, _ptr(rows_out), stream))
+
+    # -- sharded verbs over NVLink peer memory (collective; include/meepo.h) -------------------
+    def peer_prepare(self, rank: int, world: int, max_batch: int, region_keys: int = 0) -> bytes:
+        """Allocate this rank's exchange window; returns the opaque blob to all-gather."""
+        buf = C.create_string_buffer(capi.PEER_BLOB_BYTES)
+        self.lib.check(self.lib.peer_prepare(self._h, int(rank), int(world), int(max_batch), int(region_keys), buf))
+        return buf.raw
+
+    def peer_attach(self, blobs: bytes):
+        """`blobs` = the world blobs concatenated in rank order."""
+        self.lib.check(self.lib.peer_attach(self._h, blobs))
+
+    def peer_detach(self):
+        self.lib.check(self.lib.peer_detach(self._h))
+
+    def sharded_find_or_insert(self, keys, rows_out, status_out=None, n=None, stream=None):
+        n = self._n(keys, n)
+        self.lib.check(self.lib.sharded_find_or_insert(self._h, _ptr(keys), n, _ptr(rows_out), _ptr(status_out), stream))
+        return rows_out, status_out
+
+    def sharded_lookup(self, keys, rows_out, found_out=None, n=None, stream=None):
+        n = self._n(keys, n)
+        self.lib.check(self.lib.sharded_lookup(self._h, _ptr(keys), n, _ptr(rows_out), _ptr(found_out), stream))
+        return rows_out, found_out
+
+    def sharded_apply_gradients(self, keys, grads, n=None, stream=None):
+        n = self._n(keys, n)
+        self.lib.check(self.lib.sharded_apply_gradients(self._h, _ptr(keys), _ptr(grads), n, stream))
