@@ -371,7 +371,7 @@ def main():
         gr = (st1["peer_grads_received"] - st0["peer_grads_received"]) / args.steps
         alg["sharded.owner_find_or_insert"] = kr * (16 + 2 * R)
         alg["sharded.owner_apply"] = gr * R + U_avg * (2 * R + 2 * w["dim"] * 4)
-        alg["sharded.push_grads"] = gr * 2 * R
+        alg["dedup.reduce_store"] = B * R + gr * R  # reads every gradient row, stores the unique sums to the owners
         alg["sharded.expand"] = B * 2 * R
     kernels = {}
     for name, (cnt, ms) in prof.items():

@@ -87,11 +87,11 @@ __device__ __forceinline__ uint4 pack4(const float* f) {
 template <bool BF16, int OPT>
 __device__ __forceinline__ void opt_finish(const TableView& t, uint32_t slot, uint32_t q,
                                            const OptIn<BF16, OPT>& in, const float (&g)[Chunk<BF16>::E],
-                                           float alpha, uint4* reduce_out) {
+                                           float alpha, uint4* reduce_row) {
   constexpr int E = Chunk<BF16>::E;
   constexpr int SQ = OptIn<BF16, OPT>::SQ;
   if constexpr (OPT == kStoreOnly) {
-    st_stream(reduce_out + (size_t)slot * t.cpr + q, narrow<BF16>(g));
+    st_stream(reduce_row + q, narrow<BF16>(g));  // kStoreOnly: reduce_row = output row of this sort key
     return;
   }
   uint4* rowp = t.rows + (size_t)slot * t.cpr + q;
@@ -142,10 +142,10 @@ __device__ __forceinline__ void opt_finish(const TableView& t, uint32_t slot, ui
 template <bool BF16, int OPT>
 __device__ __forceinline__ void optimizer_chunk(const TableView& t, uint32_t slot, uint32_t q,
                                                 const float (&g)[Chunk<BF16>::E], float alpha,
-                                                uint4* reduce_out) {
+                                                uint4* reduce_row) {
   OptIn<BF16, OPT> in;
   opt_issue<BF16, OPT>(t, slot, q, in);
-  opt_finish<BF16, OPT>(t, slot, q, in, g, alpha, reduce_out);
+  opt_finish<BF16, OPT>(t, slot, q, in, g, alpha, reduce_row);
 }
 
 // Adam: per-row step count -> scalar step size (double math, rounded once). Every lane of the

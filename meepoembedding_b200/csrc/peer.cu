@@ -13,12 +13,14 @@
 //     barrier
 //     r: expand         rows_out[i] = ret_rows[loc[inverse[i]]]
 //   apply_gradients
-//     r: dedup + fixed-shape pre-reduction of duplicate gradients (rounded to the table dtype)
-//     r: push_grads     (key, summed gradient row) -> o.recv_*[r][p], rows stored over NVLink
+//     r: dedup the batch; assign every unique key its position p at its owner (key -> o.recv_keys[r][p])
+//     r: fixed-shape pre-reduction of duplicate gradients (sort by unique id + segmented sum, rounded
+//        to the table dtype) whose store IS the exchange: each summed row goes straight to
+//        o.recv_grads[r][p] over NVLink — no local copy of the unique gradients, no separate push
 //     barrier
-//     o: group the received entries by slot in an L2-resident scratch table (one cell per key, a
-//        bitmask of contributing senders, contrib[cell][sender] = entry) and apply ONE optimizer
-//        step per key with the senders' partial sums added in rank order — deterministic, no sort
+//     o: slot of every received entry, stable sort by slot (entries enumerate rank-major, so each
+//        key's partial sums stay in rank order) and the same fused reduce + optimizer kernel as the
+//        single table: ONE optimizer step per key, deterministic
 //     barrier
 //
 // Only bulk stores and the barrier flags cross NVLink: every table mutation (CAS insert, tag
@@ -62,9 +64,8 @@ struct PeerWork {
   uint32_t cnt[kMaxPeers];           // entries received from source s
   uint32_t recv_off[kMaxPeers + 1];  // exclusive prefix of cnt
   uint32_t tile_off[kMaxPeers + 1];  // exclusive prefix of ceil(cnt / 32)
-  uint32_t mask;                     // group table size - 1 (power of two >= 2 * received entries)
-  uint32_t n_groups;                 // unique keys among the received entries
-  uint32_t pad[2];
+  uint32_t max_cnt;                  // max over sources of cnt
+  uint32_t pad[3];
 };
 
 struct PeerBlob {  // what ranks hand each other (opaque to the caller, MEEPO_PEER_BLOB_BYTES)
@@ -89,10 +90,7 @@ struct PeerState {
   uint32_t* send_cnt = nullptr;
   PeerWork* work = nullptr;
   uint32_t* loc = nullptr;         // [max_batch]     window position of unique key u: owner * region + p
-  uint2* cells = nullptr;          // [m_max]         {slot, sender bitmask}
-  uint32_t* contrib = nullptr;     // [m_max][world]  entry index of sender s for this cell
-  uint32_t* group_list = nullptr;  // [world*region]  occupied cells
-  uint64_t m_max = 0;
+  uint4* trash_row = nullptr;      // [cpr]           where rows of keys beyond a full lane go
   PeerSet ps{};
   void* opened[kMaxPeers] = {};
   unsigned long long seq = 0;
@@ -176,10 +174,9 @@ __global__ void __launch_bounds__(32) peer_barrier_kernel(const __grid_constant_
     }
     work->recv_off[ps.world] = ro;
     work->tile_off[ps.world] = to;
-    uint32_t m = 1024;
-    while (m < 2u * ro) m <<= 1;
-    work->mask = for_apply ? m - 1 : 0u;
-    work->n_groups = 0;
+    uint32_t mx = 0;
+    for (uint32_t s = 0; s < ps.world; s++) mx = max(mx, work->cnt[s]);
+    work->max_cnt = mx;
     if (ro) atomicAdd(counters + (for_apply ? C_PEER_GRADS : C_PEER_KEYS), (unsigned long long)ro);
   }
 }
@@ -223,54 +220,32 @@ __global__ void __launch_bounds__(256) push_keys_kernel(const __grid_constant__ 
   }
 }
 
-// (key, pre-reduced gradient row) of every unique key -> the owner's window. A warp owns 32
-// consecutive unique keys: the source rows are one contiguous block, the destination rows are
-// whole rows in the owner's region; 4 x 16-byte loads in flight per lane.
-__global__ void __launch_bounds__(256) push_grads_kernel(const __grid_constant__ PeerSet ps,
-                                                         const uint64_t* __restrict__ ukeys,
-                                                         const uint4* __restrict__ ugrads,
-                                                         const unsigned long long* __restrict__ n_unique,
-                                                         uint32_t* __restrict__ send_cnt) {
+// Backward: position of every unique key at its owner. The key goes there now; row_ptrs[u] is where
+// the reduce kernel will store the key's summed gradient row (straight into the owner's window).
+__global__ void __launch_bounds__(256) assign_grad_rows_kernel(const __grid_constant__ PeerSet ps,
+                                                               const uint64_t* __restrict__ ukeys,
+                                                               const unsigned long long* __restrict__ n_unique,
+                                                               uint32_t* __restrict__ send_cnt,
+                                                               uint4** __restrict__ row_ptrs, uint4* trash_row) {
   const uint32_t n = (uint32_t)*n_unique;
   const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-  const uint32_t ntiles = (n + 31u) >> 5;
-  const uint32_t cpr = ps.cpr;
-  for (uint32_t tile = warp; tile < ntiles; tile += nwarps) {
-    const uint32_t u = tile * 32u + lane;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
+    const uint32_t u = base + lane;
     const bool act = u < n;
     const unsigned am = __ballot_sync(0xFFFFFFFFu, act);
-    unsigned long long dst = 0;
-    if (act) {
-      const uint64_t key = __ldg(ukeys + u);
-      const uint32_t o = owner_of(key, ps.world);
-      const uint32_t p = claim_position(send_cnt, o, am, lane);
-      if (p < ps.region) {
-        const size_t e = (size_t)ps.rank * ps.region + p;
-        ps.w[o].recv_keys[e] = key;
-        dst = reinterpret_cast<unsigned long long>(ps.w[o].recv_grads + e * cpr);
-      } else {
-        atomicOr(ps.w[ps.rank].error, (uint32_t)PE_REGION_OVERFLOW);
-      }
+    if (!act) continue;
+    const uint64_t key = __ldg(ukeys + u);
+    const uint32_t o = owner_of(key, ps.world);
+    const uint32_t p = claim_position(send_cnt, o, am, lane);
+    if (p >= ps.region) {
+      atomicOr(ps.w[ps.rank].error, (uint32_t)PE_REGION_OVERFLOW);
+      row_ptrs[u] = trash_row;
+      continue;
     }
-    const uint32_t chunks = min(32u, n - tile * 32u) * cpr;
-    const uint4* src = ugrads + (size_t)tile * 32u * cpr;
-    for (uint32_t c0 = 0; c0 < chunks; c0 += 128) {
-      uint4 v[4];
-      uint4* d[4];
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const uint32_t c = c0 + k * 32 + lane;
-        const uint32_t j = min(c / cpr, 31u);
-        uint4* row = reinterpret_cast<uint4*>(__shfl_sync(0xFFFFFFFFu, dst, j));
-        d[k] = (c < chunks && row) ? row + (c - j * cpr) : nullptr;
-        if (d[k]) v[k] = ld_nc(src + c);
-      }
-#pragma unroll
-      for (int k = 0; k < 4; k++)
-        if (d[k]) st_stream(d[k], v[k]);
-    }
+    const size_t e = (size_t)ps.rank * ps.region + p;
+    ps.w[o].recv_keys[e] = key;
+    row_ptrs[u] = ps.w[o].recv_grads + e * ps.cpr;
   }
 }
 
@@ -286,23 +261,26 @@ __global__ void __launch_bounds__(256) owner_probe_gather_kernel(TableView t, co
   const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
   const uint32_t cpr = CPR > 0 ? (uint32_t)CPR : t.cpr;
   const PeerWindow& me = ps.w[ps.rank];
-  const uint32_t ntiles = work->tile_off[ps.world];
+  const uint32_t max_tiles = (work->max_cnt + 31u) >> 5;
   TileCounts cnt;
-  for (uint32_t tile = warp; tile < ntiles; tile += nwarps) {
-    uint32_t s = 0;
-#pragma unroll
-    for (uint32_t k = 1; k < kMaxPeers; k++) s += (k < ps.world && __ldg(work->tile_off + k) <= tile) ? 1u : 0u;
-    const uint32_t p0 = (tile - __ldg(work->tile_off + s)) * 32u;
-    const uint32_t cnt_s = work->cnt[s];
-    const uint32_t tile_keys = min(32u, cnt_s - p0);
-    const bool valid = lane < tile_keys;
-    const size_t e = (size_t)s * ps.region + p0 + lane;  // in my window: [source][position]
-    const uint64_t key = valid ? ld_window(me.recv_keys + e) : MEEPO_KEY_EMPTY;
-    const uint32_t occ = valid ? ld_window(me.recv_occ + e) : 0u;
-    const size_t r = (size_t)ps.rank * ps.region + p0;    // in the requester's window: [owner][position]
-    probe_gather_tile<CPR, INSERT>(t, key, valid, tile_keys, ps.w[s].ret_rows + r * cpr,
-                                   valid ? ps.w[s].ret_status + r + lane : nullptr, nullptr, nullptr, occ, nl, cnt,
-                                   lane);
+  // Row k of every source's tile list, sources rotated by (rank, k): at any moment the owners are
+  // spread over all requesters (no incast on one NVLink port) and local tiles overlap remote ones.
+  for (uint32_t k = warp; k < max_tiles; k += nwarps) {
+    for (uint32_t j = 0; j < ps.world; j++) {
+      const uint32_t s = (ps.rank + 1u + j + k) % ps.world;
+      const uint32_t p0 = k * 32u;
+      const uint32_t cnt_s = work->cnt[s];
+      if (p0 >= cnt_s) continue;
+      const uint32_t tile_keys = min(32u, cnt_s - p0);
+      const bool valid = lane < tile_keys;
+      const size_t e = (size_t)s * ps.region + p0 + lane;  // in my window: [source][position]
+      const uint64_t key = valid ? ld_window(me.recv_keys + e) : MEEPO_KEY_EMPTY;
+      const uint32_t occ = valid ? ld_window(me.recv_occ + e) : 0u;
+      const size_t r = (size_t)ps.rank * ps.region + p0;    // in the requester's window: [owner][position]
+      probe_gather_tile<CPR, INSERT>(t, key, valid, tile_keys, ps.w[s].ret_rows + r * cpr,
+                                     valid ? ps.w[s].ret_status + r + lane : nullptr, nullptr, nullptr, occ, nl, cnt,
+                                     lane);
+    }
   }
   flush_tile_counts(t, cnt, lane);
 }
@@ -365,134 +343,34 @@ __global__ void __launch_bounds__(256) expand_kernel(const uint4* __restrict__ r
   }
 }
 
-// --- owner: group received gradient entries by key, then one optimizer step per key ---------------
-__global__ void __launch_bounds__(256) owner_clear_kernel(uint2* __restrict__ cells, const PeerWork* __restrict__ work) {
-  const uint32_t m = work->mask + 1u;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x)
-    cells[i] = make_uint2(kNil, 0u);
-}
-
-__device__ __forceinline__ uint32_t hash_slot(uint32_t s) {
-  s ^= s >> 16;
-  s *= 0x7FEB352Du;
-  s ^= s >> 15;
-  s *= 0x846CA68Bu;
-  s ^= s >> 16;
-  return s;
-}
-
-__global__ void __launch_bounds__(256) owner_group_kernel(TableView t, const __grid_constant__ PeerSet ps,
-                                                          PeerWork* __restrict__ work, uint2* __restrict__ cells,
-                                                          uint32_t* __restrict__ contrib,
-                                                          uint32_t* __restrict__ group_list) {
+// --- owner: slot of every received gradient entry (sort key) + its position in the window (value) ---
+// Entries enumerate rank-major, so the stable sort keeps each key's partial sums in rank order.
+// Positions past the received count pad the sort to its host-known size with the "absent" key.
+__global__ void __launch_bounds__(256) recv_slots_kernel(TableView t, const __grid_constant__ PeerSet ps,
+                                                         const PeerWork* __restrict__ work, uint32_t n_pad,
+                                                         uint32_t* __restrict__ sort_key,
+                                                         uint32_t* __restrict__ sort_val) {
   const uint32_t n = work->recv_off[ps.world];
-  const uint32_t mask = work->mask;
-  const uint32_t lane = threadIdx.x & 31u;
   const PeerWindow& me = ps.w[ps.rank];
   uint32_t dropped = 0;
-  const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
-    const uint32_t i = base + lane;
-    bool winner = false;
-    uint32_t h = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x) {
+    uint32_t slot = t.slots, e = 0;
     if (i < n) {
       uint32_t s = 0;
       for (uint32_t k = 1; k < ps.world; k++) s += work->recv_off[k] <= i ? 1u : 0u;
-      const uint32_t e = s * ps.region + (i - work->recv_off[s]);
+      e = s * ps.region + (i - work->recv_off[s]);
       const uint64_t key = ld_window(me.recv_keys + e);
-      const uint32_t slot = key_valid(key) ? probe_find<kReadOnly>(t, key) : kNil;
-      if (slot == kNil) {
+      const uint32_t f = key_valid(key) ? probe_find<kReadOnly>(t, key) : kNil;
+      if (f == kNil)
         dropped++;
-      } else {
-        h = hash_slot(slot) & mask;
-        while (true) {
-          const uint32_t old = atomicCAS(&cells[h].x, kNil, slot);
-          if (old == kNil) winner = true;
-          if (old == kNil || old == slot) break;
-          h = (h + 1) & mask;
-        }
-        atomicOr(&cells[h].y, 1u << s);
-        contrib[(size_t)h * ps.world + s] = e;
-      }
+      else
+        slot = f;
     }
-    const unsigned wm = __ballot_sync(0xFFFFFFFFu, winner);
-    if (wm) {
-      const int leader = __ffs(wm) - 1;
-      uint32_t b = 0;
-      if ((int)lane == leader) b = atomicAdd(&work->n_groups, (uint32_t)__popc(wm));
-      b = __shfl_sync(0xFFFFFFFFu, b, leader);
-      if (winner) group_list[b + __popc(wm & ((1u << lane) - 1u))] = h;
-    }
+    sort_key[i] = slot;
+    sort_val[i] = e;
   }
   dropped = __reduce_add_sync(0xFFFFFFFFu, dropped);
-  if (lane == 0 && dropped) atomicAdd(t.counters + C_DROPPED, (unsigned long long)dropped);
-}
-
-// One group of lanes per key: the senders' partial sums (each already rounded to the table dtype)
-// are added in rank order — a single leaf of the normative tree, <= world terms — and the optimizer
-// is applied to row + state in the same registers. All loads of a key are issued before the math.
-template <bool BF16, int OPT>
-__global__ void __launch_bounds__(256) owner_apply_kernel(TableView t, const __grid_constant__ PeerSet ps,
-                                                          const PeerWork* __restrict__ work,
-                                                          const uint2* __restrict__ cells,
-                                                          const uint32_t* __restrict__ contrib,
-                                                          const uint32_t* __restrict__ group_list,
-                                                          uint32_t group_lanes) {
-  constexpr int E = Chunk<BF16>::E;
-  const uint32_t GL = group_lanes;
-  const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t gl = lane & (GL - 1);
-  const unsigned gmask = (GL == 32 ? 0xFFFFFFFFu : ((1u << GL) - 1u) << (lane & ~(GL - 1)));
-  const uint32_t groups_per_block = blockDim.x / GL;
-  const uint32_t group = blockIdx.x * groups_per_block + threadIdx.x / GL;
-  const uint32_t ngroups = gridDim.x * groups_per_block;
-  const uint32_t U = work->n_groups;
-  const uint4* grads = ps.w[ps.rank].recv_grads;
-  if (blockIdx.x == 0 && threadIdx.x == 0 && U) atomicAdd(t.counters + C_UPDATES, (unsigned long long)U);
-  for (uint32_t g = group; g < U; g += ngroups) {
-    const uint32_t h = __ldg(group_list + g);
-    const uint2 cell = cells[h];
-    const uint32_t slot = cell.x, senders = cell.y;
-    uint32_t ent[kMaxPeers];
-#pragma unroll
-    for (uint32_t s = 0; s < kMaxPeers; s++)
-      ent[s] = ((senders >> s) & 1u) ? __ldg(contrib + (size_t)h * ps.world + s) : kNil;
-    const float alpha = adam_alpha<OPT>(t, slot, gmask, gl == 0);
-    for (uint32_t q = gl; q < t.cpr; q += GL) {
-      OptIn<BF16, OPT> in;
-      opt_issue<BF16, OPT>(t, slot, q, in);
-      uint4 raw[kMaxPeers];
-#pragma unroll
-      for (uint32_t s = 0; s < kMaxPeers; s++)
-        if (ent[s] != kNil) raw[s] = ld_stream(grads + (size_t)ent[s] * t.cpr + q);
-      float acc[E];
-      bool first = true;
-#pragma unroll
-      for (uint32_t s = 0; s < kMaxPeers; s++) {
-        if (ent[s] == kNil) continue;
-        float x[E];
-        widen<BF16>(raw[s], x);
-        if (first) {
-#pragma unroll
-          for (int k = 0; k < E; k++) acc[k] = x[k];
-          first = false;
-        } else {
-#pragma unroll
-          for (int k = 0; k < E; k++) acc[k] = __fadd_rn(acc[k], x[k]);
-        }
-      }
-      opt_finish<BF16, OPT>(t, slot, q, in, acc, alpha, nullptr);
-    }
-  }
-}
-
-template <bool BF16>
-static const void* pick_owner_apply(int opt) {
-  switch (opt) {
-    case MEEPO_SGD: return (const void*)owner_apply_kernel<BF16, MEEPO_SGD>;
-    case MEEPO_ADAGRAD: return (const void*)owner_apply_kernel<BF16, MEEPO_ADAGRAD>;
-    default: return (const void*)owner_apply_kernel<BF16, MEEPO_ADAM>;
-  }
+  if ((threadIdx.x & 31u) == 0 && dropped) atomicAdd(t.counters + C_DROPPED, (unsigned long long)dropped);
 }
 
 // --- host side ---------------------------------------------------------------------------------
@@ -503,7 +381,8 @@ static size_t forward_ws_bytes(const meepo_table* t, const PeerState* p) {
 }
 static size_t backward_ws_bytes(const meepo_table* t, const PeerState* p) {
   const uint64_t n = p->max_batch;
-  return dedup_bytes(t, n, true) + Workspace::pad(n * 8) + Workspace::pad(n * (size_t)t->row_bytes) + 256 + 4096;
+  return dedup_bytes(t, n, true) + 2 * Workspace::pad(n * 8) + 256 +
+         SegWork::bytes((uint64_t)p->world * p->region, t->v.dim, bits_for(t->v.slots)) + 4096;
 }
 
 void destroy_peer(meepo_table* t) {
@@ -607,41 +486,33 @@ static meepo_status sharded_apply(meepo_table* t, const uint64_t* keys, const vo
   PeerState* p = t->peer;
   MEEPO_TRY(t->ws.reserve(backward_ws_bytes(t, p), stream));
   uint64_t* ukeys = t->ws.take<uint64_t>(std::max<uint64_t>(n, 1));
-  uint4* ugrads = reinterpret_cast<uint4*>(t->ws.take<char>(std::max<uint64_t>(n, 1) * t->row_bytes));
+  uint4** row_ptrs = t->ws.take<uint4*>(std::max<uint64_t>(n, 1));
   uint64_t* n_unique = t->ws.take<uint64_t>(1);
-  MEEPO_TRY(dedup_run(t, keys, n ? grads : nullptr, n, DedupOut{ukeys, ugrads, nullptr, n_unique, nullptr}, stream));
+  const uint64_t n_pad = (uint64_t)p->world * p->region;
+  SegWork ow;  // owner side
+  ow.take(t->ws, n_pad, t->v.dim, bits_for(t->v.slots));
+  SegWork sw;  // sender side
+  DedupOut dd{ukeys, nullptr, nullptr, n_unique, nullptr, reinterpret_cast<void* const*>(row_ptrs)};
+  MEEPO_TRY(dedup_hash(t, keys, n, dd, true, sw, stream));
   {
-    ProfScope ps(t, "sharded.push_grads", stream);
+    ProfScope ps(t, "sharded.assign_grad_rows", stream);
     MEEPO_CUDA_TRY(cudaMemsetAsync(p->send_cnt, 0, kMaxPeers * 4, stream));
-    const uint64_t tiles = (std::max<uint64_t>(n, 1) + 31) / 32;
-    const int grid = grid_for(t, (const void*)push_grads_kernel, 256, 0, (tiles + 7) / 8);
-    push_grads_kernel<<<grid, 256, 0, stream>>>(p->ps, ukeys, ugrads, (const unsigned long long*)n_unique, p->send_cnt);
+    const int grid = grid_for(t, (const void*)assign_grad_rows_kernel, 256, 0, (std::max<uint64_t>(n, 1) + 255) / 256);
+    assign_grad_rows_kernel<<<grid, 256, 0, stream>>>(p->ps, ukeys, (const unsigned long long*)n_unique, p->send_cnt,
+                                                      row_ptrs, p->trash_row);
     MEEPO_CUDA_TRY(cudaGetLastError());
   }
+  MEEPO_TRY(dedup_reduce(t, sw, grads, n, dd, stream));  // summed rows land in the owners' windows
   MEEPO_TRY(barrier(t, p->send_cnt, true, stream));
-  const uint64_t max_recv = (uint64_t)p->world * p->region;
   {
-    ProfScope ps(t, "sharded.owner_group(2 kernels)", stream);
-    const int g1 = grid_for(t, (const void*)owner_clear_kernel, 256, 0, (p->m_max + 255) / 256);
-    owner_clear_kernel<<<g1, 256, 0, stream>>>(p->cells, p->work);
-    const int g2 = grid_for(t, (const void*)owner_group_kernel, 256, 0, (max_recv + 255) / 256);
-    owner_group_kernel<<<g2, 256, 0, stream>>>(t->v, p->ps, p->work, p->cells, p->contrib, p->group_list);
+    ProfScope ps(t, "sharded.owner_slots", stream);
+    const int grid = grid_for(t, (const void*)recv_slots_kernel, 256, 0, (n_pad + 255) / 256);
+    recv_slots_kernel<<<grid, 256, 0, stream>>>(t->v, p->ps, p->work, (uint32_t)n_pad, ow.sk_in, ow.sv_in);
     MEEPO_CUDA_TRY(cudaGetLastError());
   }
-  {
-    ProfScope ps(t, "sharded.owner_apply", stream);
-    uint32_t gl = 1;
-    while (gl * 2 <= t->v.cpr && gl < 32) gl *= 2;
-    const void* kern = t->v.dtype == MEEPO_BF16 ? pick_owner_apply<true>(t->v.opt) : pick_owner_apply<false>(t->v.opt);
-    const uint64_t groups_per_block = 256 / gl;
-    const int grid = grid_for(t, kern, 256, 0, (max_recv + groups_per_block - 1) / groups_per_block);
-    const PeerWork* work = p->work;
-    const uint2* cells = p->cells;
-    const uint32_t* contrib = p->contrib;
-    const uint32_t* group_list = p->group_list;
-    void* args[] = {&t->v, &p->ps, &work, &cells, &contrib, &group_list, &gl};
-    MEEPO_CUDA_TRY(cudaLaunchKernel(kern, dim3(grid), dim3(256), args, 0, stream));
-  }
+  static const char* const names[4] = {"sharded.owner_sort(cub)", "sharded.owner_segments(3 kernels)",
+                                       "sharded.owner_apply", "sharded.owner_long_segments(2 kernels)"};
+  MEEPO_TRY(run_segmented(t, ow, t->v.slots, p->ps.w[p->rank].recv_grads, t->v.opt, nullptr, stream, nullptr, names));
   return barrier(t, nullptr, false, stream);
 }
 
@@ -724,31 +595,21 @@ MEEPO_API meepo_status meepo_peer_prepare(meepo_table* t, uint32_t rank, uint32_
   if ((e = cudaMalloc(&p->window, p->window_bytes)) != cudaSuccess) return bail(e, "cudaMalloc(exchange window)");
   if ((e = cudaMemset(p->window, 0, kWindowHeader)) != cudaSuccess) return bail(e, "cudaMemset");
   // private scratch
-  const uint64_t max_recv = (uint64_t)world * region_keys;
-  uint64_t m = 1024;
-  while (m < 2 * max_recv) m <<= 1;
-  p->m_max = m;
   size_t off = 0;
   const size_t o_cnt = off;
   off += align_up(kMaxPeers * 4);
   const size_t o_work = off;
   off += align_up(sizeof(PeerWork));
+  const size_t o_trash = off;
+  off += align_up((size_t)t->v.cpr * 16);
   const size_t o_loc = off;
   off += align_up(max_batch * 4);
-  const size_t o_cells = off;
-  off += align_up(m * 8);
-  const size_t o_contrib = off;
-  off += align_up(m * (size_t)world * 4);
-  const size_t o_list = off;
-  off += align_up(max_recv * 4);
   if ((e = cudaMalloc(&p->local, off)) != cudaSuccess) return bail(e, "cudaMalloc(peer scratch)");
   if ((e = cudaMemset(p->local, 0, o_loc)) != cudaSuccess) return bail(e, "cudaMemset");
   p->send_cnt = reinterpret_cast<uint32_t*>(p->local + o_cnt);
   p->work = reinterpret_cast<PeerWork*>(p->local + o_work);
+  p->trash_row = reinterpret_cast<uint4*>(p->local + o_trash);
   p->loc = reinterpret_cast<uint32_t*>(p->local + o_loc);
-  p->cells = reinterpret_cast<uint2*>(p->local + o_cells);
-  p->contrib = reinterpret_cast<uint32_t*>(p->local + o_contrib);
-  p->group_list = reinterpret_cast<uint32_t*>(p->local + o_list);
   // the workspace never grows (cudaFree = device-wide sync) once the verbs are in flight
   if (t->ws.reserve(std::max(forward_ws_bytes(t, p), backward_ws_bytes(t, p)), nullptr) != MEEPO_OK) {
     destroy_peer(t);

@@ -126,9 +126,11 @@ __global__ void __launch_bounds__(256) dedup_insert_kernel(const uint64_t* __res
     uint32_t p = kNil;
     if (key_valid(key)) {
       uint32_t h = (uint32_t)(mix64(key ^ 0x5851F42D4C957F2Dull) >> 32) & mask;
-      while (true) {
-        const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(scratch + h),
-                                                 (unsigned long long)MEEPO_KEY_EMPTY, (unsigned long long)key);
+      while (true) {  // read first: duplicates of a hot key must not serialise on one atomic
+        unsigned long long old = __ldcg(reinterpret_cast<const unsigned long long*>(scratch + h));
+        if (old == MEEPO_KEY_EMPTY)
+          old = atomicCAS(reinterpret_cast<unsigned long long*>(scratch + h), (unsigned long long)MEEPO_KEY_EMPTY,
+                          (unsigned long long)key);
         if (old == MEEPO_KEY_EMPTY || old == key) {
           p = h;
           break;
@@ -250,8 +252,9 @@ size_t dedup_bytes(const meepo_table* t, uint64_t n, bool with_grads) {
   return need;
 }
 
-meepo_status dedup_run(meepo_table* t, const uint64_t* keys, const void* grads, uint64_t n, const DedupOut& o,
-                       cudaStream_t stream) {
+// phase 1: unique keys, inverse, occurrences; with_grads also prepares the (uid, batch index) sort input
+meepo_status dedup_hash(meepo_table* t, const uint64_t* keys, uint64_t n, const DedupOut& o, bool with_grads,
+                        SegWork& w, cudaStream_t stream) {
   if (n == 0) {
     MEEPO_CUDA_TRY(cudaMemsetAsync(o.n_unique, 0, 8, stream));
     return MEEPO_OK;
@@ -265,27 +268,37 @@ meepo_status dedup_run(meepo_table* t, const uint64_t* keys, const void* grads, 
   uint32_t* uid_of_slot = t->ws.take<uint32_t>(m);
   uint32_t* tile_count = t->ws.take<uint32_t>(ntiles + 1);
   uint32_t* tile_off = t->ws.take<uint32_t>(ntiles + 1);
+  if (with_grads) w.take(t->ws, n, t->v.dim, end_bit);
+  ProfScope ps(t, "dedup.hash(5 kernels)", stream);
+  MEEPO_CUDA_TRY(cudaMemsetAsync(scratch, 0xFF, (size_t)m * 8, stream));
+  if (o.occurrences) MEEPO_CUDA_TRY(cudaMemsetAsync(o.occurrences, 0, n * 4, stream));
+  const int grid = grid_for(t, (const void*)dedup_insert_kernel, 256, 0, (n + 255) / 256);
+  dedup_insert_kernel<<<grid, 256, 0, stream>>>(keys, (uint32_t)n, scratch, m - 1, pos);
+  occ_count_kernel<<<ntiles, 256, 0, stream>>>(scratch, m, tile_count);
+  excl_scan_kernel<<<1, 1024, 0, stream>>>(tile_count, tile_off, ntiles, (unsigned long long*)o.n_unique);
+  occ_fill_kernel<<<ntiles, 256, 0, stream>>>(scratch, m, tile_off, uid_of_slot, o.unique_keys);
+  dedup_inverse_kernel<<<grid, 256, 0, stream>>>(pos, (uint32_t)n, uid_of_slot, o.inverse,
+                                                 with_grads ? w.sk_in : nullptr, with_grads ? w.sv_in : nullptr,
+                                                 o.occurrences);
+  MEEPO_CUDA_TRY(cudaGetLastError());
+  return MEEPO_OK;
+}
+
+// phase 2: fixed-shape sum of each unique key's gradient rows, rounded to the table dtype, stored to
+// o.grads_out[uid] or through o.grad_rows[uid] (a pointer per unique key, e.g. into a peer's window)
+meepo_status dedup_reduce(meepo_table* t, SegWork& w, const void* grads, uint64_t n, const DedupOut& o,
+                          cudaStream_t stream) {
+  if (n == 0) return MEEPO_OK;
+  static const char* const names[4] = {"dedup.radix_sort(cub)", "dedup.segments(3 kernels)", "dedup.reduce_store",
+                                       "dedup.long_segments(2 kernels)"};
+  return run_segmented(t, w, (uint32_t)n, grads, kReduceStoreOnly, o.grads_out, stream, nullptr, names, o.grad_rows);
+}
+
+meepo_status dedup_run(meepo_table* t, const uint64_t* keys, const void* grads, uint64_t n, const DedupOut& o,
+                       cudaStream_t stream) {
   SegWork w;
-  if (grads) w.take(t->ws, n, t->v.dim, end_bit);
-  {
-    ProfScope ps(t, "dedup.hash(5 kernels)", stream);
-    MEEPO_CUDA_TRY(cudaMemsetAsync(scratch, 0xFF, (size_t)m * 8, stream));
-    if (o.occurrences) MEEPO_CUDA_TRY(cudaMemsetAsync(o.occurrences, 0, n * 4, stream));
-    const int grid = grid_for(t, (const void*)dedup_insert_kernel, 256, 0, (n + 255) / 256);
-    dedup_insert_kernel<<<grid, 256, 0, stream>>>(keys, (uint32_t)n, scratch, m - 1, pos);
-    occ_count_kernel<<<ntiles, 256, 0, stream>>>(scratch, m, tile_count);
-    excl_scan_kernel<<<1, 1024, 0, stream>>>(tile_count, tile_off, ntiles, (unsigned long long*)o.n_unique);
-    occ_fill_kernel<<<ntiles, 256, 0, stream>>>(scratch, m, tile_off, uid_of_slot, o.unique_keys);
-    dedup_inverse_kernel<<<grid, 256, 0, stream>>>(pos, (uint32_t)n, uid_of_slot, o.inverse,
-                                                   grads ? w.sk_in : nullptr, grads ? w.sv_in : nullptr,
-                                                   o.occurrences);
-    MEEPO_CUDA_TRY(cudaGetLastError());
-  }
-  if (grads) {
-    static const char* const names[4] = {"dedup.radix_sort(cub)", "dedup.segments(3 kernels)", "dedup.reduce_store",
-                                         "dedup.long_segments(2 kernels)"};
-    MEEPO_TRY(run_segmented(t, w, (uint32_t)n, grads, kReduceStoreOnly, o.grads_out, stream, nullptr, names));
-  }
+  MEEPO_TRY(dedup_hash(t, keys, n, o, grads != nullptr, w, stream));
+  if (grads) MEEPO_TRY(dedup_reduce(t, w, grads, n, o, stream));
   return MEEPO_OK;
 }
 
@@ -332,7 +345,7 @@ MEEPO_API meepo_status meepo_reduce_duplicates(meepo_table* t, const uint64_t* k
   DeviceGuard guard(t->device);
   cudaStream_t stream = (cudaStream_t)stream_;
   MEEPO_TRY(t->ws.reserve(dedup_bytes(t, n, grads != nullptr), stream));
-  return dedup_run(t, keys, grads, n, DedupOut{unique_keys_out, grads_out, inverse_out, n_unique_out, nullptr}, stream);
+  return dedup_run(t, keys, grads, n, DedupOut{unique_keys_out, grads_out, inverse_out, n_unique_out, nullptr, nullptr}, stream);
 }
 
 MEEPO_API meepo_status meepo_gather_rows(meepo_table* t, const void* rows_in, const uint32_t* index, uint64_t n,

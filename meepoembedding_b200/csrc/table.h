@@ -153,7 +153,7 @@ constexpr int kReduceStoreOnly = 3;
 int bits_for(uint32_t max_value);
 meepo_status run_segmented(meepo_table* t, SegWork& w, uint32_t limit, const void* grads, int mode,
                            void* reduce_out, cudaStream_t stream, cudaEvent_t grads_ready,
-                           const char* const* names);
+                           const char* const* names, void* const* reduce_rows = nullptr);
 // shard.cu: batch-level dedup. unique_keys[U] (order unspecified), inverse[n] (kNil for invalid
 // keys), *n_unique = U (device), occurrences[U] = duplicates per unique key (optional), grads_out[U] =
 // fixed-shape sum of each key's gradient rows rounded to the table dtype (with grads only).
@@ -163,8 +163,14 @@ struct DedupOut {
   uint32_t* inverse;
   uint64_t* n_unique;
   uint32_t* occurrences;
+  void* const* grad_rows;  // optional: destination row of unique key u instead of grads_out[u]
 };
+struct SegWork;
 size_t dedup_bytes(const meepo_table* t, uint64_t n, bool with_grads);
+meepo_status dedup_hash(meepo_table* t, const uint64_t* keys, uint64_t n, const DedupOut& o, bool with_grads,
+                        SegWork& w, cudaStream_t stream);
+meepo_status dedup_reduce(meepo_table* t, SegWork& w, const void* grads, uint64_t n, const DedupOut& o,
+                          cudaStream_t stream);
 meepo_status dedup_run(meepo_table* t, const uint64_t* keys, const void* grads, uint64_t n, const DedupOut& o,
                        cudaStream_t stream);
 int grid_for(const meepo_table* t, const void* kernel, int block, size_t smem, uint64_t blocks_needed);

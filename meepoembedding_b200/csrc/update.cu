@@ -208,8 +208,18 @@ struct ApplyArgs {
   float* partial;  // [leaves][dim]
   uint32_t group_lanes;  // power of two <= min(cpr, 32)
   uint32_t limit;        // sort keys >= limit form the "absent key" segment and are skipped
-  uint4* reduce_out;     // kStoreOnly: [unique][cpr]
+  uint4* reduce_out;         // kStoreOnly: [unique][cpr] ...
+  uint4* const* reduce_rows;  // ... or one destination row pointer per sort key (may point into a peer's window)
 };
+
+// kStoreOnly: where the summed row of sort key `key` goes.
+template <int OPT>
+__device__ __forceinline__ uint4* reduce_row_of(const ApplyArgs& a, uint32_t key, uint32_t cpr) {
+  if constexpr (OPT != kStoreOnly) return nullptr;
+  if (a.reduce_rows)
+    return reinterpret_cast<uint4*>(__ldg(reinterpret_cast<const unsigned long long*>(a.reduce_rows) + key));
+  return a.reduce_out + (size_t)key * cpr;
+}
 
 // A4: one group of lanes per segment (unique key)
 template <bool BF16, int OPT>
@@ -244,7 +254,7 @@ __global__ void __launch_bounds__(256) apply_kernel(TableView t, ApplyArgs a) {
     for (uint32_t q = gl; q < t.cpr; q += GL) {
       float acc[E];
       reduce_positions<BF16>(a.grads, a.sorted_idx, s0, s1, t.cpr, q, acc);
-      optimizer_chunk<BF16, OPT>(t, slot, q, acc, alpha, a.reduce_out);
+      optimizer_chunk<BF16, OPT>(t, slot, q, acc, alpha, reduce_row_of<OPT>(a, slot, t.cpr));
     }
   }
 }
@@ -308,14 +318,14 @@ __global__ void __launch_bounds__(256) apply_pipelined_kernel(TableView t, Apply
       float acc[E];
       widen<BF16>(gA, acc);
       if (cntA > 1) reduce_tail<BF16>(a.grads, a.sorted_idx, da.x + 1, da.x + cntA, cpr, q, acc);
-      opt_finish<BF16, OPT>(t, da.y, q, inA, acc, alpha, a.reduce_out);
+      opt_finish<BF16, OPT>(t, da.y, q, inA, acc, alpha, reduce_row_of<OPT>(a, da.y, cpr));
     }
     if (okB) {
       const float alpha = adam_alpha<OPT>(t, db.y, gmask, q == 0);
       float acc[E];
       widen<BF16>(gB, acc);
       if (cntB > 1) reduce_tail<BF16>(a.grads, a.sorted_idx, db.x + 1, db.x + cntB, cpr, q, acc);
-      opt_finish<BF16, OPT>(t, db.y, q, inB, acc, alpha, a.reduce_out);
+      opt_finish<BF16, OPT>(t, db.y, q, inB, acc, alpha, reduce_row_of<OPT>(a, db.y, cpr));
     }
     da = na;
     db = nb;
@@ -380,7 +390,7 @@ __global__ void __launch_bounds__(256) long_finish_kernel(TableView t, ApplyArgs
           acc[4 * k + 3] = __fadd_rn(acc[4 * k + 3], x.w);
         }
       }
-      optimizer_chunk<BF16, OPT>(t, slot, q, acc, alpha, a.reduce_out);
+      optimizer_chunk<BF16, OPT>(t, slot, q, acc, alpha, reduce_row_of<OPT>(a, slot, t.cpr));
     }
   }
 }
@@ -462,7 +472,7 @@ int bits_for(uint32_t max_value) {
 // (kStoreOnly -> reduce_out[sort key]).
 meepo_status run_segmented(meepo_table* t, SegWork& w, uint32_t limit, const void* grads, int mode,
                            void* reduce_out, cudaStream_t stream, cudaEvent_t grads_ready,
-                           const char* const* names) {
+                           const char* const* names, void* const* reduce_rows) {
   const uint32_t n32 = w.n;
   {
     ProfScope ps(t, names[0], stream);
@@ -490,6 +500,7 @@ meepo_status run_segmented(meepo_table* t, SegWork& w, uint32_t limit, const voi
   a.partial = w.partial;
   a.limit = limit;
   a.reduce_out = reinterpret_cast<uint4*>(reduce_out);
+  a.reduce_rows = reinterpret_cast<uint4* const*>(reduce_rows);
   uint32_t gl = 1;
   while (gl * 2 <= t->v.cpr && gl < 32) gl *= 2;
   a.group_lanes = gl;
