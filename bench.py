@@ -133,6 +133,17 @@ class ClockSampler:
         except Exception:
             self.p = None
 
+    def mark(self):
+        """Samples taken before this call (start-up, idle wait) are not reported."""
+        self.skip = self.count()
+
+    def count(self):
+        try:
+            self.f.flush()
+            return sum(1 for _ in open(self.f.name))
+        except Exception:
+            return 0
+
     def stop(self):
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -141,6 +152,7 @@ class ClockSampler:
         self.p.wait()
         self.f.flush()
         rows = [l.split(", ") for l in open(self.f.name).read().strip().splitlines() if l.strip()]
+        rows = rows[getattr(self, "skip", 0):] or rows[-1:]
         os.unlink(self.f.name)
         sm, mx, reasons = [], [], set()
         for r in rows:
@@ -335,13 +347,19 @@ def main():
             dist_.barrier()
             torch.cuda.synchronize()
 
+    clocks = ClockSampler(local_rank) if rank == 0 else None
     for i in range(args.warmup):
         step(i)
+    barrier()
+    if rank == 0:  # nvidia-smi takes a moment to start: wait for its first line, then use only what follows
+        t_wait = time.perf_counter()
+        while clocks.count() < 1 and time.perf_counter() - t_wait < 3.0:
+            time.sleep(0.02)
+        clocks.mark()
     barrier()
     st0 = table.stats()
     upd0 = st0["updates"]
     table.profile(True)
-    clocks = ClockSampler(local_rank)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
@@ -350,7 +368,7 @@ def main():
     e1.record(stream)
     barrier()
     ms_total = e0.elapsed_time(e1)
-    clk = clocks.stop()
+    clk = clocks.stop() if clocks is not None else None
     prof = table.profile_read()
     table.profile(False)
     st1 = table.stats()

@@ -510,8 +510,8 @@ static meepo_status sharded_apply(meepo_table* t, const uint64_t* keys, const vo
     recv_slots_kernel<<<grid, 256, 0, stream>>>(t->v, p->ps, p->work, (uint32_t)n_pad, ow.sk_in, ow.sv_in);
     MEEPO_CUDA_TRY(cudaGetLastError());
   }
-  static const char* const names[4] = {"sharded.owner_sort(cub)", "sharded.owner_segments(3 kernels)",
-                                       "sharded.owner_apply", "sharded.owner_long_segments(2 kernels)"};
+  static const char* const names[5] = {"sharded.owner_sort(cub)", "sharded.owner_segments(3 kernels)",
+                                       "sharded.owner_apply", "sharded.owner_long_leaves", "sharded.owner_long_finish"};
   MEEPO_TRY(run_segmented(t, ow, t->v.slots, p->ps.w[p->rank].recv_grads, t->v.opt, nullptr, stream, nullptr, names));
   return barrier(t, nullptr, false, stream);
 }

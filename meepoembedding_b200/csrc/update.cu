@@ -17,6 +17,10 @@
 namespace meepo {
 
 constexpr uint32_t kLeaf = MEEPO_REDUCE_LEAF;
+// Segments with more duplicates than this leave the per-segment kernel for the leaf kernels (the sum
+// has the same normative order either way): a 256-term chain in one group of lanes is a long
+// latency-bound tail, whereas leaves run one per group with 8 row loads in flight.
+constexpr uint32_t kLongSeg = 32;
 constexpr int kSegTile = 1024;  // sorted positions per CTA in the segment-head passes
 
 struct LongSeg {
@@ -154,33 +158,33 @@ __global__ void __launch_bounds__(256) seg_fill_kernel(const uint32_t* __restric
 }
 
 
-template <bool BF16>
+template <bool BF16, int UNROLL = 4>
 __device__ __forceinline__ void reduce_tail(const uint4* __restrict__ grads, const uint32_t* __restrict__ sidx,
                                             uint32_t j0, uint32_t s1, uint32_t cpr, uint32_t q,
                                             float (&acc)[Chunk<BF16>::E]);
 
 // acc = ((g[s0] + g[s0+1]) + ...) over sorted positions [s0, s1), chunk q of every row.
-template <bool BF16>
+template <bool BF16, int UNROLL = 4>
 __device__ __forceinline__ void reduce_positions(const uint4* __restrict__ grads,
                                                  const uint32_t* __restrict__ sidx, uint32_t s0, uint32_t s1,
                                                  uint32_t cpr, uint32_t q, float (&acc)[Chunk<BF16>::E]) {
   widen<BF16>(ld_nc(grads + (size_t)sidx[s0] * cpr + q), acc);
-  reduce_tail<BF16>(grads, sidx, s0 + 1, s1, cpr, q, acc);
+  reduce_tail<BF16, UNROLL>(grads, sidx, s0 + 1, s1, cpr, q, acc);
 }
 
 // acc = ((acc + g[j0]) + g[j0+1]) + ... over sorted positions [j0, s1)
-template <bool BF16>
+template <bool BF16, int UNROLL>
 __device__ __forceinline__ void reduce_tail(const uint4* __restrict__ grads, const uint32_t* __restrict__ sidx,
                                             uint32_t j0, uint32_t s1, uint32_t cpr, uint32_t q,
                                             float (&acc)[Chunk<BF16>::E]) {
   constexpr int E = Chunk<BF16>::E;
   uint32_t j = j0;
-  for (; j + 4 <= s1; j += 4) {
-    uint4 raw[4];
+  for (; j + UNROLL <= s1; j += UNROLL) {
+    uint4 raw[UNROLL];
 #pragma unroll
-    for (int u = 0; u < 4; u++) raw[u] = ld_nc(grads + (size_t)sidx[j + u] * cpr + q);
+    for (int u = 0; u < UNROLL; u++) raw[u] = ld_nc(grads + (size_t)sidx[j + u] * cpr + q);
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
+    for (int u = 0; u < UNROLL; u++) {
       float g[E];
       widen<BF16>(raw[u], g);
 #pragma unroll
@@ -238,7 +242,7 @@ __global__ void __launch_bounds__(256) apply_kernel(TableView t, ApplyArgs a) {
     const uint32_t slot = a.sorted_slot[s0];
     if (slot >= a.limit) continue;  // the segment of absent / invalid keys
     const uint32_t cnt = s1 - s0;
-    if (cnt > kLeaf) {  // hand over to the leaf kernels
+    if (cnt > kLongSeg) {  // hand over to the leaf kernels
       const uint32_t nleaf = (cnt + kLeaf - 1) / kLeaf;
       uint32_t base = 0;
       if (gl == 0) {
@@ -286,7 +290,7 @@ __global__ void __launch_bounds__(256) apply_pipelined_kernel(TableView t, Apply
     const uint32_t nc = desc(un + 2).x;
     const uint32_t cntA = db.x - da.x, cntB = ec - db.x;
     const bool liveA = da.y < a.limit, liveB = (u + 1 < U) && db.y < a.limit;
-    const bool okA = liveA && cntA <= kLeaf, okB = liveB && cntB <= kLeaf;
+    const bool okA = liveA && cntA <= kLongSeg, okB = liveB && cntB <= kLongSeg;
     uint4 gA = make_uint4(0, 0, 0, 0), gB = gA;
     OptIn<BF16, OPT> inA, inB;
     if (okA) {
@@ -301,7 +305,7 @@ __global__ void __launch_bounds__(256) apply_pipelined_kernel(TableView t, Apply
     for (int h = 0; h < 2; h++) {  // segments longer than a leaf go to the leaf kernels
       const bool live = h ? liveB : liveA;
       const uint32_t cnt = h ? cntB : cntA;
-      if (live && cnt > kLeaf) {
+      if (live && cnt > kLongSeg) {
         const uint32_t nleaf = (cnt + kLeaf - 1) / kLeaf;
         uint32_t base = 0;
         if (q == 0) {
@@ -334,64 +338,123 @@ __global__ void __launch_bounds__(256) apply_pipelined_kernel(TableView t, Apply
   }
 }
 
-// A5: one group per leaf of a long segment -> partial[leaf]
+// A5: leaves of long segments -> partial[leaf][dim]. A leaf is a chain of up to 256 adds in batch
+// order per column; what can be hidden is the latency under it. One thread owns one 4-byte WORD of
+// the row (one fp32 column, or two bf16 columns), so a batch of 16 independent row loads costs 16
+// registers and a warp still reads 128 contiguous bytes per row; the indices of the next batch are
+// fetched (one broadcast load per warp) while the current batch is in flight.
+__device__ __forceinline__ uint32_t ld_nc_u32(const uint32_t* p) {
+  uint32_t r;
+  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
+
 template <bool BF16>
-__global__ void __launch_bounds__(256) leaf_kernel(TableView t, ApplyArgs a) {
-  constexpr int E = Chunk<BF16>::E;
-  const uint32_t GL = a.group_lanes;
-  const uint32_t gl = threadIdx.x & (GL - 1);
-  const uint32_t groups_per_block = blockDim.x / GL;
-  const uint32_t group = blockIdx.x * groups_per_block + threadIdx.x / GL;
-  const uint32_t ngroups = gridDim.x * groups_per_block;
+__global__ void __launch_bounds__(256) leaf_kernel(TableView t, ApplyArgs a, uint32_t tpl /* threads per leaf */) {
+  constexpr uint32_t B = 16;
+  const uint32_t W = t.cpr * 4;  // 4-byte words per row
+  const uint32_t sub = threadIdx.x / tpl, wi = threadIdx.x % tpl;
+  const uint32_t lpc = blockDim.x / tpl;  // leaves per CTA
   const uint32_t nleaves = a.ds->num_leaves;
-  for (uint32_t l = group; l < nleaves; l += ngroups) {
+  const uint32_t* g32 = reinterpret_cast<const uint32_t*>(a.grads);
+  for (uint32_t l = blockIdx.x * lpc + sub; l < nleaves; l += gridDim.x * lpc) {
     const uint2 d = a.leaf_desc[l];
     const uint32_t s0 = a.seg_start[d.x] + d.y * kLeaf;
-    const uint32_t s1 = min(a.seg_start[d.x + 1], s0 + kLeaf);
-    for (uint32_t q = gl; q < t.cpr; q += GL) {
-      float acc[E];
-      reduce_positions<BF16>(a.grads, a.sorted_idx, s0, s1, t.cpr, q, acc);
-      float4* p = reinterpret_cast<float4*>(a.partial + (size_t)l * t.dim + (size_t)q * E);
+    const uint32_t cnt = min(a.seg_start[d.x + 1], s0 + kLeaf) - s0;
+    const uint32_t* sidx = a.sorted_idx + s0;
+    for (uint32_t wb = 0; wb < W; wb += tpl) {
+      const uint32_t w = wb + wi;
+      if (w >= W) continue;
+      float acc0 = 0.0f, acc1 = 0.0f;
+      bool first = true;
+      uint32_t ia[B];
 #pragma unroll
-      for (int k = 0; k < E / 4; k++) p[k] = make_float4(acc[4 * k], acc[4 * k + 1], acc[4 * k + 2], acc[4 * k + 3]);
+      for (uint32_t u = 0; u < B; u++) ia[u] = u < cnt ? __ldg(sidx + u) : 0u;
+      for (uint32_t j = 0; j < cnt; j += B) {
+        uint32_t x[B];
+#pragma unroll
+        for (uint32_t u = 0; u < B; u++)
+          if (j + u < cnt) x[u] = ld_nc_u32(g32 + (size_t)ia[u] * W + w);
+#pragma unroll
+        for (uint32_t u = 0; u < B; u++) ia[u] = j + B + u < cnt ? __ldg(sidx + j + B + u) : 0u;
+#pragma unroll
+        for (uint32_t u = 0; u < B; u++) {
+          if (j + u >= cnt) continue;
+          const float g0 = BF16 ? __uint_as_float(x[u] << 16) : __uint_as_float(x[u]);
+          const float g1 = BF16 ? __uint_as_float(x[u] & 0xFFFF0000u) : 0.0f;
+          if (first) {
+            acc0 = g0;
+            acc1 = g1;
+            first = false;
+          } else {
+            acc0 = __fadd_rn(acc0, g0);
+            if (BF16) acc1 = __fadd_rn(acc1, g1);
+          }
+        }
+      }
+      if (BF16) {
+        *reinterpret_cast<float2*>(a.partial + (size_t)l * t.dim + 2 * w) = make_float2(acc0, acc1);
+      } else {
+        a.partial[(size_t)l * t.dim + w] = acc0;
+      }
     }
   }
 }
 
-// A6: one group per long segment: G = ((leaf_0 + leaf_1) + leaf_2) + ..., then the optimizer
+// A6: one CTA per long segment: G = ((leaf_0 + leaf_1) + leaf_2) + ..., then the optimizer.
+// The hottest Zipf key of a 4M batch has ~1300 leaves, and the order of the sum is normative, so the
+// chain cannot be split — but its loads can: one thread per COLUMN keeps 32 independent, coalesced
+// 4-byte loads in flight and adds them in leaf order; the sums are transposed through shared memory
+// into the 16-byte-chunk layout of the optimizer step.
 template <bool BF16, int OPT>
 __global__ void __launch_bounds__(256) long_finish_kernel(TableView t, ApplyArgs a) {
   constexpr int E = Chunk<BF16>::E;
-  const uint32_t GL = a.group_lanes;
-  const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t gl = lane & (GL - 1);
-  const unsigned gmask = (GL == 32 ? 0xFFFFFFFFu : ((1u << GL) - 1u) << (lane & ~(GL - 1)));
-  const uint32_t groups_per_block = blockDim.x / GL;
-  const uint32_t group = blockIdx.x * groups_per_block + threadIdx.x / GL;
-  const uint32_t ngroups = gridDim.x * groups_per_block;
+  constexpr int D = 32;
+  extern __shared__ float sum_s[];  // [dim]
+  __shared__ float alpha_s;
   const uint32_t nlong = a.ds->num_long;
-  for (uint32_t li = group; li < nlong; li += ngroups) {
+  for (uint32_t li = blockIdx.x; li < nlong; li += gridDim.x) {
     const LongSeg ls = a.long_seg[li];
     const uint32_t slot = a.sorted_slot[a.seg_start[ls.seg]];
-    const float alpha = adam_alpha<OPT>(t, slot, gmask, gl == 0);
-    for (uint32_t q = gl; q < t.cpr; q += GL) {
-      float acc[E];
-      const float* p0 = a.partial + (size_t)ls.base * t.dim + (size_t)q * E;
+    for (uint32_t col = threadIdx.x; col < t.dim; col += blockDim.x) {
+      const float* p = a.partial + (size_t)ls.base * t.dim + col;
+      float acc = __ldcg(p);
+      uint32_t c = 1;
+      for (; c + D <= ls.nleaf; c += D) {  // full batches: all D loads issued before the first add
+        float x[D];
 #pragma unroll
-      for (int e = 0; e < E; e++) acc[e] = p0[e];
-      for (uint32_t c = 1; c < ls.nleaf; c++) {
-        const float4* p = reinterpret_cast<const float4*>(a.partial + (size_t)(ls.base + c) * t.dim + (size_t)q * E);
+        for (int k = 0; k < D; k++) x[k] = __ldcg(p + (size_t)(c + k) * t.dim);
 #pragma unroll
-        for (int k = 0; k < E / 4; k++) {
-          const float4 x = p[k];
-          acc[4 * k] = __fadd_rn(acc[4 * k], x.x);
-          acc[4 * k + 1] = __fadd_rn(acc[4 * k + 1], x.y);
-          acc[4 * k + 2] = __fadd_rn(acc[4 * k + 2], x.z);
-          acc[4 * k + 3] = __fadd_rn(acc[4 * k + 3], x.w);
-        }
+        for (int k = 0; k < D; k++) acc = __fadd_rn(acc, x[k]);
       }
-      optimizer_chunk<BF16, OPT>(t, slot, q, acc, alpha, reduce_row_of<OPT>(a, slot, t.cpr));
+      for (; c < ls.nleaf; c += 8) {
+        float x[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) x[k] = c + k < ls.nleaf ? __ldcg(p + (size_t)(c + k) * t.dim) : 0.0f;
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+          if (c + k < ls.nleaf) acc = __fadd_rn(acc, x[k]);
+      }
+      sum_s[col] = acc;
     }
+    if (threadIdx.x == 0) {
+      alpha_s = 0.0f;
+      if constexpr (OPT == MEEPO_ADAM) {  // per-row step count -> scalar step size (meepo.h "Update")
+        const uint32_t tt = t.steps[slot] + 1;
+        t.steps[slot] = tt;
+        const double bc1 = 1.0 - pow((double)t.beta1, (double)tt);
+        const double bc2 = 1.0 - pow((double)t.beta2, (double)tt);
+        alpha_s = (float)((double)t.lr * sqrt(bc2) / bc1);
+      }
+    }
+    __syncthreads();
+    for (uint32_t q = threadIdx.x; q < t.cpr; q += blockDim.x) {
+      float acc[E];
+#pragma unroll
+      for (int e = 0; e < E; e++) acc[e] = sum_s[q * E + e];
+      optimizer_chunk<BF16, OPT>(t, slot, q, acc, alpha_s, reduce_row_of<OPT>(a, slot, t.cpr));
+    }
+    __syncthreads();
   }
 }
 
@@ -432,7 +495,7 @@ size_t SegWork::bytes(uint64_t n, uint32_t dim, int end_bit_) {
   cub::DeviceRadixSort::SortPairs(nullptr, cub, (const uint32_t*)nullptr, (uint32_t*)nullptr,
                                   (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n, 0, end_bit_);
   const size_t ntiles_ = (n + kSegTile - 1) / kSegTile;
-  const size_t max_long_ = n / (kLeaf + 1) + 1, max_leaves_ = n / 128 + 2;
+  const size_t max_long_ = n / (kLongSeg + 1) + 1, max_leaves_ = n / kLongSeg + 2;
   return 4 * Workspace::pad(n * 4) + Workspace::pad(cub) + 2 * Workspace::pad(ntiles_ * 4) +
          Workspace::pad((n + 2) * 4) + Workspace::pad((n + 2) * 16) + Workspace::pad(max_long_ * sizeof(LongSeg)) +
          Workspace::pad(max_leaves_ * 8) + Workspace::pad(max_leaves_ * dim * 4) + 4096;
@@ -445,8 +508,8 @@ void SegWork::take(Workspace& ws, uint64_t n_, uint32_t dim, int end_bit_) {
   cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
                                   (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n, 0, end_bit);
   ntiles = (n + kSegTile - 1) / kSegTile;
-  max_long = n_ / (kLeaf + 1) + 1;
-  max_leaves = n_ / 128 + 2;
+  max_long = n_ / (kLongSeg + 1) + 1;
+  max_leaves = n_ / kLongSeg + 2;
   sk_in = ws.take<uint32_t>(n_);
   sk_out = ws.take<uint32_t>(n_);
   sv_in = ws.take<uint32_t>(n_);
@@ -524,10 +587,19 @@ meepo_status run_segmented(meepo_table* t, SegWork& w, uint32_t limit, const voi
   }
   {
     ProfScope ps(t, names[3], stream);
-    const int grid = grid_for(t, k_leaf, 256, 0, (w.max_leaves + groups_per_block - 1) / groups_per_block);
-    MEEPO_CUDA_TRY(cudaLaunchKernel(k_leaf, dim3(grid), dim3(256), args, 0, stream));
-    const int grid2 = grid_for(t, k_finish, 256, 0, (w.max_long + groups_per_block - 1) / groups_per_block);
-    MEEPO_CUDA_TRY(cudaLaunchKernel(k_finish, dim3(grid2), dim3(256), args, 0, stream));
+    const uint32_t words = t->v.cpr * 4;
+    uint32_t tpl = std::min<uint32_t>(256, (words + 31) / 32 * 32);  // whole warps per leaf
+    while (256 % tpl) tpl += 32;
+    const uint64_t lpc = 256 / tpl;
+    const int grid = grid_for(t, k_leaf, 256, 0, (w.max_leaves + lpc - 1) / lpc);
+    void* largs[] = {&t->v, &a, &tpl};
+    MEEPO_CUDA_TRY(cudaLaunchKernel(k_leaf, dim3(grid), dim3(256), largs, 0, stream));
+  }
+  {
+    ProfScope ps(t, names[4], stream);
+    const size_t smem = (size_t)t->v.dim * 4;
+    const int grid2 = grid_for(t, k_finish, 256, smem, w.max_long);
+    MEEPO_CUDA_TRY(cudaLaunchKernel(k_finish, dim3(grid2), dim3(256), args, smem, stream));
   }
   return MEEPO_OK;
 }
@@ -546,8 +618,8 @@ meepo_status launch_apply_gradients(meepo_table* t, const uint64_t* keys, const 
     grad_slots_kernel<<<grid, 256, 0, stream>>>(t->v, keys, (uint32_t)n, w.sk_in, w.sv_in, t->cache, cache_n);
     MEEPO_CUDA_TRY(cudaGetLastError());
   }
-  static const char* const names[4] = {"apply.radix_sort(cub)", "apply.segments(3 kernels)",
-                                       "apply.reduce_optimizer", "apply.long_segments(2 kernels)"};
+  static const char* const names[5] = {"apply.radix_sort(cub)", "apply.segments(3 kernels)",
+                                       "apply.reduce_optimizer", "apply.long_leaves", "apply.long_finish"};
   return run_segmented(t, w, t->v.slots, grads, t->v.opt, nullptr, stream, grads_ready, names);
 }
 
