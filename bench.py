@@ -37,6 +37,11 @@ WORKLOADS = {
                  step="find_or_insert+lookup", seed=keygen.SEEDS["cfg2"]),
     "cfg4": dict(dim=128, dtype="bf16", table_keys=125_000_000, capacity=160_000_000, batch=1 << 20, dist="zipf",
                  step="find_or_insert+apply_gradients(adagrad)", seed=keygen.SEEDS["cfg4"]),
+    # capacity pressure (BASELINE.json configs[4]): table held at ~90% load, key universe 4x the capacity, LFU
+    # eviction to the pinned host spill tier every `evict_every` steps, inside the timed region
+    "cfg5": dict(dim=128, dtype="bf16", table_keys=int(0.9 * (1 << 26)), capacity=1 << 26, batch=1 << 20, dist="zipf",
+                 step="find_or_insert+apply_gradients(adagrad)+evict(lfu)", seed=keygen.SEEDS["cfg5"],
+                 universe=4 << 26, track_scores=True, host_spill_bytes=16 << 30, evict_every=8, evict_target=0.895),
 }
 METRIC = "find_or_insert+update keys/s at dim=128"
 UNIT = "keys/s"
@@ -76,7 +81,7 @@ def algorithmic_bytes(w, B, U):
 
 def gen_batches(w, nb, dist, rank, world):
     """Host key batches (uint64) for one rank; identical streams for the GPU arm and the oracle arm."""
-    universe = w["table_keys"] * world  # global key set; each rank owns ~1/world of it by owner()
+    universe = w.get("universe", w["table_keys"] * world)  # global key set; each rank owns ~1/world of it
     rng = np.random.default_rng([w["seed"], rank, 1])
     return [keygen.batch_keys(rng, w["batch"], universe, w["seed"], dist=dist) for _ in range(nb)]
 
@@ -230,6 +235,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--set", action="append", default=[], metavar="KEY=VALUE",
+                    help="override a workload field (experiments), e.g. --set track_scores=False")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N>1: fused peer-memory verbs (csrc/peer.cu) or the NCCL all-to-all composition")
     args = ap.parse_args()
@@ -241,6 +248,9 @@ def main():
         w["capacity"] = int(args.table_keys / 0.745)
     if args.batch:
         w["batch"] = args.batch
+    for kv in args.set:
+        k, v = kv.split("=", 1)
+        w[k] = type(w[k])(eval(v)) if k in w and w[k] is not None else eval(v)
     dist = args.dist or w["dist"]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -290,7 +300,9 @@ def main():
     B = w["batch"]
     tdt = torch.float32 if w["dtype"] == "f32" else torch.bfloat16
     table = Table(dim=w["dim"], capacity=w["capacity"], dtype=w["dtype"], optimizer="adagrad", lr=0.01,
-                  init_seed=1, init_scale=0.01, device=local_rank)
+                  init_seed=1, init_scale=0.01, device=local_rank, track_scores=w.get("track_scores", False),
+                  host_spill_bytes=w.get("host_spill_bytes", 0))
+    evict_log = []
     stream = torch.cuda.current_stream()
     sp = stream.cuda_stream
     if world > 1:
@@ -340,6 +352,10 @@ def main():
                 table.lookup(dkeys[i], rows_out, status, stream=sp)
             else:
                 table.apply_gradients(dkeys[i], grads, stream=sp)
+            if w.get("evict_every") and (i + 1) % w["evict_every"] == 0:
+                t_e = time.perf_counter()
+                n_ev = table.evict("lfu", w["evict_target"], stream=sp)  # synchronous: selection + spill copy
+                evict_log.append((i, n_ev, (time.perf_counter() - t_e) * 1e3))
 
     def barrier():
         torch.cuda.synchronize()
@@ -461,6 +477,11 @@ def main():
                 "vs_baseline": None, "dtype": w["dtype"], "data": "synthetic", "config": config,
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": own_launches,
                 "clocks": clk, "kernels": kernels,
+                "evict": ({"calls_in_timed_region": len([e for e in evict_log if e[0] >= args.warmup]),
+                           "keys_evicted": [e[1] for e in evict_log if e[0] >= args.warmup],
+                           "ms_per_call_host_wall": [round(e[2], 3) for e in evict_log if e[0] >= args.warmup],
+                           "spill_keys": st1["spill_keys"], "spill_bytes": st1["spill_bytes"],
+                           "evictions_total": st1["evictions"]} if w.get("evict_every") else None),
                 "table": {"size": st1["size"], "capacity": st1["capacity"], "load": st1["size"] / st1["capacity"],
                           "overflow_buckets": st1["overflow_buckets"], "prefill_s": prefill_s,
                           "unique_per_batch": U_avg, "inserted_during_bench": st1["size"] - size0}}

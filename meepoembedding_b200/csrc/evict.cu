@@ -9,6 +9,7 @@
 // keeps the key -> slab index. Runs between batches, never concurrently with the probe kernels.
 #include <cub/device/device_radix_sort.cuh>
 
+#include <chrono>
 #include <cmath>
 #include <cstring>
 
@@ -21,25 +22,36 @@ __device__ __forceinline__ uint32_t score_of(const TableView& t, uint32_t s, int
   return policy == MEEPO_LFU ? sc.x : sc.y;
 }
 
-// histogram of byte `shift/8` of the score over live slots whose higher bytes equal `prefix`
+// Radix select over the composite (score, key), most significant byte first. Score passes
+// (key_pass == 0): histogram of byte `shift/8` of the score over live slots whose higher score bytes
+// equal `prefix`. Key passes: among the slots whose score IS the threshold `prefix`, histogram of
+// byte `shift/8` of the key over those whose higher key bytes equal `kprefix` — the tie-break
+// (smaller key first) is selected exactly instead of sorting tens of millions of tied candidates.
 __global__ void __launch_bounds__(256) score_hist_kernel(TableView t, int policy, uint32_t prefix, uint32_t mask,
-                                                         int shift, unsigned long long* __restrict__ hist) {
+                                                         int shift, int key_pass, uint64_t kprefix, uint64_t kmask,
+                                                         unsigned long long* __restrict__ hist) {
   __shared__ uint32_t sh[256];
   sh[threadIdx.x] = 0;
   __syncthreads();
   for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < t.slots; s += gridDim.x * blockDim.x) {
-    if (*key_ptr(t, s) == MEEPO_KEY_EMPTY) continue;
+    const uint64_t key = *key_ptr(t, s);
+    if (key == MEEPO_KEY_EMPTY) continue;
     const uint32_t sc = score_of(t, s, policy);
-    if ((sc & mask) == prefix) atomicAdd(&sh[(sc >> shift) & 0xFFu], 1u);
+    if ((sc & mask) != prefix) continue;
+    if (!key_pass)
+      atomicAdd(&sh[(sc >> shift) & 0xFFu], 1u);
+    else if ((key & kmask) == kprefix)
+      atomicAdd(&sh[(uint32_t)(key >> shift) & 0xFFu], 1u);
   }
   __syncthreads();
   if (sh[threadIdx.x]) atomicAdd(hist + threadIdx.x, (unsigned long long)sh[threadIdx.x]);
 }
 
-// candidates = live slots with score <= threshold (order arbitrary; sorted afterwards)
+// candidates = live slots with (score, key) <= (threshold, key_threshold) — exactly the victims
+// (order arbitrary; sorted afterwards)
 __global__ void __launch_bounds__(256) candidates_kernel(TableView t, int policy, uint32_t threshold,
-                                                         uint64_t* __restrict__ ckey, uint32_t* __restrict__ cslot,
-                                                         uint32_t* __restrict__ count) {
+                                                         uint64_t key_threshold, uint64_t* __restrict__ ckey,
+                                                         uint32_t* __restrict__ cslot, uint32_t* __restrict__ count) {
   const uint32_t lane = threadIdx.x & 31;
   for (uint32_t s0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; s0 < t.slots; s0 += gridDim.x * blockDim.x) {
     const uint32_t s = s0 + lane;
@@ -47,7 +59,10 @@ __global__ void __launch_bounds__(256) candidates_kernel(TableView t, int policy
     bool take = false;
     if (s < t.slots) {
       key = *key_ptr(t, s);
-      take = key != MEEPO_KEY_EMPTY && score_of(t, s, policy) <= threshold;
+      if (key != MEEPO_KEY_EMPTY) {
+        const uint32_t sc = score_of(t, s, policy);
+        take = sc < threshold || (sc == threshold && key <= key_threshold);
+      }
     }
     const unsigned m = __ballot_sync(0xFFFFFFFFu, take);
     if (!m) continue;
@@ -165,26 +180,26 @@ static SpillView spill_view(const meepo_table* t) {
 
 // host bookkeeping of the spill tier; mirrors the FIFO + newest-copy-wins rule of meepo.h "Evict"
 static void spill_drop(meepo_table* t, uint64_t key) {
-  auto it = t->spill_index.find(key);
-  if (it == t->spill_index.end()) return;
-  t->spill_free.push_back((uint32_t)it->second.ring_index);
-  t->spill_index.erase(it);
+  SpillTuple* it = t->spill_index.find(key);
+  if (!it) return;
+  t->spill_free.push_back((uint32_t)it->ring_index);
+  t->spill_index.erase(key);
 }
 static uint32_t spill_push(meepo_table* t, uint64_t key) {
   spill_drop(t, key);
   while (t->spill_index.size() >= t->spill_cap_tuples) {
     auto f = t->spill_fifo.front();
     t->spill_fifo.pop_front();
-    auto it = t->spill_index.find(f.second);
-    if (it != t->spill_index.end() && it->second.seq == f.first) {
-      t->spill_free.push_back((uint32_t)it->second.ring_index);
-      t->spill_index.erase(it);
+    SpillTuple* it = t->spill_index.find(f.second);
+    if (it && it->seq == f.first) {
+      t->spill_free.push_back((uint32_t)it->ring_index);
+      t->spill_index.erase(f.second);
     }
   }
   const uint32_t slab = t->spill_free.back();
   t->spill_free.pop_back();
   const uint64_t seq = t->spill_seq++;
-  t->spill_index[key] = SpillTuple{seq, slab};
+  t->spill_index.put(key, SpillTuple{seq, slab});
   t->spill_fifo.emplace_back(seq, key);
   return slab;
 }
@@ -222,8 +237,9 @@ MEEPO_API meepo_status meepo_evict(meepo_table* t, int32_t policy, double target
   uint64_t remaining = k, ties = 0;
   const int sgrid = grid1d(t, t->v.slots);
   for (int shift = 24; shift >= 0; shift -= 8) {
+    ProfScope ps(t, "evict.select(radix pass)", stream);
     MEEPO_CUDA_TRY(cudaMemsetAsync(d_hist, 0, sizeof h_hist, stream));
-    score_hist_kernel<<<sgrid, 256, 0, stream>>>(t->v, policy, prefix, mask, shift, d_hist);
+    score_hist_kernel<<<sgrid, 256, 0, stream>>>(t->v, policy, prefix, mask, shift, 0, 0ull, 0ull, d_hist);
     MEEPO_CUDA_TRY(cudaMemcpyAsync(h_hist, d_hist, sizeof h_hist, cudaMemcpyDeviceToHost, stream));
     MEEPO_CUDA_TRY(cudaStreamSynchronize(stream));
     uint64_t cum = 0;
@@ -239,7 +255,30 @@ MEEPO_API meepo_status meepo_evict(meepo_table* t, int32_t policy, double target
     mask |= 0xFFu << shift;
   }
   const uint32_t T = prefix;
-  const uint64_t ncand = (k - remaining) + ties;  // scores < T, plus every tie
+  // `remaining` of the `ties` slots with score == T go too: the ones with the smallest keys
+  uint64_t Tkey = MEEPO_KEY_EMPTY;
+  if (remaining < ties) {
+    uint64_t kprefix = 0, kmask = 0;
+    for (int shift = 56; shift >= 0; shift -= 8) {
+      ProfScope ps(t, "evict.select(radix pass)", stream);
+      MEEPO_CUDA_TRY(cudaMemsetAsync(d_hist, 0, sizeof h_hist, stream));
+      score_hist_kernel<<<sgrid, 256, 0, stream>>>(t->v, policy, T, 0xFFFFFFFFu, shift, 1, kprefix, kmask, d_hist);
+      MEEPO_CUDA_TRY(cudaMemcpyAsync(h_hist, d_hist, sizeof h_hist, cudaMemcpyDeviceToHost, stream));
+      MEEPO_CUDA_TRY(cudaStreamSynchronize(stream));
+      uint64_t cum = 0;
+      int b = 0;
+      for (; b < 256; b++) {
+        if (cum + h_hist[b] >= remaining) break;
+        cum += h_hist[b];
+      }
+      if (b == 256) return fail(MEEPO_ECUDA, "evict: inconsistent key histogram");
+      remaining -= cum;
+      kprefix |= (uint64_t)b << shift;
+      kmask |= 0xFFull << shift;
+    }
+    Tkey = kprefix;
+  }
+  const uint64_t ncand = k;  // exactly the victims
 
   // --- candidates ordered by (score, key): sort by key, then stable sort by score
   size_t cub1 = 0, cub2 = 0;
@@ -263,8 +302,10 @@ MEEPO_API meepo_status meepo_evict(meepo_table* t, int32_t policy, double target
   uint32_t* vslot = t->ws.take<uint32_t>(k);
   uint32_t* vslab = t->ws.take<uint32_t>(k);
   uint32_t* d_count = &t->dstate->evict_count;
+  {
+  ProfScope ps(t, "evict.order_candidates(4 kernels + 2 cub sorts)", stream);
   MEEPO_CUDA_TRY(cudaMemsetAsync(d_count, 0, 4, stream));
-  candidates_kernel<<<sgrid, 256, 0, stream>>>(t->v, policy, T, ckey, cslot, d_count);
+  candidates_kernel<<<sgrid, 256, 0, stream>>>(t->v, policy, T, Tkey, ckey, cslot, d_count);
   const int cgrid = grid1d(t, ncand);
   iota_kernel<<<cgrid, 256, 0, stream>>>(ord_a, (uint32_t)ncand);
   MEEPO_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, cub1, (const uint64_t*)ckey, ckey_sorted, (const uint32_t*)ord_a,
@@ -274,6 +315,7 @@ MEEPO_API meepo_status meepo_evict(meepo_table* t, int32_t policy, double target
                                                  (int)ncand, 0, 32, stream));
   victims_kernel<<<grid1d(t, k), 256, 0, stream>>>(ord_c, cslot, ckey, (uint32_t)k, vslot, vkey);
   MEEPO_CUDA_TRY(cudaGetLastError());
+  }
 
   // --- spill the last min(k, cap) victims (earlier ones would be pushed out by the FIFO anyway)
   if (t->spill_cap_tuples) {
@@ -283,18 +325,31 @@ MEEPO_API meepo_status meepo_evict(meepo_table* t, int32_t policy, double target
     MEEPO_CUDA_TRY(cudaMemcpyAsync(hk.data(), vkey + (k - m), m * 8, cudaMemcpyDeviceToHost, stream));
     MEEPO_CUDA_TRY(cudaStreamSynchronize(stream));
     if (k > m) {  // everything older is pushed out by m == cap fresh tuples
-      std::vector<uint64_t> old;
-      for (auto& kv : t->spill_index) old.push_back(kv.first);
-      for (uint64_t key : old) spill_drop(t, key);
+      t->spill_index.clear();
       t->spill_fifo.clear();
+      t->spill_free.clear();
+      for (uint64_t i = t->spill_cap_tuples; i-- > 0;) t->spill_free.push_back((uint32_t)i);
     }
-    for (uint64_t j = 0; j < m; j++) hs[j] = spill_push(t, hk[j]);
+    const auto h0 = std::chrono::steady_clock::now();
+    t->spill_index.reserve(std::min<uint64_t>(t->spill_index.size() + m, t->spill_cap_tuples));
+    for (uint64_t j = 0; j < m; j++) {  // the index is far larger than the host caches: fetch ahead
+      if (j + 16 < m) t->spill_index.prefetch(hk[j + 16]);
+      hs[j] = spill_push(t, hk[j]);
+    }
+    prof_add_host(t, "evict.host_index(wall)",
+                  std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count());
     MEEPO_CUDA_TRY(cudaMemcpyAsync(vslab, hs.data(), m * 4, cudaMemcpyHostToDevice, stream));
     const int wgrid = (int)std::max<uint64_t>(1, std::min<uint64_t>((m + 7) / 8, (uint64_t)t->num_sms * 4));
-    spill_copy_kernel<<<wgrid, 256, 0, stream>>>(t->v, spill_view(t), vslot + (k - m), vslab, (uint32_t)m);
+    {
+      ProfScope ps(t, "evict.spill_copy(pcie)", stream);
+      spill_copy_kernel<<<wgrid, 256, 0, stream>>>(t->v, spill_view(t), vslot + (k - m), vslab, (uint32_t)m);
+    }
     MEEPO_CUDA_TRY(cudaStreamSynchronize(stream));  // hs must outlive the copy
   }
-  release_kernel<<<grid1d(t, k), 256, 0, stream>>>(t->v, vslot, (uint32_t)k);
+  {
+    ProfScope ps(t, "evict.release", stream);
+    release_kernel<<<grid1d(t, k), 256, 0, stream>>>(t->v, vslot, (uint32_t)k);
+  }
   MEEPO_CUDA_TRY(cudaGetLastError());
   MEEPO_CUDA_TRY(cudaStreamSynchronize(stream));
   if (n_evicted) *n_evicted = k;
@@ -332,15 +387,15 @@ MEEPO_API meepo_status meepo_spill_readmit(meepo_table* t, const uint64_t* keys,
       st = MEEPO_KEY_FOUND;
       if (!admitted.count(k)) spill_drop(t, k);
     } else {
-      auto it = t->spill_index.find(k);
-      if (it == t->spill_index.end())
+      SpillTuple* it = t->spill_index.find(k);
+      if (!it)
         st = MEEPO_KEY_MISS;
       else if (size + ins_keys.size() >= t->v.slots)
         st = MEEPO_KEY_FULL;
       else {
         ins_keys.push_back(k);
-        ins_slab.push_back((uint32_t)it->second.ring_index);
-        t->spill_index.erase(it);  // the slab is recycled after the copy below
+        ins_slab.push_back((uint32_t)it->ring_index);
+        t->spill_index.erase(k);  // the slab is recycled after the copy below
         admitted[k] = 1;
         st = MEEPO_KEY_INSERTED;
       }
@@ -352,11 +407,9 @@ MEEPO_API meepo_status meepo_spill_readmit(meepo_table* t, const uint64_t* keys,
     t->cache_valid = false;
     MEEPO_CUDA_TRY(cudaMemcpyAsync(d_keys, ins_keys.data(), m * 8, cudaMemcpyHostToDevice, stream));
     MEEPO_CUDA_TRY(cudaMemcpyAsync(d_slab, ins_slab.data(), m * 4, cudaMemcpyHostToDevice, stream));
-    NewList nl{d_new, &t->dstate->new_count[t->foi_parity]};
-    uint32_t* next = &t->dstate->new_count[t->foi_parity ^ 1];
-    t->foi_parity ^= 1;
+    NewList nl{d_new};
     MEEPO_TRY(import_probe_launch(t, d_keys, m, d_slot, nullptr, nl, stream));
-    MEEPO_TRY(publish_slots(t, nl.slots, nl.count, next, m, stream));
+    MEEPO_TRY(publish_slots(t, nl.slots, m, stream));
     const int wgrid = (int)std::max<uint64_t>(1, std::min<uint64_t>((m + 7) / 8, (uint64_t)t->num_sms * 4));
     readmit_copy_kernel<<<wgrid, 256, 0, stream>>>(t->v, spill_view(t), d_slot, d_slab, (uint32_t)m);
     MEEPO_CUDA_TRY(cudaGetLastError());

@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(256) import_probe_kernel(TableView t, const ui
     const Probe pr = probe_find_or_insert(t, keys[i]);
     slot_out[i] = pr.slot;
     if (status_out) status_out[i] = (uint8_t)pr.status;
-    if (pr.winner) nl.slots[atomicAdd(nl.count, 1u)] = pr.slot;
+    nl.slots[i] = pr.winner ? pr.slot : kNil;
     if (pr.status == MEEPO_KEY_FULL) atomicAdd(t.counters + C_FULL, 1ull);
   }
 }
@@ -224,12 +224,10 @@ meepo_status import_device(meepo_table* t, const uint64_t* keys, const void* row
                            cudaStream_t stream, uint32_t* slot_buf, uint32_t* new_slots) {
   if (n == 0) return MEEPO_OK;
   t->cache_valid = false;
-  NewList nl{new_slots, &t->dstate->new_count[t->foi_parity]};
-  uint32_t* next = &t->dstate->new_count[t->foi_parity ^ 1];
-  t->foi_parity ^= 1;
+  NewList nl{new_slots};
   const int grid = (int)std::min<uint64_t>((n + 255) / 256, (uint64_t)t->num_sms * 8);
   MEEPO_TRY(import_probe_launch(t, keys, n, slot_buf, status_out, nl, stream));
-  MEEPO_TRY(publish_slots(t, nl.slots, nl.count, next, n, stream));
+  MEEPO_TRY(publish_slots(t, nl.slots, n, stream));
   arena_scatter_kernel<<<warp_grid(t, n), 256, 0, stream>>>(t->v.rows, slot_buf, (uint32_t)n, t->v.cpr,
                                                             reinterpret_cast<const uint4*>(rows),
                                                             make_uint4(0, 0, 0, 0), 0);

@@ -5,7 +5,7 @@
 namespace meepo {
 
 template <int CPR, bool INSERT>
-__global__ void __launch_bounds__(256) probe_gather_kernel(TableView t, const uint64_t* __restrict__ keys,
+__global__ void __launch_bounds__(256, 4) probe_gather_kernel(TableView t, const uint64_t* __restrict__ keys,
                                                            uint32_t n, uint4* __restrict__ out,
                                                            uint8_t* __restrict__ status, NewList nl, SlotCache sc) {
   const uint32_t lane = threadIdx.x & 31u;
@@ -14,33 +14,36 @@ __global__ void __launch_bounds__(256) probe_gather_kernel(TableView t, const ui
   const uint32_t ntiles = (n + 31u) >> 5;
   const uint32_t cpr = CPR > 0 ? (uint32_t)CPR : t.cpr;
   TileCounts cnt;
+  __shared__ uint32_t sc_slot[kScoreCells], sc_freq[kScoreCells];
+  const ScoreCache scache{sc_slot, sc_freq};
+  score_cache_init(t, scache);
   for (uint32_t tile = warp; tile < ntiles; tile += nwarps) {
     const uint32_t i = tile * 32u + lane;
     const uint32_t tile_keys = min(32u, n - tile * 32u);
     const uint64_t key = i < n ? __ldg(keys + i) : MEEPO_KEY_EMPTY;
     probe_gather_tile<CPR, INSERT>(t, key, i < n, tile_keys, out + (size_t)tile * 32u * cpr,
                                    status ? status + i : nullptr, sc.slots ? sc.slots + i : nullptr,
-                                   sc.keys ? sc.keys + i : nullptr, 1u, nl, cnt, lane);
+                                   sc.keys ? sc.keys + i : nullptr, 1u, nl.slots ? nl.slots + i : nullptr, cnt,
+                                   scache, lane);
   }
+  score_cache_flush(t, scache);
   flush_tile_counts(t, cnt, lane);
 }
 
-// Writes the tags of the slots claimed by the preceding probe_gather_kernel<.., true> and folds the
-// count into the table size. `cur` is this call's counter, `next` the other one (zeroed here so the
-// next find_or_insert starts from 0 without a memset node).
-__global__ void publish_kernel(TableView t, const uint32_t* __restrict__ new_slots, const uint32_t* cur,
-                               uint32_t* next) {
-  const uint32_t n = *cur;
+// Writes the tags of the slots claimed by the preceding probe_gather_kernel<.., true> (new_slots[i]
+// != kNil) and folds their number into the table size.
+__global__ void __launch_bounds__(256) publish_kernel(TableView t, const uint32_t* __restrict__ new_slots, uint32_t n) {
+  uint32_t mine = 0;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const uint32_t s = new_slots[i];
+    const uint32_t s = __ldg(new_slots + i);
+    if (s == kNil) continue;
     *tag_ptr(t, s) = (uint8_t)digest_of(mix64(*key_ptr(t, s)));
+    mine++;
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    *next = 0;
-    if (n) {
-      atomicAdd(t.counters + C_SIZE, (unsigned long long)n);
-      atomicAdd(t.counters + C_INSERTS, (unsigned long long)n);
-    }
+  mine = __reduce_add_sync(0xFFFFFFFFu, mine);
+  if ((threadIdx.x & 31u) == 0 && mine) {
+    atomicAdd(t.counters + C_SIZE, (unsigned long long)mine);
+    atomicAdd(t.counters + C_INSERTS, (unsigned long long)mine);
   }
 }
 
@@ -65,8 +68,7 @@ meepo_status probe_gather_begin(meepo_table* t, uint64_t n_total, bool insert, c
   t->epoch++;
   t->v.epoch = (uint32_t)t->epoch;
   t->cur_new.slots = nullptr;
-  t->cur_new.count = nullptr;
-  t->cur_new_next = nullptr;
+  t->cur_new_off = 0;
   t->cache_valid = false;
   t->cache_off = 0;
   t->cache_n = 0;
@@ -87,9 +89,6 @@ meepo_status probe_gather_begin(meepo_table* t, uint64_t n_total, bool insert, c
   if (insert && n_total) {
     MEEPO_TRY(t->ws.reserve(Workspace::pad(n_total * 4), stream));
     t->cur_new.slots = t->ws.take<uint32_t>(n_total);
-    t->cur_new.count = &t->dstate->new_count[t->foi_parity];
-    t->cur_new_next = &t->dstate->new_count[t->foi_parity ^ 1];
-    t->foi_parity ^= 1;
   }
   return MEEPO_OK;
 }
@@ -102,7 +101,8 @@ meepo_status probe_gather_chunk(meepo_table* t, const uint64_t* keys, uint64_t n
   const int grid = grid_for(t, kern, 256, 0, (tiles + 7) / 8);
   uint32_t n32 = (uint32_t)n;
   uint4* out = reinterpret_cast<uint4*>(rows_out);
-  NewList nl{t->cur_new.slots, t->cur_new.count};
+  NewList nl{insert ? t->cur_new.slots + t->cur_new_off : nullptr};  // chunks fill consecutive ranges
+  t->cur_new_off += n;
   SlotCache sc{nullptr, nullptr};
   if (t->cache_n) {  // chunks of one call fill consecutive ranges
     sc.keys = t->cache.keys + t->cache_off;
@@ -116,10 +116,10 @@ meepo_status probe_gather_chunk(meepo_table* t, const uint64_t* keys, uint64_t n
   return MEEPO_OK;
 }
 
-meepo_status publish_slots(meepo_table* t, const uint32_t* slots, const uint32_t* cur, uint32_t* next,
-                           uint64_t n_max, cudaStream_t stream) {
-  const int pgrid = (int)std::max<uint64_t>(1, std::min<uint64_t>((n_max + 255) / 256, (uint64_t)t->num_sms * 8));
-  publish_kernel<<<pgrid, 256, 0, stream>>>(t->v, slots, cur, next);
+meepo_status publish_slots(meepo_table* t, const uint32_t* slots, uint64_t n, cudaStream_t stream) {
+  if (n == 0) return MEEPO_OK;
+  const int pgrid = (int)std::max<uint64_t>(1, std::min<uint64_t>((n + 255) / 256, (uint64_t)t->num_sms * 8));
+  publish_kernel<<<pgrid, 256, 0, stream>>>(t->v, slots, (uint32_t)n);
   MEEPO_CUDA_TRY(cudaGetLastError());
   return MEEPO_OK;
 }
@@ -127,7 +127,7 @@ meepo_status publish_slots(meepo_table* t, const uint32_t* slots, const uint32_t
 meepo_status probe_gather_end(meepo_table* t, uint64_t n_total, bool insert, cudaStream_t stream) {
   if (!insert || !n_total) return MEEPO_OK;
   ProfScope ps(t, "find_or_insert.publish", stream);
-  return publish_slots(t, t->cur_new.slots, t->cur_new.count, t->cur_new_next, n_total, stream);
+  return publish_slots(t, t->cur_new.slots, n_total, stream);
 }
 
 meepo_status launch_probe_gather(meepo_table* t, const uint64_t* keys, uint64_t n, void* rows_out,

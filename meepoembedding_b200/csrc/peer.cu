@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(256) assign_grad_rows_kernel(const __grid_cons
 // tile go to one contiguous block of that requester's ret_rows and the tile body is exactly the
 // single-table one with a peer pointer as its output.
 template <int CPR, bool INSERT>
-__global__ void __launch_bounds__(256) owner_probe_gather_kernel(TableView t, const __grid_constant__ PeerSet ps,
+__global__ void __launch_bounds__(256, 4) owner_probe_gather_kernel(TableView t, const __grid_constant__ PeerSet ps,
                                                                  const PeerWork* __restrict__ work, NewList nl) {
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -263,6 +263,9 @@ __global__ void __launch_bounds__(256) owner_probe_gather_kernel(TableView t, co
   const PeerWindow& me = ps.w[ps.rank];
   const uint32_t max_tiles = (work->max_cnt + 31u) >> 5;
   TileCounts cnt;
+  __shared__ uint32_t sc_slot[kScoreCells], sc_freq[kScoreCells];
+  const ScoreCache scache{sc_slot, sc_freq};
+  score_cache_init(t, scache);
   // Row k of every source's tile list, sources rotated by (rank, k): at any moment the owners are
   // spread over all requesters (no incast on one NVLink port) and local tiles overlap remote ones.
   for (uint32_t k = warp; k < max_tiles; k += nwarps) {
@@ -278,10 +281,11 @@ __global__ void __launch_bounds__(256) owner_probe_gather_kernel(TableView t, co
       const uint32_t occ = valid ? ld_window(me.recv_occ + e) : 0u;
       const size_t r = (size_t)ps.rank * ps.region + p0;    // in the requester's window: [owner][position]
       probe_gather_tile<CPR, INSERT>(t, key, valid, tile_keys, ps.w[s].ret_rows + r * cpr,
-                                     valid ? ps.w[s].ret_status + r + lane : nullptr, nullptr, nullptr, occ, nl, cnt,
-                                     lane);
+                                     valid ? ps.w[s].ret_status + r + lane : nullptr, nullptr, nullptr, occ,
+                                     nl.slots + e, cnt, scache, lane);
     }
   }
+  score_cache_flush(t, scache);
   flush_tile_counts(t, cnt, lane);
 }
 
@@ -440,9 +444,9 @@ static meepo_status sharded_forward(meepo_table* t, const uint64_t* keys, uint64
   uint32_t* inverse = t->ws.take<uint32_t>(std::max<uint64_t>(n, 1));
   uint32_t* uocc = t->ws.take<uint32_t>(std::max<uint64_t>(n, 1));  // hit/miss stats and LFU scores count occurrences
   uint64_t* n_unique = t->ws.take<uint64_t>(1);
-  NewList nl{t->ws.take<uint32_t>((size_t)p->world * p->region), &t->dstate->new_count[t->foi_parity]};
-  uint32_t* nl_next = &t->dstate->new_count[t->foi_parity ^ 1];
-  if (insert) t->foi_parity ^= 1;
+  const uint64_t n_window = (uint64_t)p->world * p->region;
+  NewList nl{t->ws.take<uint32_t>(n_window)};  // one cell per window entry
+  if (insert) MEEPO_CUDA_TRY(cudaMemsetAsync(nl.slots, 0xFF, n_window * 4, stream));
   MEEPO_TRY(dedup_run(t, keys, nullptr, n, DedupOut{ukeys, nullptr, inverse, n_unique, uocc}, stream));
   {
     ProfScope ps(t, "sharded.push_keys", stream);
@@ -464,7 +468,7 @@ static meepo_status sharded_forward(meepo_table* t, const uint64_t* keys, uint64
   }
   if (insert) {
     ProfScope ps(t, "find_or_insert.publish", stream);
-    MEEPO_TRY(publish_slots(t, nl.slots, nl.count, nl_next, (uint64_t)p->world * p->region, stream));
+    MEEPO_TRY(publish_slots(t, nl.slots, n_window, stream));
   }
   MEEPO_TRY(barrier(t, nullptr, false, stream));
   if (n) {

@@ -43,7 +43,34 @@ __device__ __forceinline__ void gather_tile_fast(const TableView& t, uint32_t sl
   }
 }
 
-// Generic-width version (any cpr), also the path for tiles that contain freshly inserted keys.
+// Freshly inserted keys of a tile, after the fast gather has moved every other row (their slots are
+// masked out there): one key at a time, the lanes cover its chunks. A chunk of a new row is computed
+// (init_chunk is a pure function of key and column), never loaded; the CAS winner also writes it —
+// and the initial optimizer state — to the arenas.
+template <int CPR>
+__device__ __forceinline__ void fixup_fresh(const TableView& t, uint64_t key, const Probe& pr, uint32_t tile_keys,
+                                            uint4* __restrict__ out_tile, uint32_t lane) {
+  unsigned m = __ballot_sync(0xFFFFFFFFu, pr.status == MEEPO_KEY_INSERTED);
+  while (m) {
+    const int j = __ffs(m) - 1;
+    m &= m - 1;
+    const uint32_t s = __shfl_sync(0xFFFFFFFFu, pr.slot, j);
+    const bool win = __shfl_sync(0xFFFFFFFFu, (int)pr.winner, j);
+    const uint64_t kj = __shfl_sync(0xFFFFFFFFu, key, j);
+    if ((uint32_t)j >= tile_keys) continue;
+    for (uint32_t off = lane; off < (uint32_t)CPR; off += 32) {
+      const uint4 v = init_chunk(t, kj, off);
+      if (win) t.rows[(size_t)s * CPR + off] = v;
+      st_stream(out_tile + (size_t)j * CPR + off, v);
+    }
+    if (win) {
+      const uint4 sv = init_state_chunk(t);
+      for (uint32_t off = lane; off < t.scpr; off += 32) t.state[(size_t)s * t.scpr + off] = sv;
+    }
+  }
+}
+
+// Generic-width version (any cpr): the fallback for row widths without a specialised kernel.
 __device__ __forceinline__ void gather_tile_slow(const TableView& t, uint64_t key, const Probe& pr,
                                                  uint32_t tile_keys, uint4* __restrict__ out_tile,
                                                  uint32_t lane) {
@@ -74,16 +101,58 @@ struct TileCounts {
   uint32_t hit = 0, miss = 0, full = 0;
 };
 
+// LFU / LRU score updates (meepo.h "Evict": freq += occurrences, last_epoch = epoch) go through a
+// small per-CTA table in shared memory and reach the score array once per CTA and slot: the hottest
+// Zipf key is ~8% of a batch, and reductions on ONE global address serialise in L2 (measured: +0.2 ms
+// on a 1M-key batch without this). A slot whose cell is taken by another slot updates global memory
+// directly. The kernel calls score_cache_init before and score_cache_flush after its tile loop.
+constexpr uint32_t kScoreCells = 512;
+struct ScoreCache {
+  uint32_t* slot;  // [kScoreCells], kNil = free
+  uint32_t* freq;  // [kScoreCells]
+};
+__device__ __forceinline__ void score_cache_init(const TableView& t, const ScoreCache& sc) {
+  if (!t.scores) return;
+  for (uint32_t i = threadIdx.x; i < kScoreCells; i += blockDim.x) {
+    sc.slot[i] = kNil;
+    sc.freq[i] = 0;
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ void score_cache_add(const TableView& t, const ScoreCache& sc, uint32_t s, uint32_t n) {
+  const uint32_t h = (s * 0x9E3779B1u) >> (32 - 9);
+  const uint32_t old = atomicCAS(&sc.slot[h], kNil, s);
+  if (old == kNil || old == s) {
+    atomicAdd(&sc.freq[h], n);
+  } else {
+    atomicAdd(&t.scores[s].x, n);
+    t.scores[s].y = t.epoch;
+  }
+}
+__device__ __forceinline__ void score_cache_flush(const TableView& t, const ScoreCache& sc) {
+  if (!t.scores) return;
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < kScoreCells; i += blockDim.x) {
+    const uint32_t s = sc.slot[i];
+    if (s != kNil) {
+      atomicAdd(&t.scores[s].x, sc.freq[i]);
+      t.scores[s].y = t.epoch;
+    }
+  }
+}
+static_assert(kScoreCells == 1u << 9, "score_cache_add hashes to 9 bits");
+
 // Probe + gather of one tile. Lane `lane` holds `key` (valid == false for the lanes past the end of
 // the tile, whose key must be MEEPO_KEY_EMPTY). status_out / slot_out / key_out are this lane's own
-// output cells (may be null). occurrences = how many batch occurrences this key stands for (1, or
+// output cells (may be null; new_out = this element's cell of the NewList). occurrences = how many batch occurrences this key stands for (1, or
 // the sender's duplicate count on the sharded path): added to the hit/miss counters and to the key's
 // LFU score.
 template <int CPR, bool INSERT>
 __device__ __forceinline__ void probe_gather_tile(const TableView& t, uint64_t key, bool valid, uint32_t tile_keys,
                                                   uint4* __restrict__ out_tile, uint8_t* status_out,
                                                   uint32_t* slot_out, uint64_t* key_out, uint32_t occurrences,
-                                                  const NewList& nl, TileCounts& cnt, uint32_t lane) {
+                                                  uint32_t* new_out, TileCounts& cnt, const ScoreCache& sc,
+                                                  uint32_t lane) {
   Probe pr{kNil, MEEPO_KEY_INVALID, false};
   if (INSERT) {
     pr = probe_find_or_insert(t, key);
@@ -100,27 +169,25 @@ __device__ __forceinline__ void probe_gather_tile(const TableView& t, uint64_t k
     cnt.hit += pr.status == MEEPO_KEY_FOUND ? occurrences : 0u;
     cnt.miss += pr.status == MEEPO_KEY_MISS ? occurrences : 0u;
     cnt.full += pr.status == MEEPO_KEY_FULL ? occurrences : 0u;
-    if (t.scores && pr.slot != kNil) {  // meepo.h "Evict": freq += occurrences, last_epoch = epoch
-      atomicAdd(&t.scores[pr.slot].x, occurrences);
-      t.scores[pr.slot].y = t.epoch;
-    }
+  }
+  if (t.scores) {  // meepo.h "Evict": freq += occurrences, last_epoch = epoch
+    // duplicates of a key inside the tile are folded into one update first
+    const uint32_t s = valid ? pr.slot : kNil;
+    const unsigned peers = __match_any_sync(0xFFFFFFFFu, s);
+    const uint32_t total = __reduce_add_sync(peers, occurrences);
+    if (s != kNil && lane == (uint32_t)(__ffs(peers) - 1)) score_cache_add(t, sc, s, total);
   }
   bool fresh = false;
   if (INSERT) {
-    const unsigned wm = __ballot_sync(0xFFFFFFFFu, pr.winner);
-    if (wm) {  // list the claimed slots for publish_kernel (one atomic per warp)
-      const int leader = __ffs(wm) - 1;
-      uint32_t base = 0;
-      if ((int)lane == leader) base = atomicAdd(nl.count, (uint32_t)__popc(wm));
-      base = __shfl_sync(0xFFFFFFFFu, base, leader);
-      if (pr.winner) nl.slots[base + __popc(wm & ((1u << lane) - 1u))] = pr.slot;
-    }
+    if (valid && new_out) *new_out = pr.winner ? pr.slot : kNil;  // for publish_kernel
     fresh = __any_sync(0xFFFFFFFFu, pr.status == MEEPO_KEY_INSERTED);
   }
-  if (CPR > 0 && !fresh)
-    gather_tile_fast<(CPR > 0 ? CPR : 1)>(t, pr.slot, tile_keys, out_tile, lane);
-  else
+  if (CPR > 0) {
+    gather_tile_fast<(CPR > 0 ? CPR : 1)>(t, pr.status == MEEPO_KEY_INSERTED ? kNil : pr.slot, tile_keys, out_tile, lane);
+    if (fresh) fixup_fresh<(CPR > 0 ? CPR : 1)>(t, key, pr, tile_keys, out_tile, lane);
+  } else {
     gather_tile_slow(t, key, pr, tile_keys, out_tile, lane);
+  }
 }
 
 // stats: one atomic per warp per counter for the whole launch

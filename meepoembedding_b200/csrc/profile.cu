@@ -55,6 +55,13 @@ ProfScope::~ProfScope() {
     t_->prof->pending.push_back(ProfRecord{name_, a_, b});
   }
 }
+// host-side phases (wall clock) reported next to the kernels
+void prof_add_host(meepo_table* t, const char* name, double ms) {
+  if (!t->prof || !t->prof->on) return;
+  auto& x = t->prof->acc[name];
+  x.first += 1;
+  x.second += ms;
+}
 void destroy_profiler(meepo_table* t) {
   if (!t->prof) return;
   t->prof->drain();

@@ -134,6 +134,7 @@ MEEPO_API meepo_status meepo_create(const meepo_config* cfg, meepo_table** out) 
           cudaSuccess)
         return bail(e, "cudaHostAlloc(spill)");
       for (uint64_t i = t->spill_cap_tuples; i-- > 0;) t->spill_free.push_back((uint32_t)i);
+      t->spill_index.reserve(t->spill_cap_tuples);  // no rehash while evicting
     }
   }
   if ((e = cudaDeviceSynchronize()) != cudaSuccess) return bail(e, "cudaDeviceSynchronize");

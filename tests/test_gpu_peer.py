@@ -5,10 +5,12 @@ for the backward pass the oracle reproduces the sharded reduction structure — 
 meepo_reduce_duplicates (fixed-shape tree, rounded to the table dtype), then the ranks' partial sums
 in rank order — and the union of the shards must equal the oracle table bit for bit.
 
-`test_peer_single_process` drives `world` tables from one process (each rank on its own stream, all
-on cuda:0 or spread over the visible GPUs), so the whole protocol — push, device-side barriers,
-owner kernels, peer stores, expand — runs on a 1-GPU box. `test_peer_multiprocess_ipc` is the real
-deployment shape (one process per GPU, CUDA IPC windows) and needs >= 2 GPUs.
+`test_peer_single_process` drives `world` tables from ONE process, one GPU per rank (peer access
+instead of IPC); `test_peer_multiprocess_ipc` is the deployment shape (one process per GPU, CUDA IPC
+windows). Both need >= `world` GPUs: ranks meet in device-side flag barriers, and kernels that wait
+on one another must never share a GPU (nothing guarantees they run concurrently — B200_PROFILING.md),
+so on a 1-GPU box only the world == 1 case runs (the full protocol against itself); the multi-rank
+cases run under `gpurun --gpus 2|4|8` (logs under profiles/).
 """
 import os
 import socket
@@ -74,8 +76,9 @@ def _gpu_export(t, dev):
 def test_peer_single_process(oracle_lib, cuda_lib, world, dtype, dim, optimizer, scores):
     import torch
 
-    ndev = torch.cuda.device_count()
-    devs = [r % ndev for r in range(world)]
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs: ranks that wait on one another must not share a device")
+    devs = list(range(world))
     rdt = np.float32 if dtype == "f32" else np.uint16
     tdt = torch.float32 if dtype == "f32" else torch.bfloat16
     cap = 1 << 14
