@@ -237,6 +237,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--set", action="append", default=[], metavar="KEY=VALUE",
                     help="override a workload field (experiments), e.g. --set track_scores=False")
+    ap.add_argument("--force-sharded", action="store_true",
+                    help="N=1 only: run the step through the sharded peer-memory verbs (world 1) — profiling aid")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N>1: fused peer-memory verbs (csrc/peer.cu) or the NCCL all-to-all composition")
     args = ap.parse_args()
@@ -288,12 +290,16 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    sharded_mode = world > 1 or args.force_sharded
     if world > 1:
         import torch.distributed as dist_
         dist_.init_process_group("nccl", device_id=dev)
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
-    if world > 1:
+    if world == 1 and args.force_sharded:
+        import torch.distributed as dist_
+        dist_.init_process_group("gloo", init_method="tcp://127.0.0.1:29533", rank=0, world_size=1)
+    if sharded_mode:
         from meepoembedding_b200.sharded import PeerShardedTable, ShardedTable
 
     R = w["dim"] * esize(w["dtype"])
@@ -305,7 +311,7 @@ def main():
     evict_log = []
     stream = torch.cuda.current_stream()
     sp = stream.cuda_stream
-    if world > 1:
+    if sharded_mode:
         if args.exchange == "peer":
             # one (sender, owner) lane holds the unique keys one rank sends one owner: B/world on average
             region = min(w["batch"], int(w["batch"] / world * 1.25) + 4096)
@@ -343,7 +349,7 @@ def main():
     second_lookup = w["step"].endswith("lookup")
 
     def step(i):
-        if world > 1:
+        if sharded_mode:
             sharded.find_or_insert(dkeys[i], rows_out, status)
             sharded.apply_gradients(dkeys[i], grads)
         else:
@@ -400,7 +406,7 @@ def main():
     # ---- roofline of the dominant kernel group (CUDA events on the launch stream, inside the timed region)
     peak, peak_src = load_peaks()
     alg = algorithmic_bytes(w, B, U_avg)
-    if world > 1:  # owner-side kernels of the sharded verbs: entries actually received by this rank
+    if sharded_mode:  # owner-side kernels of the sharded verbs: entries actually received by this rank
         kr = (st1["peer_keys_received"] - st0["peer_keys_received"]) / args.steps
         gr = (st1["peer_grads_received"] - st0["peer_grads_received"]) / args.steps
         alg["sharded.owner_find_or_insert"] = kr * (16 + 2 * R)
@@ -486,7 +492,7 @@ def main():
                           "overflow_buckets": st1["overflow_buckets"], "prefill_s": prefill_s,
                           "unique_per_batch": U_avg, "inserted_during_bench": st1["size"] - size0}}
         print(json.dumps(line))
-    if world > 1:
+    if sharded_mode:
         if args.exchange == "peer":
             sharded.close()
         dist_.destroy_process_group()

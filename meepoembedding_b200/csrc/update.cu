@@ -339,24 +339,66 @@ __global__ void __launch_bounds__(256) apply_pipelined_kernel(TableView t, Apply
 }
 
 // A5: leaves of long segments -> partial[leaf][dim]. A leaf is a chain of up to 256 adds in batch
-// order per column; what can be hidden is the latency under it. One thread owns one 4-byte WORD of
-// the row (one fp32 column, or two bf16 columns), so a batch of 16 independent row loads costs 16
-// registers and a warp still reads 128 contiguous bytes per row; the indices of the next batch are
-// fetched (one broadcast load per warp) while the current batch is in flight.
-__device__ __forceinline__ uint32_t ld_nc_u32(const uint32_t* p) {
-  uint32_t r;
-  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
-  return r;
-}
+// order per column; what can be hidden is the latency under it. One thread owns one piece of the row
+// of V 4-byte words, so a batch of 16 independent row loads costs 16*V registers and a warp still
+// reads 128*V contiguous bytes per row; the indices of the next batch are fetched (broadcast loads,
+// L1 hits) while the current batch is in flight. Full batches run without predicates — an earlier
+// per-element-predicated version issued 17 instructions per load (ncu). V = 2 for rows above 256 B
+// (fewer instructions per byte: 0.46 -> 0.34 ms on cfg3/Zipf), V = 1 below (more threads per leaf:
+// 0.125 -> 0.065 ms on cfg4, where a 1M batch has too few leaves to fill the GPU).
+template <int V>
+struct Piece;
+template <>
+struct Piece<1> {
+  using T = uint32_t;
+  static __device__ __forceinline__ T ld(const T* p) {
+    T r;
+    asm("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+  }
+  static __device__ __forceinline__ uint32_t word(const T& v, int) { return v; }
+};
+template <>
+struct Piece<2> {
+  using T = uint2;
+  static __device__ __forceinline__ T ld(const T* p) {
+    T r;
+    asm("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+  }
+  static __device__ __forceinline__ uint32_t word(const T& v, int i) { return i ? v.y : v.x; }
+};
 
-template <bool BF16>
+template <bool BF16, int V>
+struct LeafAcc {
+  static constexpr int N = (BF16 ? 2 : 1) * V;  // columns per piece
+  float a[N];
+  template <bool FIRST>
+  __device__ __forceinline__ void take(const typename Piece<V>::T& x) {
+#pragma unroll
+    for (int i = 0; i < V; i++) {
+      const uint32_t w = Piece<V>::word(x, i);
+      if constexpr (BF16) {
+        const float lo = __uint_as_float(w << 16), hi = __uint_as_float(w & 0xFFFF0000u);
+        a[2 * i] = FIRST ? lo : __fadd_rn(a[2 * i], lo);
+        a[2 * i + 1] = FIRST ? hi : __fadd_rn(a[2 * i + 1], hi);
+      } else {
+        a[i] = FIRST ? __uint_as_float(w) : __fadd_rn(a[i], __uint_as_float(w));
+      }
+    }
+  }
+};
+
+template <bool BF16, int V>
 __global__ void __launch_bounds__(256) leaf_kernel(TableView t, ApplyArgs a, uint32_t tpl /* threads per leaf */) {
   constexpr uint32_t B = 16;
-  const uint32_t W = t.cpr * 4;  // 4-byte words per row
+  using P = Piece<V>;
+  constexpr int N = LeafAcc<BF16, V>::N;
+  const uint32_t W = t.cpr * 4 / V;  // pieces per row
   const uint32_t sub = threadIdx.x / tpl, wi = threadIdx.x % tpl;
   const uint32_t lpc = blockDim.x / tpl;  // leaves per CTA
   const uint32_t nleaves = a.ds->num_leaves;
-  const uint32_t* g32 = reinterpret_cast<const uint32_t*>(a.grads);
+  const typename P::T* g = reinterpret_cast<const typename P::T*>(a.grads);
   for (uint32_t l = blockIdx.x * lpc + sub; l < nleaves; l += gridDim.x * lpc) {
     const uint2 d = a.leaf_desc[l];
     const uint32_t s0 = a.seg_start[d.x] + d.y * kLeaf;
@@ -365,38 +407,44 @@ __global__ void __launch_bounds__(256) leaf_kernel(TableView t, ApplyArgs a, uin
     for (uint32_t wb = 0; wb < W; wb += tpl) {
       const uint32_t w = wb + wi;
       if (w >= W) continue;
-      float acc0 = 0.0f, acc1 = 0.0f;
-      bool first = true;
-      uint32_t ia[B];
+      const typename P::T* col = g + w;
+      LeafAcc<BF16, V> acc;
+      uint32_t ia[B];  // indices of the batch about to be loaded, always fetched one batch ahead
 #pragma unroll
       for (uint32_t u = 0; u < B; u++) ia[u] = u < cnt ? __ldg(sidx + u) : 0u;
+      bool first = true;
       for (uint32_t j = 0; j < cnt; j += B) {
-        uint32_t x[B];
+        typename P::T x[B];
+        const bool full = j + B <= cnt;
+        if (full) {
 #pragma unroll
-        for (uint32_t u = 0; u < B; u++)
-          if (j + u < cnt) x[u] = ld_nc_u32(g32 + (size_t)ia[u] * W + w);
+          for (uint32_t u = 0; u < B; u++) x[u] = P::ld(col + (size_t)ia[u] * W);
+        } else {
 #pragma unroll
-        for (uint32_t u = 0; u < B; u++) ia[u] = j + B + u < cnt ? __ldg(sidx + j + B + u) : 0u;
+          for (uint32_t u = 0; u < B; u++)
+            if (j + u < cnt) x[u] = P::ld(col + (size_t)ia[u] * W);
+        }
+        if (j + B < cnt) {
 #pragma unroll
-        for (uint32_t u = 0; u < B; u++) {
-          if (j + u >= cnt) continue;
-          const float g0 = BF16 ? __uint_as_float(x[u] << 16) : __uint_as_float(x[u]);
-          const float g1 = BF16 ? __uint_as_float(x[u] & 0xFFFF0000u) : 0.0f;
-          if (first) {
-            acc0 = g0;
-            acc1 = g1;
-            first = false;
-          } else {
-            acc0 = __fadd_rn(acc0, g0);
-            if (BF16) acc1 = __fadd_rn(acc1, g1);
-          }
+          for (uint32_t u = 0; u < B; u++) ia[u] = j + B + u < cnt ? __ldg(sidx + j + B + u) : 0u;
+        }
+        if (first)
+          acc.template take<true>(x[0]);
+        else
+          acc.template take<false>(x[0]);
+        first = false;
+        if (full) {
+#pragma unroll
+          for (uint32_t u = 1; u < B; u++) acc.template take<false>(x[u]);
+        } else {
+#pragma unroll
+          for (uint32_t u = 1; u < B; u++)
+            if (j + u < cnt) acc.template take<false>(x[u]);
         }
       }
-      if (BF16) {
-        *reinterpret_cast<float2*>(a.partial + (size_t)l * t.dim + 2 * w) = make_float2(acc0, acc1);
-      } else {
-        a.partial[(size_t)l * t.dim + w] = acc0;
-      }
+      float* out = a.partial + (size_t)l * t.dim + (size_t)w * N;
+#pragma unroll
+      for (int i = 0; i < N; i++) out[i] = acc.a[i];
     }
   }
 }
@@ -575,7 +623,9 @@ meepo_status run_segmented(meepo_table* t, SegWork& w, uint32_t limit, const voi
     pick_apply<true>(mode, pipelined, k_apply, k_finish);
   else
     pick_apply<false>(mode, pipelined, k_apply, k_finish);
-  const void* k_leaf = bf16 ? (const void*)leaf_kernel<true> : (const void*)leaf_kernel<false>;
+  const int leaf_v = t->row_bytes > 256 ? 2 : 1;  // 4-byte words per thread in the leaf kernel
+  const void* k_leaf = bf16 ? (leaf_v == 2 ? (const void*)leaf_kernel<true, 2> : (const void*)leaf_kernel<true, 1>)
+                            : (leaf_v == 2 ? (const void*)leaf_kernel<false, 2> : (const void*)leaf_kernel<false, 1>);
   void* args[] = {&t->v, &a};
   const uint64_t groups_per_block = 256 / gl;
   if (grads_ready) MEEPO_CUDA_TRY(cudaStreamWaitEvent(stream, grads_ready, 0));
@@ -587,8 +637,8 @@ meepo_status run_segmented(meepo_table* t, SegWork& w, uint32_t limit, const voi
   }
   {
     ProfScope ps(t, names[3], stream);
-    const uint32_t words = t->v.cpr * 4;
-    uint32_t tpl = std::min<uint32_t>(256, (words + 31) / 32 * 32);  // whole warps per leaf
+    const uint32_t pieces = t->v.cpr * 4 / leaf_v;  // pieces per row, one thread each
+    uint32_t tpl = std::min<uint32_t>(256, (pieces + 31) / 32 * 32);  // whole warps per leaf
     while (256 % tpl) tpl += 32;
     const uint64_t lpc = 256 / tpl;
     const int grid = grid_for(t, k_leaf, 256, 0, (w.max_leaves + lpc - 1) / lpc);
