@@ -228,7 +228,8 @@ MEEPO_API meepo_status meepo_evict(meepo_table* t, int32_t policy, double target
   const uint64_t target = (uint64_t)std::floor(target_load * (double)t->v.slots);
   if (size <= target) return MEEPO_OK;
   const uint64_t k = size - target;
-  t->cache_valid = false;  // slots are about to change owners
+  t->cache_valid = false;
+  t->slot_gen++;  // slots are about to change owners
 
   // --- radix select: threshold T = score of the k-th smallest, need `remaining` of the ties
   unsigned long long* d_hist = t->dstate->hist;
@@ -405,6 +406,7 @@ MEEPO_API meepo_status meepo_spill_readmit(meepo_table* t, const uint64_t* keys,
   const uint64_t m = ins_keys.size();
   if (m) {
     t->cache_valid = false;
+    t->slot_gen++;
     MEEPO_CUDA_TRY(cudaMemcpyAsync(d_keys, ins_keys.data(), m * 8, cudaMemcpyHostToDevice, stream));
     MEEPO_CUDA_TRY(cudaMemcpyAsync(d_slab, ins_slab.data(), m * 4, cudaMemcpyHostToDevice, stream));
     NewList nl{d_new};

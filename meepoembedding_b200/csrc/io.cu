@@ -224,6 +224,7 @@ meepo_status import_device(meepo_table* t, const uint64_t* keys, const void* row
                            cudaStream_t stream, uint32_t* slot_buf, uint32_t* new_slots) {
   if (n == 0) return MEEPO_OK;
   t->cache_valid = false;
+  t->slot_gen++;
   NewList nl{new_slots};
   const int grid = (int)std::min<uint64_t>((n + 255) / 256, (uint64_t)t->num_sms * 8);
   MEEPO_TRY(import_probe_launch(t, keys, n, slot_buf, status_out, nl, stream));

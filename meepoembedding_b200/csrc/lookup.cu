@@ -70,6 +70,7 @@ meepo_status probe_gather_begin(meepo_table* t, uint64_t n_total, bool insert, c
   t->cur_new.slots = nullptr;
   t->cur_new_off = 0;
   t->cache_valid = false;
+  t->slot_gen++;
   t->cache_off = 0;
   t->cache_n = 0;
   if (t->cache_enabled && n_total) {

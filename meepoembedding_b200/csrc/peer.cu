@@ -23,6 +23,12 @@
 //        single table: ONE optimizer step per key, deterministic
 //     barrier
 //
+// A backward pass over the batch of the preceding forward pass (the training loop) reuses it: the
+// sender skips the dedup and the key push (positions and owners are remembered, the keys are still in
+// the owners' windows), the owner takes each entry's slot from the forward pass instead of probing.
+// Whether the batch is the same is decided on the device (a compare kernel sets a flag that the
+// skippable kernels read), per sender, and an owner whose table changed in between probes anyway.
+//
 // Only bulk stores and the barrier flags cross NVLink: every table mutation (CAS insert, tag
 // publish, optimizer step) is done by the owner on its own HBM. Every count that depends on the
 // data (unique keys, keys per owner, received entries) stays on the device: grids are persistent
@@ -46,6 +52,7 @@ enum PeerError : uint32_t { PE_TIMEOUT = 1u, PE_REGION_OVERFLOW = 2u };
 struct PeerWindow {
   unsigned long long* flags;  // [kMaxPeers] barrier sequence number last signalled by each source
   uint32_t* recv_cnt;         // [kMaxPeers] entries source s pushed in the current phase
+  uint32_t* recv_reuse;       // [kMaxPeers] source s re-sent the entries of its last forward pass (same positions)
   uint32_t* error;            // sticky PeerError bits
   uint64_t* recv_keys;        // [world][region]      keys pushed by source s
   uint32_t* recv_occ;         // [world][region]      batch occurrences behind each pushed key
@@ -91,6 +98,17 @@ struct PeerState {
   PeerWork* work = nullptr;
   uint32_t* loc = nullptr;         // [max_batch]     window position of unique key u: owner * region + p
   uint4* trash_row = nullptr;      // [cpr]           where rows of keys beyond a full lane go
+  // the dedup of the last verb (persistent so that a backward pass can reuse the forward pass's)
+  uint64_t* ukeys = nullptr;       // [max_batch]     unique keys
+  uint32_t* inverse = nullptr;     // [max_batch]     unique id of every batch element
+  uint64_t* n_unique = nullptr;    // [1]
+  uint64_t* fwd_keys = nullptr;    // [max_batch]     copy of the last forward batch
+  uint32_t* fwd_send_cnt = nullptr;  // [kMaxPeers]   entries per owner of the last forward push
+  uint32_t* reuse_flag = nullptr;  // [1]             this backward batch == the last forward batch
+  uint32_t* entry_slot = nullptr;  // [world*region]  owner side: slot of every entry of the last forward pass
+  bool fwd_valid = false;          // the last sharded verb on this table was a forward pass ...
+  uint64_t fwd_n = 0;              // ... of this many keys
+  uint64_t entry_gen = ~0ull;      // table slot generation when entry_slot was written
   PeerSet ps{};
   void* opened[kMaxPeers] = {};
   unsigned long long seq = 0;
@@ -104,6 +122,7 @@ static void carve_window(char* base, uint32_t world, uint64_t region, uint32_t c
   size_t off = 0;
   w.flags = reinterpret_cast<unsigned long long*>(base + off);
   w.recv_cnt = reinterpret_cast<uint32_t*>(base + off + 128);
+  w.recv_reuse = reinterpret_cast<uint32_t*>(base + off + 192);
   w.error = reinterpret_cast<uint32_t*>(base + off + 256);
   off += kWindowHeader;
   const size_t cells = (size_t)world * region;
@@ -144,11 +163,14 @@ __device__ __forceinline__ uint32_t ld_window(const uint32_t* p) { return __ldcg
 // a peer that never shows up sets PE_TIMEOUT instead of hanging the GPU.
 __global__ void __launch_bounds__(32) peer_barrier_kernel(const __grid_constant__ PeerSet ps, unsigned long long seq,
                                                           const uint32_t* send_cnt, PeerWork* work, int for_apply,
-                                                          unsigned long long* counters,
+                                                          unsigned long long* counters, uint32_t* save_cnt,
+                                                          const uint32_t* reuse_flag,
                                                           unsigned long long timeout_ns) {
   const uint32_t j = threadIdx.x;
   if (j < ps.world) {
     if (send_cnt) ps.w[j].recv_cnt[ps.rank] = min(send_cnt[j], ps.region);
+    if (send_cnt && save_cnt) save_cnt[j] = send_cnt[j];
+    if (reuse_flag) ps.w[j].recv_reuse[ps.rank] = *reuse_flag ? 1u : 0u;
     __threadfence_system();
     st_release_sys(ps.w[j].flags + ps.rank, seq);
     const unsigned long long* mine = ps.w[ps.rank].flags + j;
@@ -220,16 +242,52 @@ __global__ void __launch_bounds__(256) push_keys_kernel(const __grid_constant__ 
   }
 }
 
+// Backward: is this the batch of the last forward pass? (flag preset to 1, cleared on any mismatch)
+__global__ void __launch_bounds__(256) same_batch_kernel(const uint64_t* __restrict__ keys,
+                                                         const uint64_t* __restrict__ fwd_keys, uint32_t n,
+                                                         uint32_t* __restrict__ flag) {
+  bool same = true;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    same &= __ldg(keys + i) == __ldg(fwd_keys + i);
+  if (!__all_sync(0xFFFFFFFFu, same) && (threadIdx.x & 31u) == 0) *flag = 0u;
+}
+// sort input of the pre-reduction: (unique id, batch index); invalid keys sort last and are skipped
+__global__ void __launch_bounds__(256) fill_sort_kernel(const uint32_t* __restrict__ inverse, uint32_t n,
+                                                        uint32_t* __restrict__ sort_key,
+                                                        uint32_t* __restrict__ sort_val) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t u = __ldg(inverse + i);
+    sort_key[i] = u == kNil ? n : u;
+    sort_val[i] = i;
+  }
+}
+
 // Backward: position of every unique key at its owner. The key goes there now; row_ptrs[u] is where
 // the reduce kernel will store the key's summed gradient row (straight into the owner's window).
 __global__ void __launch_bounds__(256) assign_grad_rows_kernel(const __grid_constant__ PeerSet ps,
                                                                const uint64_t* __restrict__ ukeys,
                                                                const unsigned long long* __restrict__ n_unique,
                                                                uint32_t* __restrict__ send_cnt,
-                                                               uint4** __restrict__ row_ptrs, uint4* trash_row) {
+                                                               uint4** __restrict__ row_ptrs, uint4* trash_row,
+                                                               const uint32_t* __restrict__ reuse_flag,
+                                                               uint32_t* __restrict__ loc,
+                                                               const uint32_t* __restrict__ fwd_send_cnt) {
   const uint32_t n = (uint32_t)*n_unique;
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t stride = gridDim.x * blockDim.x;
+  if (*reuse_flag) {  // same batch as the forward pass: same owners, same positions, keys already there
+    if (blockIdx.x == 0 && threadIdx.x < ps.world) send_cnt[threadIdx.x] = fwd_send_cnt[threadIdx.x];
+    for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n; u += stride) {
+      const uint32_t l = loc[u];
+      if (l == kNil) {
+        row_ptrs[u] = trash_row;
+      } else {
+        const uint32_t o = l / ps.region, pos = l - o * ps.region;
+        row_ptrs[u] = ps.w[o].recv_grads + ((size_t)ps.rank * ps.region + pos) * ps.cpr;
+      }
+    }
+    return;
+  }
   for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
     const uint32_t u = base + lane;
     const bool act = u < n;
@@ -241,11 +299,13 @@ __global__ void __launch_bounds__(256) assign_grad_rows_kernel(const __grid_cons
     if (p >= ps.region) {
       atomicOr(ps.w[ps.rank].error, (uint32_t)PE_REGION_OVERFLOW);
       row_ptrs[u] = trash_row;
+      loc[u] = kNil;
       continue;
     }
     const size_t e = (size_t)ps.rank * ps.region + p;
     ps.w[o].recv_keys[e] = key;
     row_ptrs[u] = ps.w[o].recv_grads + e * ps.cpr;
+    loc[u] = o * ps.region + p;
   }
 }
 
@@ -255,7 +315,8 @@ __global__ void __launch_bounds__(256) assign_grad_rows_kernel(const __grid_cons
 // single-table one with a peer pointer as its output.
 template <int CPR, bool INSERT>
 __global__ void __launch_bounds__(256, 4) owner_probe_gather_kernel(TableView t, const __grid_constant__ PeerSet ps,
-                                                                 const PeerWork* __restrict__ work, NewList nl) {
+                                                                 const PeerWork* __restrict__ work, NewList nl,
+                                                                 uint32_t* __restrict__ entry_slot) {
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -281,7 +342,7 @@ __global__ void __launch_bounds__(256, 4) owner_probe_gather_kernel(TableView t,
       const uint32_t occ = valid ? ld_window(me.recv_occ + e) : 0u;
       const size_t r = (size_t)ps.rank * ps.region + p0;    // in the requester's window: [owner][position]
       probe_gather_tile<CPR, INSERT>(t, key, valid, tile_keys, ps.w[s].ret_rows + r * cpr,
-                                     valid ? ps.w[s].ret_status + r + lane : nullptr, nullptr, nullptr, occ,
+                                     valid ? ps.w[s].ret_status + r + lane : nullptr, entry_slot + e, nullptr, occ,
                                      nl.slots + e, cnt, scache, lane);
     }
   }
@@ -353,7 +414,8 @@ __global__ void __launch_bounds__(256) expand_kernel(const uint4* __restrict__ r
 __global__ void __launch_bounds__(256) recv_slots_kernel(TableView t, const __grid_constant__ PeerSet ps,
                                                          const PeerWork* __restrict__ work, uint32_t n_pad,
                                                          uint32_t* __restrict__ sort_key,
-                                                         uint32_t* __restrict__ sort_val) {
+                                                         uint32_t* __restrict__ sort_val,
+                                                         const uint32_t* __restrict__ entry_slot, int entry_valid) {
   const uint32_t n = work->recv_off[ps.world];
   const PeerWindow& me = ps.w[ps.rank];
   uint32_t dropped = 0;
@@ -363,8 +425,13 @@ __global__ void __launch_bounds__(256) recv_slots_kernel(TableView t, const __gr
       uint32_t s = 0;
       for (uint32_t k = 1; k < ps.world; k++) s += work->recv_off[k] <= i ? 1u : 0u;
       e = s * ps.region + (i - work->recv_off[s]);
-      const uint64_t key = ld_window(me.recv_keys + e);
-      const uint32_t f = key_valid(key) ? probe_find<kReadOnly>(t, key) : kNil;
+      uint32_t f;
+      if (entry_valid && ld_window(me.recv_reuse + s)) {  // the entries of the last forward pass, re-sent
+        f = __ldg(entry_slot + e);
+      } else {
+        const uint64_t key = ld_window(me.recv_keys + e);
+        f = key_valid(key) ? probe_find<kReadOnly>(t, key) : kNil;
+      }
       if (f == kNil)
         dropped++;
       else
@@ -380,12 +447,11 @@ __global__ void __launch_bounds__(256) recv_slots_kernel(TableView t, const __gr
 // --- host side ---------------------------------------------------------------------------------
 static size_t forward_ws_bytes(const meepo_table* t, const PeerState* p) {
   const uint64_t n = p->max_batch;
-  return dedup_bytes(t, n, false) + Workspace::pad(n * 8) + 2 * Workspace::pad(n * 4) + 256 +
-         Workspace::pad((size_t)p->world * p->region * 4) + 4096;
+  return dedup_bytes(t, n, false) + Workspace::pad(n * 4) + Workspace::pad((size_t)p->world * p->region * 4) + 4096;
 }
 static size_t backward_ws_bytes(const meepo_table* t, const PeerState* p) {
   const uint64_t n = p->max_batch;
-  return dedup_bytes(t, n, true) + 2 * Workspace::pad(n * 8) + 256 +
+  return dedup_bytes(t, n, true) + Workspace::pad(n * 8) + 256 +
          SegWork::bytes((uint64_t)p->world * p->region, t->v.dim, bits_for(t->v.slots)) + 4096;
 }
 
@@ -418,7 +484,8 @@ static meepo_status barrier(meepo_table* t, const uint32_t* send_cnt, bool for_a
   ProfScope ps(t, "sharded.barrier", stream);
   p->seq++;
   peer_barrier_kernel<<<1, 32, 0, stream>>>(p->ps, p->seq, send_cnt, send_cnt ? p->work : nullptr, for_apply ? 1 : 0,
-                                            t->v.counters, p->timeout_ns);
+                                            t->v.counters, send_cnt && !for_apply ? p->fwd_send_cnt : nullptr,
+                                            send_cnt && for_apply ? p->reuse_flag : nullptr, p->timeout_ns);
   MEEPO_CUDA_TRY(cudaGetLastError());
   return MEEPO_OK;
 }
@@ -439,11 +506,13 @@ static meepo_status sharded_forward(meepo_table* t, const uint64_t* keys, uint64
   t->cache_valid = false;
   t->epoch++;
   t->v.epoch = (uint32_t)t->epoch;
+  p->fwd_valid = false;
   MEEPO_TRY(t->ws.reserve(forward_ws_bytes(t, p), stream));
-  uint64_t* ukeys = t->ws.take<uint64_t>(std::max<uint64_t>(n, 1));
-  uint32_t* inverse = t->ws.take<uint32_t>(std::max<uint64_t>(n, 1));
+  uint64_t* ukeys = p->ukeys;
+  uint32_t* inverse = p->inverse;
   uint32_t* uocc = t->ws.take<uint32_t>(std::max<uint64_t>(n, 1));  // hit/miss stats and LFU scores count occurrences
-  uint64_t* n_unique = t->ws.take<uint64_t>(1);
+  uint64_t* n_unique = p->n_unique;
+  if (n) MEEPO_CUDA_TRY(cudaMemcpyAsync(p->fwd_keys, keys, n * 8, cudaMemcpyDeviceToDevice, stream));
   const uint64_t n_window = (uint64_t)p->world * p->region;
   NewList nl{t->ws.take<uint32_t>(n_window)};  // one cell per window entry
   if (insert) MEEPO_CUDA_TRY(cudaMemsetAsync(nl.slots, 0xFF, n_window * 4, stream));
@@ -463,7 +532,7 @@ static meepo_status sharded_forward(meepo_table* t, const uint64_t* keys, uint64
     const uint64_t tiles = ((uint64_t)p->world * p->region + 31) / 32 + p->world;
     const int grid = grid_for(t, kern, 256, 0, (tiles + 7) / 8);
     const PeerWork* work = p->work;
-    void* args[] = {&t->v, &p->ps, &work, &nl};
+    void* args[] = {&t->v, &p->ps, &work, &nl, &p->entry_slot};
     MEEPO_CUDA_TRY(cudaLaunchKernel(kern, dim3(grid), dim3(256), args, 0, stream));
   }
   if (insert) {
@@ -480,6 +549,9 @@ static meepo_status sharded_forward(meepo_table* t, const uint64_t* keys, uint64
                                             reinterpret_cast<uint4*>(rows_out), status_out);
     MEEPO_CUDA_TRY(cudaGetLastError());
   }
+  p->fwd_valid = true;  // a backward pass over the same batch may reuse the dedup, the positions and the slots
+  p->fwd_n = n;
+  p->entry_gen = t->slot_gen;
   return MEEPO_OK;
 }
 
@@ -489,21 +561,35 @@ static meepo_status sharded_apply(meepo_table* t, const uint64_t* keys, const vo
   DeviceGuard guard(t->device);
   PeerState* p = t->peer;
   MEEPO_TRY(t->ws.reserve(backward_ws_bytes(t, p), stream));
-  uint64_t* ukeys = t->ws.take<uint64_t>(std::max<uint64_t>(n, 1));
+  uint64_t* ukeys = p->ukeys;
   uint4** row_ptrs = t->ws.take<uint4*>(std::max<uint64_t>(n, 1));
-  uint64_t* n_unique = t->ws.take<uint64_t>(1);
+  uint64_t* n_unique = p->n_unique;
   const uint64_t n_pad = (uint64_t)p->world * p->region;
   SegWork ow;  // owner side
   ow.take(t->ws, n_pad, t->v.dim, bits_for(t->v.slots));
   SegWork sw;  // sender side
-  DedupOut dd{ukeys, nullptr, nullptr, n_unique, nullptr, reinterpret_cast<void* const*>(row_ptrs)};
-  MEEPO_TRY(dedup_hash(t, keys, n, dd, true, sw, stream));
+  if (n) sw.take(t->ws, n, t->v.dim, bits_for((uint32_t)n));
+  // the batch of the last forward pass? decided on the device; only the first backward pass after it qualifies
+  const bool may_reuse = p->fwd_valid && n == p->fwd_n && n > 0 && !getenv("MEEPO_PEER_NO_REUSE");
+  p->fwd_valid = false;
+  {
+    ProfScope ps(t, "sharded.same_batch", stream);
+    MEEPO_CUDA_TRY(cudaMemsetAsync(p->reuse_flag, may_reuse ? 1 : 0, 4, stream));
+    if (may_reuse) {
+      const int grid = grid_for(t, (const void*)same_batch_kernel, 256, 0, (n + 255) / 256);
+      same_batch_kernel<<<grid, 256, 0, stream>>>(keys, p->fwd_keys, (uint32_t)n, p->reuse_flag);
+    }
+  }
+  DedupOut dd{ukeys, nullptr, p->inverse, n_unique, nullptr, reinterpret_cast<void* const*>(row_ptrs)};
+  SegWork unused;
+  MEEPO_TRY(dedup_hash(t, keys, n, dd, false, unused, stream, p->reuse_flag));  // no-op when the flag is set
   {
     ProfScope ps(t, "sharded.assign_grad_rows", stream);
     MEEPO_CUDA_TRY(cudaMemsetAsync(p->send_cnt, 0, kMaxPeers * 4, stream));
     const int grid = grid_for(t, (const void*)assign_grad_rows_kernel, 256, 0, (std::max<uint64_t>(n, 1) + 255) / 256);
+    if (n) fill_sort_kernel<<<grid, 256, 0, stream>>>(p->inverse, (uint32_t)n, sw.sk_in, sw.sv_in);
     assign_grad_rows_kernel<<<grid, 256, 0, stream>>>(p->ps, ukeys, (const unsigned long long*)n_unique, p->send_cnt,
-                                                      row_ptrs, p->trash_row);
+                                                      row_ptrs, p->trash_row, p->reuse_flag, p->loc, p->fwd_send_cnt);
     MEEPO_CUDA_TRY(cudaGetLastError());
   }
   MEEPO_TRY(dedup_reduce(t, sw, grads, n, dd, stream));  // summed rows land in the owners' windows
@@ -511,7 +597,9 @@ static meepo_status sharded_apply(meepo_table* t, const uint64_t* keys, const vo
   {
     ProfScope ps(t, "sharded.owner_slots", stream);
     const int grid = grid_for(t, (const void*)recv_slots_kernel, 256, 0, (n_pad + 255) / 256);
-    recv_slots_kernel<<<grid, 256, 0, stream>>>(t->v, p->ps, p->work, (uint32_t)n_pad, ow.sk_in, ow.sv_in);
+    const int entry_valid = p->entry_gen == t->slot_gen ? 1 : 0;  // did anything move slots since the forward pass?
+    recv_slots_kernel<<<grid, 256, 0, stream>>>(t->v, p->ps, p->work, (uint32_t)n_pad, ow.sk_in, ow.sv_in, p->entry_slot,
+                                                entry_valid);
     MEEPO_CUDA_TRY(cudaGetLastError());
   }
   static const char* const names[5] = {"sharded.owner_sort(cub)", "sharded.owner_segments(3 kernels)",
@@ -561,6 +649,7 @@ static meepo_status warm_up(meepo_table* t) {
   p->seq = 0;
   p->ps = saved;
   p->attached = false;
+  p->fwd_valid = false;
   t->epoch = epoch;
   t->v.epoch = (uint32_t)epoch;
   return rc;
@@ -606,10 +695,31 @@ MEEPO_API meepo_status meepo_peer_prepare(meepo_table* t, uint32_t rank, uint32_
   off += align_up(sizeof(PeerWork));
   const size_t o_trash = off;
   off += align_up((size_t)t->v.cpr * 16);
+  const size_t o_fcnt = off;
+  off += align_up(kMaxPeers * 4);
+  const size_t o_flag = off;
+  off += align_up(4);
+  const size_t o_nu = off;
+  off += align_up(8);
   const size_t o_loc = off;
   off += align_up(max_batch * 4);
+  const size_t o_inv = off;
+  off += align_up(max_batch * 4);
+  const size_t o_ukeys = off;
+  off += align_up(max_batch * 8);
+  const size_t o_fkeys = off;
+  off += align_up(max_batch * 8);
+  const size_t o_eslot = off;
+  off += align_up((size_t)world * region_keys * 4);
   if ((e = cudaMalloc(&p->local, off)) != cudaSuccess) return bail(e, "cudaMalloc(peer scratch)");
   if ((e = cudaMemset(p->local, 0, o_loc)) != cudaSuccess) return bail(e, "cudaMemset");
+  p->fwd_send_cnt = reinterpret_cast<uint32_t*>(p->local + o_fcnt);
+  p->reuse_flag = reinterpret_cast<uint32_t*>(p->local + o_flag);
+  p->n_unique = reinterpret_cast<uint64_t*>(p->local + o_nu);
+  p->inverse = reinterpret_cast<uint32_t*>(p->local + o_inv);
+  p->ukeys = reinterpret_cast<uint64_t*>(p->local + o_ukeys);
+  p->fwd_keys = reinterpret_cast<uint64_t*>(p->local + o_fkeys);
+  p->entry_slot = reinterpret_cast<uint32_t*>(p->local + o_eslot);
   p->send_cnt = reinterpret_cast<uint32_t*>(p->local + o_cnt);
   p->work = reinterpret_cast<PeerWork*>(p->local + o_work);
   p->trash_row = reinterpret_cast<uint4*>(p->local + o_trash);

@@ -162,10 +162,8 @@ __device__ __forceinline__ void probe_gather_tile(const TableView& t, uint64_t k
   }
   if (valid) {
     if (status_out) *status_out = (uint8_t)pr.status;
-    if (slot_out) {
-      *slot_out = pr.slot;
-      *key_out = key;
-    }
+    if (slot_out) *slot_out = pr.slot;
+    if (key_out) *key_out = key;
     cnt.hit += pr.status == MEEPO_KEY_FOUND ? occurrences : 0u;
     cnt.miss += pr.status == MEEPO_KEY_MISS ? occurrences : 0u;
     cnt.full += pr.status == MEEPO_KEY_FULL ? occurrences : 0u;

@@ -14,8 +14,12 @@ constexpr int kScanTile = 1024;  // elements per CTA in the occupancy passes
 
 // ---------------------------------------------------------------------------------------------
 // single-CTA exclusive scan (n is small: tiles x shards). out[n] = total.
+// `skip` (optional, device): the whole pass is a no-op when *skip != 0 (the sharded backward pass reuses
+// the dedup of the preceding forward pass when the batch is the same; the host cannot know that).
 __global__ void __launch_bounds__(1024) excl_scan_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
-                                                         uint32_t n, unsigned long long* total64) {
+                                                         uint32_t n, unsigned long long* total64,
+                                                         const uint32_t* __restrict__ skip) {
+  if (skip && *skip) return;
   __shared__ uint32_t warp_sum[32];
   __shared__ uint32_t carry_s;
   if (threadIdx.x == 0) carry_s = 0;
@@ -120,7 +124,8 @@ __global__ void __launch_bounds__(256) part_scatter_kernel(const uint64_t* __res
 // batch-level dedup
 __global__ void __launch_bounds__(256) dedup_insert_kernel(const uint64_t* __restrict__ keys, uint32_t n,
                                                            uint64_t* __restrict__ scratch, uint32_t mask,
-                                                           uint32_t* __restrict__ pos) {
+                                                           uint32_t* __restrict__ pos, const uint32_t* __restrict__ skip) {
+  if (skip && *skip) return;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint64_t key = __ldg(keys + i);
     uint32_t p = kNil;
@@ -143,7 +148,9 @@ __global__ void __launch_bounds__(256) dedup_insert_kernel(const uint64_t* __res
 }
 
 __global__ void __launch_bounds__(256) occ_count_kernel(const uint64_t* __restrict__ scratch, uint32_t m,
-                                                        uint32_t* __restrict__ tile_count) {
+                                                        uint32_t* __restrict__ tile_count,
+                                                        const uint32_t* __restrict__ skip) {
+  if (skip && *skip) return;
   const uint32_t base = blockIdx.x * kScanTile;
   int total = 0;
 #pragma unroll
@@ -157,7 +164,8 @@ __global__ void __launch_bounds__(256) occ_count_kernel(const uint64_t* __restri
 __global__ void __launch_bounds__(256) occ_fill_kernel(const uint64_t* __restrict__ scratch, uint32_t m,
                                                        const uint32_t* __restrict__ tile_off,
                                                        uint32_t* __restrict__ uid_of_slot,
-                                                       uint64_t* __restrict__ unique_out) {
+                                                       uint64_t* __restrict__ unique_out, const uint32_t* __restrict__ skip) {
+  if (skip && *skip) return;
   __shared__ uint32_t warp_cnt[8];
   const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   uint32_t running = tile_off[blockIdx.x];
@@ -192,7 +200,9 @@ __global__ void __launch_bounds__(256) dedup_inverse_kernel(const uint32_t* __re
                                                             uint32_t* __restrict__ inverse_out,
                                                             uint32_t* __restrict__ sort_key,
                                                             uint32_t* __restrict__ sort_val,
-                                                            uint32_t* __restrict__ occurrences) {
+                                                            uint32_t* __restrict__ occurrences,
+                                                            const uint32_t* __restrict__ skip) {
+  if (skip && *skip) return;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint32_t p = pos[i];
     const uint32_t u = p == kNil ? kNil : uid_of_slot[p];
@@ -254,7 +264,7 @@ size_t dedup_bytes(const meepo_table* t, uint64_t n, bool with_grads) {
 
 // phase 1: unique keys, inverse, occurrences; with_grads also prepares the (uid, batch index) sort input
 meepo_status dedup_hash(meepo_table* t, const uint64_t* keys, uint64_t n, const DedupOut& o, bool with_grads,
-                        SegWork& w, cudaStream_t stream) {
+                        SegWork& w, cudaStream_t stream, const uint32_t* skip) {
   if (n == 0) {
     MEEPO_CUDA_TRY(cudaMemsetAsync(o.n_unique, 0, 8, stream));
     return MEEPO_OK;
@@ -273,13 +283,13 @@ meepo_status dedup_hash(meepo_table* t, const uint64_t* keys, uint64_t n, const 
   MEEPO_CUDA_TRY(cudaMemsetAsync(scratch, 0xFF, (size_t)m * 8, stream));
   if (o.occurrences) MEEPO_CUDA_TRY(cudaMemsetAsync(o.occurrences, 0, n * 4, stream));
   const int grid = grid_for(t, (const void*)dedup_insert_kernel, 256, 0, (n + 255) / 256);
-  dedup_insert_kernel<<<grid, 256, 0, stream>>>(keys, (uint32_t)n, scratch, m - 1, pos);
-  occ_count_kernel<<<ntiles, 256, 0, stream>>>(scratch, m, tile_count);
-  excl_scan_kernel<<<1, 1024, 0, stream>>>(tile_count, tile_off, ntiles, (unsigned long long*)o.n_unique);
-  occ_fill_kernel<<<ntiles, 256, 0, stream>>>(scratch, m, tile_off, uid_of_slot, o.unique_keys);
+  dedup_insert_kernel<<<grid, 256, 0, stream>>>(keys, (uint32_t)n, scratch, m - 1, pos, skip);
+  occ_count_kernel<<<ntiles, 256, 0, stream>>>(scratch, m, tile_count, skip);
+  excl_scan_kernel<<<1, 1024, 0, stream>>>(tile_count, tile_off, ntiles, (unsigned long long*)o.n_unique, skip);
+  occ_fill_kernel<<<ntiles, 256, 0, stream>>>(scratch, m, tile_off, uid_of_slot, o.unique_keys, skip);
   dedup_inverse_kernel<<<grid, 256, 0, stream>>>(pos, (uint32_t)n, uid_of_slot, o.inverse,
                                                  with_grads ? w.sk_in : nullptr, with_grads ? w.sv_in : nullptr,
-                                                 o.occurrences);
+                                                 o.occurrences, skip);
   MEEPO_CUDA_TRY(cudaGetLastError());
   return MEEPO_OK;
 }
@@ -328,7 +338,7 @@ MEEPO_API meepo_status meepo_shard_partition(meepo_table* t, const uint64_t* key
   uint32_t* off = t->ws.take<uint32_t>(cells + 1);
   ProfScope ps(t, "shard.partition(3 kernels)", stream);
   part_hist_kernel<<<ntiles, 256, 0, stream>>>(keys, (uint32_t)n, num_shards, ntiles, hist);
-  excl_scan_kernel<<<1, 1024, 0, stream>>>(hist, off, (uint32_t)cells, nullptr);
+  excl_scan_kernel<<<1, 1024, 0, stream>>>(hist, off, (uint32_t)cells, nullptr, nullptr);
   part_scatter_kernel<<<ntiles, 256, 0, stream>>>(keys, (uint32_t)n, num_shards, ntiles, off, counts_out, perm_out,
                                                   keys_sorted_out);
   MEEPO_CUDA_TRY(cudaGetLastError());

@@ -172,6 +172,7 @@ struct meepo_table {
   meepo::SlotCache cache{nullptr, nullptr};
   uint64_t cache_cap = 0, cache_n = 0, cache_off = 0;
   bool cache_valid = false, cache_enabled = true;
+  uint64_t slot_gen = 0;  // bumped whenever slots may change owners outside the sharded verbs (evict, import, ...)
   uint64_t epoch = 0;
   struct meepo::Profiler* prof = nullptr;  // per-kernel event timing, off unless enabled
   // host-buffer front end (pinned staging + private streams), created lazily
@@ -247,7 +248,7 @@ struct DedupOut {
 struct SegWork;
 size_t dedup_bytes(const meepo_table* t, uint64_t n, bool with_grads);
 meepo_status dedup_hash(meepo_table* t, const uint64_t* keys, uint64_t n, const DedupOut& o, bool with_grads,
-                        SegWork& w, cudaStream_t stream);
+                        SegWork& w, cudaStream_t stream, const uint32_t* skip = nullptr);
 meepo_status dedup_reduce(meepo_table* t, SegWork& w, const void* grads, uint64_t n, const DedupOut& o,
                           cudaStream_t stream);
 meepo_status dedup_run(meepo_table* t, const uint64_t* keys, const void* grads, uint64_t n, const DedupOut& o,

@@ -146,6 +146,31 @@ def test_peer_single_process(oracle_lib, cuda_lib, world, dtype, dim, optimizer,
             np.testing.assert_array_equal(lst[r].cpu().numpy(), ost[700 * r:700 * (r + 1)])
             np.testing.assert_array_equal(_np_rows(lrows[r], dtype), orows[700 * r:700 * (r + 1)])
 
+        # The apply above ran right after find_or_insert on the same batch: it reused the forward pass (dedup,
+        # positions, slots). Now the other paths. Step-dependent:
+        #   even steps: a backward pass over a DIFFERENT batch than the last forward verb (full path);
+        #   odd steps:  the batch of the last forward verb (the lookup), but every table is touched by a local
+        #               verb in between, so the owners must probe instead of trusting the remembered slots.
+        if step % 2 == 0:
+            keys2 = [np.roll(k, 1) for k in per_keys]
+        else:
+            keys2 = lk
+            absent = keygen.keys_from_ranks(np.arange(10**9, 10**9 + 50 * world, dtype=np.uint64), 99)
+            das = [put(absent[50 * r:50 * (r + 1)].view(np.int64), r) for r in range(world)]
+            sync()
+            for r in range(world):  # a local verb on every rank: bumps the slot generation (and the epoch, in step)
+                tables[r].lookup(das[r], stream=streams[r].cuda_stream)
+            ref.lookup(absent)      # keeps epoch and miss counters comparable
+        grads2 = [grads_for(dtype, rng.normal(0, 0.1, size=(k.size, dim))) for k in keys2]
+        dk2 = [put(k.view(np.int64), r) for r, k in enumerate(keys2)]
+        dg2 = [put(g.view(np.int16) if dtype == "bf16" else g, r, tdt if dtype == "bf16" else None)
+               for r, g in enumerate(grads2)]
+        sync()
+        for r in range(world):
+            tables[r].sharded_apply_gradients(dk2[r], dg2[r], n=keys2[r].size, stream=streams[r].cuda_stream)
+        sync()
+        _oracle_backward(ref, keys2, grads2, dim, rdt)
+
     # union of the shards == the single oracle table; every key sits on its owner; stats add up
     rk, rr, rs, rsc, rstep = export_sorted(ref)
     parts = [_gpu_export(t, f"cuda:{devs[r]}") for r, t in enumerate(tables)]
