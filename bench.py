@@ -431,6 +431,19 @@ def main():
                 "algorithmic_bytes_per_launch": alg[top],
                 "step_achieved_gbs": alg["step"] / (ms_step * 1e-3) / 1e9,
                 "step_frac": alg["step"] / (ms_step * 1e-3) / 1e9 / peak}
+    nvlink = None
+    if world > 1 and args.exchange == "peer":
+        # the two NVLink-bound kernels store (world-1)/world of their rows into peers' windows
+        out = {}
+        for name, rows_per_launch in (("sharded.owner_find_or_insert", kr), ("dedup.reduce_store", gr)):
+            if name in kernels:
+                b = rows_per_launch * (world - 1) / world * (R + 8)
+                out[name] = {"bytes_out_per_launch": b, "achieved_gbs": b / (kernels[name]["avg_ms"] * 1e-3) / 1e9}
+        if out:
+            topn = max(out, key=lambda k: kernels[k]["avg_ms"])
+            nvlink = {"kernel": topn, "achieved": out[topn]["achieved_gbs"], "peak": 770.0, "unit": "GB/s per direction",
+                      "frac": out[topn]["achieved_gbs"] / 770.0, "kernels": out,
+                      "peak_source": "measured peer copy per direction (B200_PROFILING.md); 900 nominal"}
     own_launches = 0
     for name, k in kernels.items():
         if "(cub)" in name:
@@ -517,7 +530,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": w["dtype"], "data": "synthetic", "config": config,
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": own_launches,
+                "roofline": roofline, "nvlink": nvlink, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": own_launches,
                 "clocks": clk, "kernels": kernels,
                 "evict": ({"calls_in_timed_region": len([e for e in evict_log if e[0] >= args.warmup]),
                            "keys_evicted": [e[1] for e in evict_log if e[0] >= args.warmup],

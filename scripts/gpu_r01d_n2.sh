@@ -12,6 +12,6 @@ run() { # name, extra args
   python scripts/show_bench.py gpurun_out/d_$name.json 2>&1 | head -30
 }
 run n2_cfg3_peer
-# run n2_cfg3_nccl --exchange nccl
+run n2_cfg3_nccl --exchange nccl
 run n2_cfg4_peer --workload cfg4
 run n2_cfg3_zipf_peer --dist zipf
