@@ -602,7 +602,7 @@ static meepo_status sharded_apply(meepo_table* t, const uint64_t* keys, const vo
                                                 entry_valid);
     MEEPO_CUDA_TRY(cudaGetLastError());
   }
-  static const char* const names[5] = {"sharded.owner_sort(cub)", "sharded.owner_segments(3 kernels)",
+  static const char* const names[5] = {"sharded.owner_sort", "sharded.owner_segments(3 kernels)",
                                        "sharded.owner_apply", "sharded.owner_long_leaves", "sharded.owner_long_finish"};
   MEEPO_TRY(run_segmented(t, ow, t->v.slots, p->ps.w[p->rank].recv_grads, t->v.opt, nullptr, stream, nullptr, names));
   return barrier(t, nullptr, false, stream);

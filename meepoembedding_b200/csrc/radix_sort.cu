@@ -1,0 +1,285 @@
+// radix_sort.cu — stable LSD radix sort of (u32 key, u32 value) pairs on the low `end_bit` bits of the
+// key: the grouping step of apply_gradients (key = slot, value = batch index), of the sender-side
+// pre-reduction (key = unique id) and of the owner side of the sharded backward pass.
+//
+// 8-bit digits, one scatter pass per digit, "onesweep" shape: ONE histogram kernel counts every
+// digit of every pass up front, a tiny kernel turns the counts into per-pass bin bases, and each
+// pass is a single kernel whose tiles (4096 pairs, taken in order from a device counter) learn their
+// offset inside every bin from the tiles before them by decoupled look-back over a (tile, bin)
+// array of flagged counts — no per-pass histogram / scan launches and no second read of the keys.
+//   per tile: warp-striped 16 keys per thread; stable rank of every key among the tile's keys with
+//   the same digit by warp match (__match_any_sync) + per-warp digit counters in shared memory;
+//   the tile is reordered by digit through shared memory so that every digit's run is stored to
+//   global memory as one contiguous, coalesced piece.
+// Arrays of a few million pairs stay in the 126 MB L2 between passes. The spin of the look-back is
+// bounded: a tile that never shows up raises a flag (and the sort result is wrong) instead of hanging.
+#include "table.h"
+
+namespace meepo {
+
+namespace {
+constexpr int kRsThreads = 256;
+constexpr int kRsItems = 16;
+constexpr int kRsTile = kRsThreads * kRsItems;  // 4096 pairs
+constexpr int kRsWarps = kRsThreads / 32;
+constexpr uint32_t kFlagPartial = 1u << 30, kFlagInclusive = 2u << 30, kFlagMask = 3u << 30, kCountMask = ~kFlagMask;
+
+struct RsTemp {
+  uint32_t* hist;      // [passes][256] digit counts, then (in place) exclusive bin bases
+  uint32_t* counters;  // [passes] next tile to hand out
+  uint32_t* lookback;  // [passes][tiles][256]
+  uint32_t* k_tmp;     // [n]
+  uint32_t* v_tmp;     // [n]
+};
+
+__global__ void __launch_bounds__(256) rs_hist_kernel(const uint32_t* __restrict__ keys, uint32_t n, int passes,
+                                                      int end_bit, uint32_t* __restrict__ hist) {
+  __shared__ uint32_t sh[4][256];
+  for (int p = 0; p < passes; p++) sh[p][threadIdx.x] = 0;
+  __syncthreads();
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t k = __ldg(keys + i);
+#pragma unroll
+    for (int p = 0; p < 4; p++) {
+      if (p >= passes) break;
+      const int bits = min(8, end_bit - 8 * p);
+      atomicAdd(&sh[p][(k >> (8 * p)) & ((1u << bits) - 1u)], 1u);
+    }
+  }
+  __syncthreads();
+  for (int p = 0; p < passes; p++)
+    if (sh[p][threadIdx.x]) atomicAdd(hist + p * 256 + threadIdx.x, sh[p][threadIdx.x]);
+}
+
+// counts -> exclusive bin bases, in place; one warp-shuffle scan per pass
+__global__ void __launch_bounds__(256) rs_scan_kernel(uint32_t* __restrict__ hist, int passes) {
+  __shared__ uint32_t warp_tot[8];
+  const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+  for (int p = 0; p < passes; p++) {
+    const uint32_t v = hist[p * 256 + threadIdx.x];
+    uint32_t x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+      if (lane >= (uint32_t)d) x += y;
+    }
+    if (lane == 31) warp_tot[w] = x;
+    __syncthreads();
+    uint32_t before = 0;
+    for (uint32_t j = 0; j < w; j++) before += warp_tot[j];
+    hist[p * 256 + threadIdx.x] = before + x - v;
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(kRsThreads) rs_onesweep_kernel(const uint32_t* __restrict__ k_in,
+                                                                 const uint32_t* __restrict__ v_in,
+                                                                 uint32_t* __restrict__ k_out,
+                                                                 uint32_t* __restrict__ v_out, uint32_t n, int shift,
+                                                                 int bits, const uint32_t* __restrict__ bin_base,
+                                                                 uint32_t* __restrict__ tile_counter,
+                                                                 uint32_t* __restrict__ lookback,
+                                                                 uint32_t* __restrict__ error) {
+  __shared__ uint32_t s_keys[kRsTile];
+  __shared__ uint32_t s_vals[kRsTile];
+  __shared__ uint32_t s_cnt[kRsWarps][256];  // per-warp digit counts, then exclusive offsets over the warps
+  __shared__ uint32_t s_bin_start[256];      // start of every digit's run in the reordered tile
+  __shared__ uint32_t s_global[256];         // global index of the first key of every digit's run
+  __shared__ uint32_t s_warp_tot[kRsWarps];
+  __shared__ uint32_t s_tile;
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
+  const uint32_t dmask = (1u << bits) - 1u;
+  if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
+#pragma unroll
+  for (int j = 0; j < kRsWarps; j++) s_cnt[j][tid] = 0;
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const uint32_t base = tile * kRsTile;
+  const uint32_t valid = min((uint32_t)kRsTile, n - base);
+
+  // 1. load (warp-striped: element e = w*512 + k*32 + lane) and rank within the warp
+  uint32_t key[kRsItems], val[kRsItems], rank[kRsItems];
+#pragma unroll
+  for (int k = 0; k < kRsItems; k++) {
+    const uint32_t e = w * (kRsItems * 32) + k * 32 + lane;
+    key[k] = e < valid ? __ldg(k_in + base + e) : 0xFFFFFFFFu;
+    val[k] = e < valid ? __ldg(v_in + base + e) : 0u;
+  }
+#pragma unroll
+  for (int k = 0; k < kRsItems; k++) {
+    const uint32_t e = w * (kRsItems * 32) + k * 32 + lane;
+    const bool ok = e < valid;
+    const uint32_t d = ok ? (key[k] >> shift) & dmask : 256u + lane;  // padding matches nothing
+    const unsigned peers = __match_any_sync(0xFFFFFFFFu, d);
+    const int leader = __ffs(peers) - 1;
+    uint32_t before = 0;
+    if (ok && (int)lane == leader) {
+      before = s_cnt[w][d];
+      s_cnt[w][d] = before + __popc(peers);
+    }
+    before = __shfl_sync(0xFFFFFFFFu, before, leader);
+    rank[k] = before + __popc(peers & ((1u << lane) - 1u));  // among this warp's earlier keys with digit d
+    __syncwarp();
+  }
+  __syncthreads();
+
+  // 2. thread d: exclusive offsets of digit d over the warps, tile count of digit d
+  uint32_t tile_cnt = 0;
+#pragma unroll
+  for (int j = 0; j < kRsWarps; j++) {
+    const uint32_t c = s_cnt[j][tid];
+    s_cnt[j][tid] = tile_cnt;
+    tile_cnt += c;
+  }
+  // 3. publish the tile's count of digit d, then look back for the tiles before it
+  uint32_t* lb = lookback + (size_t)tile * 256 + tid;
+  if (tile == 0) {
+    st_volatile_u32(lb, tile_cnt | kFlagInclusive);
+  } else {
+    st_volatile_u32(lb, tile_cnt | kFlagPartial);
+  }
+  uint32_t excl = 0;
+  if (tile > 0) {
+    for (uint32_t prev = tile; prev-- > 0;) {
+      const uint32_t* q = lookback + (size_t)prev * 256 + tid;
+      uint32_t v = ld_volatile_u32(q);
+      for (uint32_t spin = 0; (v & kFlagMask) == 0; spin++) {
+        if (spin > (1u << 24)) {  // a tile that never shows up: give up rather than hang
+          atomicExch(error, 1u);
+          v = kFlagInclusive;
+          break;
+        }
+        __nanosleep(32);
+        v = ld_volatile_u32(q);
+      }
+      excl += v & kCountMask;
+      if (v & kFlagInclusive) break;
+    }
+    st_volatile_u32(lb, (excl + tile_cnt) | kFlagInclusive);
+  }
+  s_global[tid] = __ldg(bin_base + tid) + excl;
+  // 4. exclusive scan of the tile counts over the digits -> start of every run in the reordered tile
+  {
+    uint32_t x = tile_cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+      if (lane >= (uint32_t)d) x += y;
+    }
+    if (lane == 31) s_warp_tot[w] = x;
+    __syncthreads();
+    uint32_t before = 0;
+    for (uint32_t j = 0; j < w; j++) before += s_warp_tot[j];
+    s_bin_start[tid] = before + x - tile_cnt;
+  }
+  __syncthreads();
+
+  // 5. reorder by digit through shared memory (stable: digit run, then warp, then rank within the warp)
+#pragma unroll
+  for (int k = 0; k < kRsItems; k++) {
+    const uint32_t e = w * (kRsItems * 32) + k * 32 + lane;
+    if (e < valid) {
+      const uint32_t d = (key[k] >> shift) & dmask;
+      const uint32_t pos = s_bin_start[d] + s_cnt[w][d] + rank[k];
+      s_keys[pos] = key[k];
+      s_vals[pos] = val[k];
+    }
+  }
+  __syncthreads();
+  // 6. every digit's run goes out as one contiguous piece
+  for (uint32_t j = tid; j < valid; j += kRsThreads) {
+    const uint32_t k = s_keys[j];
+    const uint32_t d = (k >> shift) & dmask;
+    const uint32_t dst = s_global[d] + (j - s_bin_start[d]);
+    k_out[dst] = k;
+    v_out[dst] = s_vals[j];
+  }
+}
+
+RsTemp carve(char* temp, uint64_t n, int passes) {
+  const uint64_t tiles = (n + kRsTile - 1) / kRsTile;
+  RsTemp r;
+  size_t off = 0;
+  r.hist = reinterpret_cast<uint32_t*>(temp + off);
+  off += Workspace::pad(4 * 256 * 4);
+  r.counters = reinterpret_cast<uint32_t*>(temp + off);
+  off += Workspace::pad(8 * 4);
+  r.lookback = reinterpret_cast<uint32_t*>(temp + off);
+  off += Workspace::pad((size_t)passes * tiles * 256 * 4);
+  r.k_tmp = reinterpret_cast<uint32_t*>(temp + off);
+  off += Workspace::pad(n * 4);
+  r.v_tmp = reinterpret_cast<uint32_t*>(temp + off);
+  return r;
+}
+}  // namespace
+
+bool radix_sort_supported(uint64_t n, int end_bit) {
+  static const bool use_cub = getenv("MEEPO_SORT_CUB") != nullptr;
+  return !use_cub && n > 0 && n < (1ull << 30) && end_bit >= 1 && end_bit <= 32;
+}
+
+size_t radix_sort_temp_bytes(uint64_t n, int end_bit) {
+  const int passes = (end_bit + 7) / 8;
+  const uint64_t tiles = (n + kRsTile - 1) / kRsTile;
+  return Workspace::pad(4 * 256 * 4) + Workspace::pad(8 * 4) + Workspace::pad((size_t)passes * tiles * 256 * 4) +
+         2 * Workspace::pad(n * 4) + 256;
+}
+
+// (k_in, v_in) -> (k_out, v_out), stable, on key bits [0, end_bit). temp: radix_sort_temp_bytes(), 256-byte aligned.
+meepo_status radix_sort_pairs(meepo_table* t, char* temp, const uint32_t* k_in, uint32_t* k_out,
+                              const uint32_t* v_in, uint32_t* v_out, uint32_t n, int end_bit, cudaStream_t stream) {
+  const int passes = (end_bit + 7) / 8;
+  const uint32_t tiles = (n + kRsTile - 1) / kRsTile;
+  RsTemp r = carve(temp, n, passes);
+  // histogram + counters + look-back state are one contiguous zero-filled block
+  MEEPO_CUDA_TRY(cudaMemsetAsync(r.hist, 0, (char*)r.k_tmp - (char*)r.hist, stream));
+  const int hgrid = (int)std::max<uint64_t>(1, std::min<uint64_t>(((uint64_t)n + 255) / 256, (uint64_t)t->num_sms * 8));
+  rs_hist_kernel<<<hgrid, 256, 0, stream>>>(k_in, n, passes, end_bit, r.hist);
+  rs_scan_kernel<<<1, 256, 0, stream>>>(r.hist, passes);
+  // ping-pong so that the last pass lands in the caller's output arrays
+  const uint32_t* src_k = k_in;
+  const uint32_t* src_v = v_in;
+  for (int p = 0; p < passes; p++) {
+    const bool to_out = ((passes - 1 - p) % 2) == 0;
+    uint32_t* dst_k = to_out ? k_out : r.k_tmp;
+    uint32_t* dst_v = to_out ? v_out : r.v_tmp;
+    const int bits = std::min(8, end_bit - 8 * p);
+    rs_onesweep_kernel<<<tiles, kRsThreads, 0, stream>>>(src_k, src_v, dst_k, dst_v, n, 8 * p, bits, r.hist + p * 256,
+                                                         r.counters + p, r.lookback + (size_t)p * tiles * 256,
+                                                         &t->dstate->pad[0]);
+    src_k = dst_k;
+    src_v = dst_v;
+  }
+  MEEPO_CUDA_TRY(cudaGetLastError());
+  return MEEPO_OK;
+}
+
+}  // namespace meepo
+
+using namespace meepo;
+
+// Test hook (not part of include/meepo.h): sort device arrays, report the look-back error flag.
+extern "C" MEEPO_API meepo_status meepo_internal_sort_pairs(meepo_table* t, const uint32_t* k_in, uint32_t* k_out,
+                                                            const uint32_t* v_in, uint32_t* v_out, uint64_t n,
+                                                            int32_t end_bit, void* stream_) {
+  if (!t || !radix_sort_supported(n, end_bit)) return fail(MEEPO_EINVAL, "unsupported sort size / bit count");
+  DeviceGuard guard(t->device);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MEEPO_TRY(t->ws.reserve(radix_sort_temp_bytes(n, end_bit), stream));
+  char* temp = t->ws.take<char>(radix_sort_temp_bytes(n, end_bit));
+  MEEPO_TRY(radix_sort_pairs(t, temp, k_in, k_out, v_in, v_out, (uint32_t)n, end_bit, stream));
+  uint32_t err = 0;
+  MEEPO_CUDA_TRY(cudaStreamSynchronize(stream));
+  MEEPO_CUDA_TRY(cudaMemcpy(&err, &t->dstate->pad[0], 4, cudaMemcpyDeviceToHost));
+  if (err) return fail(MEEPO_ECUDA, "radix sort: look-back gave up waiting for a tile");
+  return MEEPO_OK;
+}

@@ -299,7 +299,7 @@ meepo_status dedup_hash(meepo_table* t, const uint64_t* keys, uint64_t n, const 
 meepo_status dedup_reduce(meepo_table* t, SegWork& w, const void* grads, uint64_t n, const DedupOut& o,
                           cudaStream_t stream) {
   if (n == 0) return MEEPO_OK;
-  static const char* const names[5] = {"dedup.radix_sort(cub)", "dedup.segments(3 kernels)", "dedup.reduce_store",
+  static const char* const names[5] = {"dedup.radix_sort", "dedup.segments(3 kernels)", "dedup.reduce_store",
                                        "dedup.long_leaves", "dedup.long_finish"};
   return run_segmented(t, w, (uint32_t)n, grads, kReduceStoreOnly, o.grads_out, stream, nullptr, names, o.grad_rows);
 }

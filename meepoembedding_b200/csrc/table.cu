@@ -187,6 +187,9 @@ MEEPO_API meepo_status meepo_stats(meepo_table* t, meepo_stats_t* out) {
   out->epoch = t->epoch;
   out->row_bytes = t->row_bytes;
   out->state_bytes = t->state_bytes;
+  uint32_t sort_err = 0;
+  MEEPO_CUDA_TRY(cudaMemcpy(&sort_err, &t->dstate->pad[0], 4, cudaMemcpyDeviceToHost));
+  if (sort_err) return fail(MEEPO_ECUDA, "radix sort: look-back gave up waiting for a tile; results are wrong");
   return peer_error_check(t);
 }
 

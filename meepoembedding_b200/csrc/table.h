@@ -50,7 +50,7 @@ struct DeviceState {
   uint32_t num_segments;   // apply_gradients scratch
   uint32_t num_long, num_leaves;
   uint32_t evict_count;
-  uint32_t pad[2];
+  uint32_t pad[2];         // pad[0]: sticky "radix sort gave up waiting for a tile" flag
   unsigned long long scratch64[8];
   unsigned long long hist[256];  // evict: radix-select histogram
 };
@@ -231,6 +231,11 @@ struct SegWork {
 };
 constexpr int kReduceStoreOnly = 3;
 int bits_for(uint32_t max_value);
+// radix_sort.cu: stable LSD sort of (u32 key, u32 value) pairs on key bits [0, end_bit)
+bool radix_sort_supported(uint64_t n, int end_bit);
+size_t radix_sort_temp_bytes(uint64_t n, int end_bit);
+meepo_status radix_sort_pairs(meepo_table* t, char* temp, const uint32_t* k_in, uint32_t* k_out, const uint32_t* v_in,
+                              uint32_t* v_out, uint32_t n, int end_bit, cudaStream_t stream);
 meepo_status run_segmented(meepo_table* t, SegWork& w, uint32_t limit, const void* grads, int mode,
                            void* reduce_out, cudaStream_t stream, cudaEvent_t grads_ready,
                            const char* const* names, void* const* reduce_rows = nullptr);

@@ -11,6 +11,8 @@
 // run in parallel (leaf_kernel) and are finished by long_finish_kernel.
 #include <cub/device/device_radix_sort.cuh>
 
+#include <map>
+
 #include "optimizer.cuh"
 #include "table.h"
 
@@ -542,6 +544,7 @@ size_t SegWork::bytes(uint64_t n, uint32_t dim, int end_bit_) {
   size_t cub = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, cub, (const uint32_t*)nullptr, (uint32_t*)nullptr,
                                   (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n, 0, end_bit_);
+  if (radix_sort_supported(n, end_bit_)) cub = std::max(cub, radix_sort_temp_bytes(n, end_bit_));
   const size_t ntiles_ = (n + kSegTile - 1) / kSegTile;
   const size_t max_long_ = n / (kLongSeg + 1) + 1, max_leaves_ = n / kLongSeg + 2;
   return 4 * Workspace::pad(n * 4) + Workspace::pad(cub) + 2 * Workspace::pad(ntiles_ * 4) +
@@ -555,6 +558,7 @@ void SegWork::take(Workspace& ws, uint64_t n_, uint32_t dim, int end_bit_) {
   cub_bytes = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
                                   (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n, 0, end_bit);
+  if (radix_sort_supported(n_, end_bit)) cub_bytes = std::max(cub_bytes, radix_sort_temp_bytes(n_, end_bit));
   ntiles = (n + kSegTile - 1) / kSegTile;
   max_long = n_ / (kLongSeg + 1) + 1;
   max_leaves = n_ / kLongSeg + 2;
@@ -572,6 +576,15 @@ void SegWork::take(Workspace& ws, uint64_t n_, uint32_t dim, int end_bit_) {
   partial = ws.take<float>(max_leaves * dim);
 }
 
+// "<prefix>(N kernels)" for the hand-written sort (histogram + scan + one kernel per digit), "<prefix>(cub)" else;
+// the strings live for the life of the process (the profiler keeps the pointers).
+static const char* sort_scope_name(const char* prefix, int kernels) {
+  static std::map<std::pair<const char*, int>, std::string> names;
+  auto& s = names[{prefix, kernels}];
+  if (s.empty()) s = std::string(prefix) + (kernels ? "(" + std::to_string(kernels) + " kernels)" : "(cub)");
+  return s.c_str();
+}
+
 int bits_for(uint32_t max_value) {
   int b = 1;
   while (b < 32 && (max_value >> b)) b++;
@@ -586,8 +599,11 @@ meepo_status run_segmented(meepo_table* t, SegWork& w, uint32_t limit, const voi
                            const char* const* names, void* const* reduce_rows) {
   const uint32_t n32 = w.n;
   {
-    ProfScope ps(t, names[0], stream);
-    MEEPO_CUDA_TRY(cub::DeviceRadixSort::SortPairs(w.cub_tmp, w.cub_bytes, (const uint32_t*)w.sk_in, w.sk_out,
+    ProfScope ps(t, sort_scope_name(names[0], radix_sort_supported(n32, w.end_bit) ? (w.end_bit + 7) / 8 + 2 : 0), stream);
+    if (radix_sort_supported(n32, w.end_bit))  // hand-written onesweep (radix_sort.cu); CUB only beyond 2^30 pairs
+      MEEPO_TRY(radix_sort_pairs(t, w.cub_tmp, w.sk_in, w.sk_out, w.sv_in, w.sv_out, n32, w.end_bit, stream));
+    else
+      MEEPO_CUDA_TRY(cub::DeviceRadixSort::SortPairs(w.cub_tmp, w.cub_bytes, (const uint32_t*)w.sk_in, w.sk_out,
                                                    (const uint32_t*)w.sv_in, w.sv_out, (int)n32, 0, w.end_bit,
                                                    stream));
   }
@@ -668,7 +684,7 @@ meepo_status launch_apply_gradients(meepo_table* t, const uint64_t* keys, const 
     grad_slots_kernel<<<grid, 256, 0, stream>>>(t->v, keys, (uint32_t)n, w.sk_in, w.sv_in, t->cache, cache_n);
     MEEPO_CUDA_TRY(cudaGetLastError());
   }
-  static const char* const names[5] = {"apply.radix_sort(cub)", "apply.segments(3 kernels)",
+  static const char* const names[5] = {"apply.radix_sort", "apply.segments(3 kernels)",
                                        "apply.reduce_optimizer", "apply.long_leaves", "apply.long_finish"};
   return run_segmented(t, w, t->v.slots, grads, t->v.opt, nullptr, stream, grads_ready, names);
 }
