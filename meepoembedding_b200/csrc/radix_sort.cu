@@ -8,7 +8,7 @@
 // offset inside every bin from the tiles before them by decoupled look-back over a (tile, bin)
 // array of flagged counts — no per-pass histogram / scan launches and no second read of the keys.
 //   per tile: warp-striped 16 keys per thread; stable rank of every key among the tile's keys with
-//   the same digit by warp match (__match_any_sync) + per-warp digit counters in shared memory;
+//   the same digit by warp match (one ballot per digit bit) + per-warp digit counters in shared memory;
 //   the tile is reordered by digit through shared memory so that every digit's run is stored to
 //   global memory as one contiguous, coalesced piece.
 // Arrays of a few million pairs stay in the 126 MB L2 between passes. The spin of the look-back is
@@ -26,37 +26,52 @@ constexpr uint32_t kFlagPartial = 1u << 30, kFlagInclusive = 2u << 30, kFlagMask
 
 struct RsTemp {
   uint32_t* hist;      // [passes][256] digit counts, then (in place) exclusive bin bases
-  uint32_t* counters;  // [passes] next tile to hand out
+  uint32_t* counters;  // [passes] next tile to hand out; [4] blocks of the histogram kernel that are done
   uint32_t* lookback;  // [passes][tiles][256]
   uint32_t* k_tmp;     // [n]
   uint32_t* v_tmp;     // [n]
 };
 
+// Digit counts of every pass in one read of the keys (16-byte loads). The last block to finish turns
+// the counts into exclusive bin bases in place, which saves a launch.
 __global__ void __launch_bounds__(256) rs_hist_kernel(const uint32_t* __restrict__ keys, uint32_t n, int passes,
-                                                      int end_bit, uint32_t* __restrict__ hist) {
+                                                      int end_bit, uint32_t* __restrict__ hist,
+                                                      uint32_t* __restrict__ blocks_done) {
   __shared__ uint32_t sh[4][256];
+  __shared__ uint32_t warp_tot[8];
+  __shared__ bool last;
   for (int p = 0; p < passes; p++) sh[p][threadIdx.x] = 0;
   __syncthreads();
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const uint32_t k = __ldg(keys + i);
+  uint32_t mask[4];
 #pragma unroll
-    for (int p = 0; p < 4; p++) {
-      if (p >= passes) break;
-      const int bits = min(8, end_bit - 8 * p);
-      atomicAdd(&sh[p][(k >> (8 * p)) & ((1u << bits) - 1u)], 1u);
-    }
+  for (int p = 0; p < 4; p++) mask[p] = p < passes ? (1u << min(8, end_bit - 8 * p)) - 1u : 0u;
+  auto count = [&](uint32_t k) {
+#pragma unroll
+    for (int p = 0; p < 4; p++)
+      if (p < passes) atomicAdd(&sh[p][(k >> (8 * p)) & mask[p]], 1u);
+  };
+  const uint32_t n4 = ((reinterpret_cast<uintptr_t>(keys) & 15u) == 0) ? n / 4 : 0;
+  const uint4* k4 = reinterpret_cast<const uint4*>(keys);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+    const uint4 v = __ldg(k4 + i);
+    count(v.x);
+    count(v.y);
+    count(v.z);
+    count(v.w);
   }
+  for (uint32_t i = n4 * 4 + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) count(__ldg(keys + i));
   __syncthreads();
   for (int p = 0; p < passes; p++)
     if (sh[p][threadIdx.x]) atomicAdd(hist + p * 256 + threadIdx.x, sh[p][threadIdx.x]);
-}
-
-// counts -> exclusive bin bases, in place; one warp-shuffle scan per pass
-__global__ void __launch_bounds__(256) rs_scan_kernel(uint32_t* __restrict__ hist, int passes) {
-  __shared__ uint32_t warp_tot[8];
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(blocks_done, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!last) return;
+  // counts -> exclusive bin bases, in place; one warp-shuffle scan per pass
   const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
   for (int p = 0; p < passes; p++) {
-    const uint32_t v = hist[p * 256 + threadIdx.x];
+    const uint32_t v = __ldcg(hist + p * 256 + threadIdx.x);
     uint32_t x = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -81,7 +96,7 @@ __device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
   asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-__global__ void __launch_bounds__(kRsThreads) rs_onesweep_kernel(const uint32_t* __restrict__ k_in,
+__global__ void __launch_bounds__(kRsThreads, 4) rs_onesweep_kernel(const uint32_t* __restrict__ k_in,
                                                                  const uint32_t* __restrict__ v_in,
                                                                  uint32_t* __restrict__ k_out,
                                                                  uint32_t* __restrict__ v_out, uint32_t n, int shift,
@@ -118,9 +133,18 @@ __global__ void __launch_bounds__(kRsThreads) rs_onesweep_kernel(const uint32_t*
   for (int k = 0; k < kRsItems; k++) {
     const uint32_t e = w * (kRsItems * 32) + k * 32 + lane;
     const bool ok = e < valid;
-    const uint32_t d = ok ? (key[k] >> shift) & dmask : 256u + lane;  // padding matches nothing
-    const unsigned peers = __match_any_sync(0xFFFFFFFFu, d);
-    const int leader = __ffs(peers) - 1;
+    const uint32_t d = ok ? (key[k] >> shift) & dmask : 0u;
+    // lanes holding the same digit, one ballot per digit bit: the hardware match (__match_any_sync) walks
+    // the distinct values of the warp one by one (~30 per instruction here) and bounded the whole kernel
+    unsigned peers = __ballot_sync(0xFFFFFFFFu, ok);  // padding matches nothing
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+      if (b < bits) {
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, (d >> b) & 1u);
+        peers &= ((d >> b) & 1u) ? m : ~m;
+      }
+    }
+    const int leader = ok ? __ffs(peers) - 1 : (int)lane;
     uint32_t before = 0;
     if (ok && (int)lane == leader) {
       before = s_cnt[w][d];
@@ -149,20 +173,34 @@ __global__ void __launch_bounds__(kRsThreads) rs_onesweep_kernel(const uint32_t*
   }
   uint32_t excl = 0;
   if (tile > 0) {
-    for (uint32_t prev = tile; prev-- > 0;) {
-      const uint32_t* q = lookback + (size_t)prev * 256 + tid;
-      uint32_t v = ld_volatile_u32(q);
-      for (uint32_t spin = 0; (v & kFlagMask) == 0; spin++) {
-        if (spin > (1u << 24)) {  // a tile that never shows up: give up rather than hang
-          atomicExch(error, 1u);
-          v = kFlagInclusive;
-          break;
+    // Walk back over the earlier tiles until one that already knows its inclusive prefix. The loads of a
+    // window of 8 predecessors are issued together: the walk is a chain of L2 round trips otherwise.
+    uint32_t prev = tile;  // tiles [0, prev) are still to be accounted for
+    bool done = false;
+    while (!done && prev > 0) {
+      constexpr uint32_t W = 8;
+      uint32_t v[W];
+#pragma unroll
+      for (uint32_t u = 0; u < W; u++)
+        v[u] = u < prev ? ld_volatile_u32(lookback + (size_t)(prev - 1 - u) * 256 + tid) : kFlagInclusive;
+#pragma unroll
+      for (uint32_t u = 0; u < W; u++) {
+        if (done || u >= prev) continue;
+        uint32_t x = v[u];
+        const uint32_t* q = lookback + (size_t)(prev - 1 - u) * 256 + tid;
+        for (uint32_t spin = 0; (x & kFlagMask) == 0; spin++) {
+          if (spin > (1u << 24)) {  // a tile that never shows up: give up rather than hang
+            atomicExch(error, 1u);
+            x = kFlagInclusive;
+            break;
+          }
+          __nanosleep(32);
+          x = ld_volatile_u32(q);
         }
-        __nanosleep(32);
-        v = ld_volatile_u32(q);
+        excl += x & kCountMask;
+        done = (x & kFlagInclusive) != 0;
       }
-      excl += v & kCountMask;
-      if (v & kFlagInclusive) break;
+      prev -= min(prev, W);
     }
     st_volatile_u32(lb, (excl + tile_cnt) | kFlagInclusive);
   }
@@ -242,9 +280,8 @@ meepo_status radix_sort_pairs(meepo_table* t, char* temp, const uint32_t* k_in, 
   RsTemp r = carve(temp, n, passes);
   // histogram + counters + look-back state are one contiguous zero-filled block
   MEEPO_CUDA_TRY(cudaMemsetAsync(r.hist, 0, (char*)r.k_tmp - (char*)r.hist, stream));
-  const int hgrid = (int)std::max<uint64_t>(1, std::min<uint64_t>(((uint64_t)n + 255) / 256, (uint64_t)t->num_sms * 8));
-  rs_hist_kernel<<<hgrid, 256, 0, stream>>>(k_in, n, passes, end_bit, r.hist);
-  rs_scan_kernel<<<1, 256, 0, stream>>>(r.hist, passes);
+  const int hgrid = (int)std::max<uint64_t>(1, std::min<uint64_t>(((uint64_t)n + 1023) / 1024, (uint64_t)t->num_sms * 4));
+  rs_hist_kernel<<<hgrid, 256, 0, stream>>>(k_in, n, passes, end_bit, r.hist, r.counters + 4);
   // ping-pong so that the last pass lands in the caller's output arrays
   const uint32_t* src_k = k_in;
   const uint32_t* src_v = v_in;

@@ -576,7 +576,7 @@ void SegWork::take(Workspace& ws, uint64_t n_, uint32_t dim, int end_bit_) {
   partial = ws.take<float>(max_leaves * dim);
 }
 
-// "<prefix>(N kernels)" for the hand-written sort (histogram + scan + one kernel per digit), "<prefix>(cub)" else;
+// "<prefix>(N kernels)" for the hand-written sort (histogram/scan + one kernel per digit), "<prefix>(cub)" else;
 // the strings live for the life of the process (the profiler keeps the pointers).
 static const char* sort_scope_name(const char* prefix, int kernels) {
   static std::map<std::pair<const char*, int>, std::string> names;
@@ -599,7 +599,7 @@ meepo_status run_segmented(meepo_table* t, SegWork& w, uint32_t limit, const voi
                            const char* const* names, void* const* reduce_rows) {
   const uint32_t n32 = w.n;
   {
-    ProfScope ps(t, sort_scope_name(names[0], radix_sort_supported(n32, w.end_bit) ? (w.end_bit + 7) / 8 + 2 : 0), stream);
+    ProfScope ps(t, sort_scope_name(names[0], radix_sort_supported(n32, w.end_bit) ? (w.end_bit + 7) / 8 + 1 : 0), stream);
     if (radix_sort_supported(n32, w.end_bit))  // hand-written onesweep (radix_sort.cu); CUB only beyond 2^30 pairs
       MEEPO_TRY(radix_sort_pairs(t, w.cub_tmp, w.sk_in, w.sk_out, w.sv_in, w.sv_out, n32, w.end_bit, stream));
     else
