@@ -37,7 +37,6 @@
 
 #include <cstring>
 
-#include "optimizer.cuh"
 #include "probe_gather.cuh"
 
 namespace meepo {

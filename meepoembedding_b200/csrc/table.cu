@@ -69,10 +69,6 @@ MEEPO_API meepo_status meepo_create(const meepo_config* cfg, meepo_table** out) 
   DeviceGuard guard(cfg->device);
   if (!guard.ok) return fail(MEEPO_ECUDA, "cudaSetDevice failed");
 
-  if (const char* g = getenv("MEEPO_L2_FETCH_GRANULARITY")) {  // experiment knob: 32 / 64 / 128
-    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
-    cudaGetLastError();
-  }
   meepo_table* t = new meepo_table();
   t->cfg = *cfg;
   t->cache_enabled = getenv("MEEPO_NO_SLOT_CACHE") == nullptr;

@@ -634,7 +634,7 @@ meepo_status run_segmented(meepo_table* t, SegWork& w, uint32_t limit, const voi
 
   const bool bf16 = t->v.dtype == MEEPO_BF16;
   const void *k_apply = nullptr, *k_finish = nullptr;
-  const bool pipelined = gl == t->v.cpr && !getenv("MEEPO_APPLY_PLAIN");
+  const bool pipelined = gl == t->v.cpr;  // one 16-byte chunk per lane: rows of <= 512 B with a power-of-two chunk count
   if (bf16)
     pick_apply<true>(mode, pipelined, k_apply, k_finish);
   else
