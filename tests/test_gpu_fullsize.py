@@ -53,7 +53,7 @@ def test_full_batch_parity_vs_oracle(oracle_lib, cuda_lib, dtype):
     grads = grads_for(dtype, rng.standard_normal((n, dim), dtype=np.float32) * np.float32(0.01))
     gpu_apply(g, keys, grads, dtype)
     o.apply_gradients(keys, grads)
-    probe = keys[:: 64]
+    probe = np.ascontiguousarray(keys[:: 64])
     rows, st = gpu_foi(g, probe, dtype, insert=False)
     orows, ost = o.lookup(probe)
     np.testing.assert_array_equal(st, ost)
