@@ -481,8 +481,10 @@ def main():
         d2h = (2 if second_lookup else 1) * (B * R + B)
         e2e = {"value": B * ne / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "steps": ne, "ms_per_step": dt / ne * 1e3,
-               "what": "meepo_find_or_insert_host + meepo_apply_gradients_host: keys and gradients from pinned "
-                       "host memory, rows and status back to pinned host memory, wall clock"}
+               "what": ("meepo_find_or_insert_host + meepo_lookup_host: keys from pinned host memory, rows and status "
+                        "back to pinned host memory twice, wall clock" if second_lookup else
+                        "meepo_find_or_insert_host + meepo_apply_gradients_host: keys and gradients from pinned "
+                        "host memory, rows and status back to pinned host memory, wall clock")}
         del hg, hrows
 
     if not args.no_e2e and sharded_mode:
