@@ -331,20 +331,40 @@ MEEPO_API meepo_status meepo_evict(meepo_table* t, int32_t policy, double target
       t->spill_free.clear();
       for (uint64_t i = t->spill_cap_tuples; i-- > 0;) t->spill_free.push_back((uint32_t)i);
     }
-    const auto h0 = std::chrono::steady_clock::now();
-    t->spill_index.reserve(std::min<uint64_t>(t->spill_index.size() + m, t->spill_cap_tuples));
-    for (uint64_t j = 0; j < m; j++) {  // the index is far larger than the host caches: fetch ahead
-      if (j + 16 < m) t->spill_index.prefetch(hk[j + 16]);
-      hs[j] = spill_push(t, hk[j]);
-    }
-    prof_add_host(t, "evict.host_index(wall)",
-                  std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count());
-    MEEPO_CUDA_TRY(cudaMemcpyAsync(vslab, hs.data(), m * 4, cudaMemcpyHostToDevice, stream));
     const int wgrid = (int)std::max<uint64_t>(1, std::min<uint64_t>((m + 7) / 8, (uint64_t)t->num_sms * 4));
+    t->spill_index.reserve(std::min<uint64_t>(t->spill_index.size() + m, t->spill_cap_tuples));
+    const bool roomy = t->spill_free.size() >= m;  // no tuple has to be pushed out to make room
+    auto h0 = std::chrono::steady_clock::now();
+    if (roomy) {
+      // Slabs first (pops only), so that the PCIe copy can start; the index is filed underneath it. A key that
+      // already has an older copy gets a fresh slab and the old one goes back to the free list afterwards —
+      // which slab a tuple sits in is not observable, what the tier holds is the same as in the loop below.
+      for (uint64_t j = 0; j < m; j++) {
+        hs[j] = t->spill_free.back();
+        t->spill_free.pop_back();
+      }
+    } else {
+      for (uint64_t j = 0; j < m; j++) {  // the index is far larger than the host caches: fetch ahead
+        if (j + 16 < m) t->spill_index.prefetch(hk[j + 16]);
+        hs[j] = spill_push(t, hk[j]);
+      }
+    }
+    MEEPO_CUDA_TRY(cudaMemcpyAsync(vslab, hs.data(), m * 4, cudaMemcpyHostToDevice, stream));
     {
       ProfScope ps(t, "evict.spill_copy(pcie)", stream);
       spill_copy_kernel<<<wgrid, 256, 0, stream>>>(t->v, spill_view(t), vslot + (k - m), vslab, (uint32_t)m);
     }
+    if (roomy) {
+      for (uint64_t j = 0; j < m; j++) {
+        if (j + 16 < m) t->spill_index.prefetch(hk[j + 16]);
+        if (SpillTuple* old = t->spill_index.find(hk[j])) t->spill_free.push_back((uint32_t)old->ring_index);
+        const uint64_t seq = t->spill_seq++;
+        t->spill_index.put(hk[j], SpillTuple{seq, hs[j]});
+        t->spill_fifo.emplace_back(seq, hk[j]);
+      }
+    }
+    prof_add_host(t, roomy ? "evict.host_index(wall, under the spill copy)" : "evict.host_index(wall)",
+                  std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count());
     MEEPO_CUDA_TRY(cudaStreamSynchronize(stream));  // hs must outlive the copy
   }
   {
