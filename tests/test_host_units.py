@@ -12,3 +12,14 @@ def test_spill_index_against_unordered_map(tmp_path):
                            os.path.join(ROOT, "tests", "cpp", "spill_index_test.cc")])
     out = subprocess.check_output([str(exe)], text=True)
     assert "spill index ok" in out
+
+
+def test_header_is_valid_c_and_cxx(tmp_path):
+    """include/meepo.h is the drop-in boundary: it must compile as plain C99 and as C++ on its own."""
+    src_c = tmp_path / "use.c"
+    src_c.write_text('#include "meepo.h"\nint main(void) { meepo_config c; (void)c; return (int)meepo_owner(1u, 2u) * 0; }\n')
+    inc = os.path.join(ROOT, "include")
+    subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-I", inc, str(src_c)])
+    src_cc = tmp_path / "use.cc"
+    src_cc.write_text('#include "meepo.h"\nint main() { meepo_stats_t s{}; return (int)s.size; }\n')
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-I", inc, str(src_cc)])
