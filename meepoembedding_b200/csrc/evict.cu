@@ -10,6 +10,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include <chrono>
+#include <thread>
 #include <cmath>
 #include <cstring>
 
@@ -354,14 +355,17 @@ MEEPO_API meepo_status meepo_evict(meepo_table* t, int32_t policy, double target
       ProfScope ps(t, "evict.spill_copy(pcie)", stream);
       spill_copy_kernel<<<wgrid, 256, 0, stream>>>(t->v, spill_view(t), vslot + (k - m), vslab, (uint32_t)m);
     }
-    if (roomy) {
-      for (uint64_t j = 0; j < m; j++) {
-        if (j + 16 < m) t->spill_index.prefetch(hk[j + 16]);
-        if (SpillTuple* old = t->spill_index.find(hk[j])) t->spill_free.push_back((uint32_t)old->ring_index);
-        const uint64_t seq = t->spill_seq++;
-        t->spill_index.put(hk[j], SpillTuple{seq, hs[j]});
-        t->spill_fifo.emplace_back(seq, hk[j]);
-      }
+    if (roomy) {  // several host threads file the index while this one appends the FIFO entries
+      const uint64_t seq0 = t->spill_seq;
+      t->spill_seq += m;
+      std::vector<uint32_t> freed;
+      std::thread filer([&] {
+        t->spill_index.replace_all(hk.data(), hs.data(), seq0, m, freed,
+                                   (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2)));
+      });
+      for (uint64_t j = 0; j < m; j++) t->spill_fifo.emplace_back(seq0 + j, hk[j]);
+      filer.join();
+      t->spill_free.insert(t->spill_free.end(), freed.begin(), freed.end());
     }
     prof_add_host(t, roomy ? "evict.host_index(wall, under the spill copy)" : "evict.host_index(wall)",
                   std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count());

@@ -2,8 +2,10 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <deque>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -81,8 +83,8 @@ struct SpillTuple {  // host spill tier bookkeeping (payload lives in the pinned
 
 // key -> SpillTuple on the host: open addressing, linear probing, backward-shift deletion. An evict
 // call files hundreds of thousands of keys here; a node-based map spends longer on that than the
-// GPU does on selecting and copying the victims.
-class SpillIndex {
+// GPU does on selecting and copying the victims. One shard of the index below.
+class SpillShard {
  public:
   SpillTuple* find(uint64_t key) {
     if (cells_.empty()) return nullptr;
@@ -156,6 +158,63 @@ class SpillIndex {
   std::vector<Cell> cells_;
   size_t mask_ = 0, size_ = 0;
 };
+
+// The index proper: 16 independent shards selected by the top bits of the key's hash (the cell inside a
+// shard comes from the low bits), so that one evict call can file its victims from several host threads —
+// the table is far larger than the host caches and every access is a DRAM round trip.
+class SpillIndex {
+ public:
+  static constexpr int kShards = 16;
+  SpillTuple* find(uint64_t key) { return sh_[shard_of(key)].find(key); }
+  void put(uint64_t key, SpillTuple v) { sh_[shard_of(key)].put(key, v); }
+  bool erase(uint64_t key) { return sh_[shard_of(key)].erase(key); }
+  void prefetch(uint64_t key) const { sh_[shard_of(key)].prefetch(key); }
+  void clear() {
+    for (auto& s : sh_) s.clear();
+  }
+  void reserve(size_t n) {
+    for (auto& s : sh_) s.reserve(n / kShards + n / (4 * kShards) + 64);
+  }
+  size_t size() const {
+    size_t n = 0;
+    for (auto& s : sh_) n += s.size();
+    return n;
+  }
+  // keys[j] -> {seq0 + j, slabs[j]} for j in [0, m): the keys are distinct; the slab of the older copy of a key,
+  // if there was one, is appended to `freed`. Runs on up to `threads` host threads, each owning whole shards.
+  void replace_all(const uint64_t* keys, const uint32_t* slabs, uint64_t seq0, size_t m, std::vector<uint32_t>& freed,
+                   int threads);
+
+ private:
+  static int shard_of(uint64_t key) { return (int)(mix64(key) >> 60); }
+  SpillShard sh_[kShards];
+};
+static_assert(SpillIndex::kShards == 16, "shard_of takes the top 4 hash bits");
+
+inline void SpillIndex::replace_all(const uint64_t* keys, const uint32_t* slabs, uint64_t seq0, size_t m,
+                                    std::vector<uint32_t>& freed, int threads) {
+  threads = std::max(1, std::min(threads, (int)kShards));
+  std::vector<std::vector<uint32_t>> old(threads);
+  auto work = [&](int tid) {
+    for (size_t j = 0; j < m; j++) {
+      const int sh = shard_of(keys[j]);
+      if (sh % threads != tid) continue;
+      if (j + 64 < m) sh_[shard_of(keys[j + 64])].prefetch(keys[j + 64]);  // harmless when it is another thread's
+      SpillShard& s = sh_[sh];
+      if (SpillTuple* o = s.find(keys[j])) old[tid].push_back((uint32_t)o->ring_index);
+      s.put(keys[j], SpillTuple{seq0 + j, slabs[j]});
+    }
+  };
+  if (threads == 1 || m < 4096) {
+    for (int tid = 0; tid < threads; tid++) work(tid);
+  } else {
+    std::vector<std::thread> pool;
+    for (int tid = 1; tid < threads; tid++) pool.emplace_back(work, tid);
+    work(0);
+    for (auto& th : pool) th.join();
+  }
+  for (auto& v : old) freed.insert(freed.end(), v.begin(), v.end());
+}
 
 }  // namespace meepo
 
