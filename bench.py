@@ -525,7 +525,7 @@ def main():
 
     cpu = None
     if not args.no_cpu_baseline and rank == 0 and world == 1:
-        r = cpu_arm(w, dist, 3, 1, min(w["table_keys"], 8_000_000), min(B, 1 << 20))
+        r = cpu_arm(w, dist, 10, 2, min(w["table_keys"], 8_000_000), min(B, 1 << 20))
         cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     if rank == 0:
