@@ -15,6 +15,7 @@ launched by meepoembedding_b200/libmeepo.so through its C ABI.
 from __future__ import annotations
 
 import argparse
+import ast
 import json
 import os
 import subprocess
@@ -252,7 +253,8 @@ def main():
         w["batch"] = args.batch
     for kv in args.set:
         k, v = kv.split("=", 1)
-        w[k] = type(w[k])(eval(v)) if k in w and w[k] is not None else eval(v)
+        lit = ast.literal_eval(v)
+        w[k] = type(w[k])(lit) if k in w and w[k] is not None else lit
     dist = args.dist or w["dist"]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
