@@ -446,6 +446,9 @@ def main():
             nvlink = {"kernel": topn, "achieved": out[topn]["achieved_gbs"], "peak": 770.0, "unit": "GB/s per direction",
                       "frac": out[topn]["achieved_gbs"] / 770.0, "kernels": out,
                       "peak_source": "measured peer copy per direction (B200_PROFILING.md); 900 nominal"}
+    if nvlink is not None and top in nvlink["kernels"]:
+        roofline["note"] = ("the dominant kernel at this N stores most of its rows into peers' windows: it is bound by "
+                            "NVLink, not HBM — see the nvlink object (achieved vs the measured 770 GB/s per direction)")
     own_launches = 0
     for name, k in kernels.items():
         if "(cub)" in name:
