@@ -102,7 +102,7 @@ extern "C" {
 #define MEEPO_API
 #endif
 
-#define MEEPO_ABI_VERSION 1u
+#define MEEPO_ABI_VERSION 2u
 #define MEEPO_KEY_EMPTY 0xFFFFFFFFFFFFFFFFull
 #define MEEPO_KEY_RESERVED 0xFFFFFFFFFFFFFFFEull
 #define MEEPO_REDUCE_LEAF 256u
@@ -168,6 +168,8 @@ typedef struct {
   uint64_t row_bytes, state_bytes; /* per slot */
   uint64_t peer_keys_received;  /* sharded forward verbs: (sender, key) entries this owner served */
   uint64_t peer_grads_received; /* sharded apply_gradients: (sender, key) gradient rows received */
+  uint64_t probe_hist[4];       /* live keys sitting 0, 1, 2, >= 3 buckets past their home bucket (probe length - 1);
+                                   the oracle, which has no buckets, reports {size, 0, 0, 0} */
 } meepo_stats_t;
 
 /* --- life cycle (synchronous) ------------------------------------------- */
@@ -188,7 +190,15 @@ MEEPO_API const char* meepo_last_error(void);
 MEEPO_API meepo_status meepo_profile_enable(meepo_table* t, int32_t on);
 MEEPO_API meepo_status meepo_profile_read(meepo_table* t, char* buf, uint64_t buf_bytes);
 
-/* --- hot path (stream-ordered, asynchronous; device pointers) ------------ */
+/* --- hot path (stream-ordered, asynchronous; device pointers) ------------ *
+ * Verbs of ONE table share its scratch memory and execute one after another:
+ * a verb issued on another stream than its predecessor first waits (on the
+ * device) for the predecessor to finish, so a caller may mix streams freely —
+ * but verbs of one table never overlap each other. Different tables are
+ * independent. A sticky device-side failure (a sort / compaction look-back or a
+ * peer barrier that timed out, an exchange-window lane that overflowed) makes
+ * every following verb of the table fail with MEEPO_ECUDA / MEEPO_ENCCL rather
+ * than compute on corrupt state. */
 /* rows_out: n*dim elements; status_out: n bytes (may be NULL). */
 MEEPO_API meepo_status meepo_find_or_insert(meepo_table* t, const uint64_t* keys, uint64_t n,
                                             void* rows_out, uint8_t* status_out, void* stream);
@@ -199,15 +209,36 @@ MEEPO_API meepo_status meepo_apply_gradients(meepo_table* t, const uint64_t* key
                                              const void* grads, uint64_t n, void* stream);
 
 /* --- host-buffer front ends (pageable or pinned host pointers) ----------- *
- * Same semantics; the library stages through its own pinned ring and
- * overlaps H2D, kernels and D2H in chunks. They return after the results are
- * in the caller's buffers. */
+ * Same semantics; the library stages through its own device buffers and
+ * overlaps H2D, kernels and D2H in chunks on private streams. The plain verbs
+ * return after the results are in the caller's buffers. */
 MEEPO_API meepo_status meepo_find_or_insert_host(meepo_table* t, const uint64_t* keys, uint64_t n,
                                                  void* rows_out, uint8_t* status_out);
 MEEPO_API meepo_status meepo_lookup_host(meepo_table* t, const uint64_t* keys, uint64_t n,
                                          void* rows_out, uint8_t* found_out);
 MEEPO_API meepo_status meepo_apply_gradients_host(meepo_table* t, const uint64_t* keys,
                                                   const void* grads, uint64_t n);
+
+/* Asynchronous forms: enqueue and return a ticket. meepo_wait(t, ticket) blocks
+ * until that verb's results are in the caller's buffers (find_or_insert /
+ * lookup) or its inputs have been consumed (apply_gradients); ticket 0 waits
+ * for everything issued so far. The table executes the verbs strictly in ISSUE
+ * ORDER, whatever their copies overlap with: a caller that issues
+ *   find_or_insert(batch i+1); apply_gradients(batch i); ...
+ * (two batches in flight) gets the rows of batch i+1 coming down over PCIe
+ * while the gradients of batch i go up, and the rows it reads are those of the
+ * table before the update of batch i — exactly what the same sequence of
+ * synchronous calls returns. Buffers must stay valid (and, for the outputs,
+ * untouched) until the ticket has been waited for; only pinned buffers
+ * overlap. At most 32 tickets may be outstanding. The oracle library executes
+ * the verb at once and hands back a ticket that is already complete. */
+MEEPO_API meepo_status meepo_find_or_insert_host_async(meepo_table* t, const uint64_t* keys, uint64_t n,
+                                                       void* rows_out, uint8_t* status_out, uint64_t* ticket);
+MEEPO_API meepo_status meepo_lookup_host_async(meepo_table* t, const uint64_t* keys, uint64_t n,
+                                               void* rows_out, uint8_t* found_out, uint64_t* ticket);
+MEEPO_API meepo_status meepo_apply_gradients_host_async(meepo_table* t, const uint64_t* keys,
+                                                        const void* grads, uint64_t n, uint64_t* ticket);
+MEEPO_API meepo_status meepo_wait(meepo_table* t, uint64_t ticket);
 
 /* --- capacity management -------------------------------------------------- */
 MEEPO_API meepo_status meepo_evict(meepo_table* t, int32_t policy, double target_load,

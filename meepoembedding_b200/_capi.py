@@ -29,7 +29,7 @@ KEY_RESERVED = 0xFFFFFFFFFFFFFFFE
 REDUCE_LEAF = 256
 MAX_PEERS = 8
 PEER_BLOB_BYTES = 256
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class Config(C.Structure):
@@ -74,10 +74,10 @@ class Stats(C.Structure):
             "peer_keys_received",
             "peer_grads_received",
         )
-    ]
+    ] + [("probe_hist", C.c_uint64 * 4)]
 
     def as_dict(self):
-        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+        return {n: (list(getattr(self, n)) if n == "probe_hist" else int(getattr(self, n))) for n, _ in self._fields_}
 
 
 _P = C.c_void_p
@@ -100,6 +100,10 @@ SIGNATURES = {
     "meepo_find_or_insert_host": (C.c_int, [_P, _P, _U64, _P, _P]),
     "meepo_lookup_host": (C.c_int, [_P, _P, _U64, _P, _P]),
     "meepo_apply_gradients_host": (C.c_int, [_P, _P, _P, _U64]),
+    "meepo_find_or_insert_host_async": (C.c_int, [_P, _P, _U64, _P, _P, C.POINTER(_U64)]),
+    "meepo_lookup_host_async": (C.c_int, [_P, _P, _U64, _P, _P, C.POINTER(_U64)]),
+    "meepo_apply_gradients_host_async": (C.c_int, [_P, _P, _P, _U64, C.POINTER(_U64)]),
+    "meepo_wait": (C.c_int, [_P, _U64]),
     "meepo_evict": (C.c_int, [_P, C.c_int32, C.c_double, C.POINTER(_U64), _P]),
     "meepo_spill_readmit": (C.c_int, [_P, _P, _U64, _P]),
     "meepo_export_buffers": (C.c_int, [_P, _P, _P, _P, _P, _P, _U64, C.POINTER(_U64)]),

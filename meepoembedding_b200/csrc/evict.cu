@@ -138,6 +138,33 @@ __global__ void release_kernel(TableView t, const uint32_t* __restrict__ vslot, 
   }
 }
 
+// Overflow bits after slots were released (meepo_evict): bit(b) must be set iff some live key sits past b on
+// the probe path from its home bucket. Insertion only ever sets the bits, so without this pass a table that
+// is filled, evicted and refilled for long enough ends up with every bit set and every miss / new key walks
+// ever longer chains. Two passes over the bucket array: clear, then every displaced key re-marks its path.
+__global__ void __launch_bounds__(256) overflow_clear_kernel(TableView t) {
+  for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < t.num_buckets; b += gridDim.x * blockDim.x) {
+    uint32_t* w = reinterpret_cast<uint32_t*>(&t.buckets[b]) + 3;  // tags 12, 13 + metadata
+    const uint32_t v = *w;
+    if (v & (1u << 16)) *w = v & ~(1u << 16);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) t.counters[C_OVERFLOW] = 0ull;
+}
+__global__ void __launch_bounds__(256) overflow_mark_kernel(TableView t) {
+  uint32_t fresh = 0;
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < t.slots; s += gridDim.x * blockDim.x) {
+    const uint64_t key = *key_ptr(t, s);
+    if (key == MEEPO_KEY_EMPTY) continue;
+    const uint32_t b = s / kBucket;
+    for (uint32_t x = bucket_of(mix64(key), t.num_buckets); x != b; x = (x + 1 == t.num_buckets) ? 0 : x + 1) {
+      uint32_t* w = reinterpret_cast<uint32_t*>(&t.buckets[x]) + 3;
+      if (!(*reinterpret_cast<volatile uint32_t*>(w) & (1u << 16)) && !(atomicOr(w, 1u << 16) & (1u << 16))) fresh++;
+    }
+  }
+  fresh = __reduce_add_sync(0xFFFFFFFFu, fresh);
+  if ((threadIdx.x & 31u) == 0 && fresh) atomicAdd(t.counters + C_OVERFLOW, (unsigned long long)fresh);
+}
+
 // one warp per re-admitted tuple: host slab -> arena slot (zero-copy loads over PCIe)
 __global__ void __launch_bounds__(256) readmit_copy_kernel(TableView t, SpillView sp, const uint32_t* __restrict__ slot,
                                                            const uint32_t* __restrict__ slab, uint32_t n) {
@@ -223,6 +250,8 @@ MEEPO_API meepo_status meepo_evict(meepo_table* t, int32_t policy, double target
   if (!t->v.scores) return fail(MEEPO_EINVAL, "evict needs MEEPO_FLAG_TRACK_SCORES");
   DeviceGuard guard(t->device);
   cudaStream_t stream = (cudaStream_t)stream_;
+  VerbScope vs(t, stream);
+  MEEPO_TRY(vs.rc);
   if (n_evicted) *n_evicted = 0;
   uint64_t size = 0;
   MEEPO_TRY(live_size(t, &size));
@@ -375,6 +404,11 @@ MEEPO_API meepo_status meepo_evict(meepo_table* t, int32_t policy, double target
     ProfScope ps(t, "evict.release", stream);
     release_kernel<<<grid1d(t, k), 256, 0, stream>>>(t->v, vslot, (uint32_t)k);
   }
+  {
+    ProfScope ps(t, "evict.rebuild_overflow(2 kernels)", stream);
+    overflow_clear_kernel<<<grid1d(t, t->v.num_buckets), 256, 0, stream>>>(t->v);
+    overflow_mark_kernel<<<grid1d(t, t->v.slots), 256, 0, stream>>>(t->v);
+  }
   MEEPO_CUDA_TRY(cudaGetLastError());
   MEEPO_CUDA_TRY(cudaStreamSynchronize(stream));
   if (n_evicted) *n_evicted = k;
@@ -388,6 +422,8 @@ MEEPO_API meepo_status meepo_spill_readmit(meepo_table* t, const uint64_t* keys,
   if (n == 0) return MEEPO_OK;
   DeviceGuard guard(t->device);
   cudaStream_t stream = nullptr;
+  VerbScope vs(t, stream);
+  MEEPO_TRY(vs.rc);
   MEEPO_TRY(t->ws.reserve(Workspace::pad(n * 8) + Workspace::pad(n) + 4 * Workspace::pad(n * 4) + 4096, stream));
   uint64_t* d_keys = t->ws.take<uint64_t>(n);
   uint8_t* d_found = t->ws.take<uint8_t>(n);

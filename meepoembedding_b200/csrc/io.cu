@@ -8,93 +8,33 @@
 #include <cstring>
 #include <memory>
 
+#include "compact.cuh"
 #include "table.h"
 
 namespace meepo {
 
-constexpr int kLiveTile = 1024;
-
-__global__ void __launch_bounds__(256) live_count_kernel(TableView t, uint32_t m,
-                                                         uint32_t* __restrict__ tile_count) {
-  const uint32_t base = blockIdx.x * kLiveTile;
-  int total = 0;
+// live (key, slot) pairs in slot order: one ordered compaction pass (compact.cuh)
+__global__ void __launch_bounds__(kCompactThreads) live_compact_kernel(TableView t, uint32_t m,
+                                                                       uint64_t* __restrict__ live_key,
+                                                                       uint32_t* __restrict__ live_slot,
+                                                                       CompactState cs) {
+  CompactTile ct = compact_begin(cs, m);
+  unsigned flags = 0;
+  uint64_t key[kCompactItems];
 #pragma unroll
-  for (int k = 0; k < kLiveTile / 256; k++) {
-    const uint32_t p = base + k * 256 + threadIdx.x;
-    total += __syncthreads_count(p < m && *key_ptr(t, p) != MEEPO_KEY_EMPTY);
+  for (int k = 0; k < kCompactItems; k++) {
+    const uint64_t p = ct.pos(k);
+    key[k] = p < m ? *key_ptr(t, (uint32_t)p) : MEEPO_KEY_EMPTY;
+    if (key[k] != MEEPO_KEY_EMPTY) flags |= 1u << k;
   }
-  if (threadIdx.x == 0) tile_count[blockIdx.x] = (uint32_t)total;
-}
-
-// tile_off is an exclusive scan of tile_count computed by scan_tiles_kernel below
-__global__ void __launch_bounds__(1024) scan_tiles_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
-                                                          uint32_t n) {
-  __shared__ uint32_t warp_sum[32];
-  __shared__ uint32_t carry_s;
-  if (threadIdx.x == 0) carry_s = 0;
-  __syncthreads();
-  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (uint32_t base = 0; base < n; base += 1024) {
-    const uint32_t i = base + threadIdx.x;
-    const uint32_t v = i < n ? in[i] : 0;
-    uint32_t x = v;
+  compact_rank(ct, flags, cs);
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
-      if (lane >= d) x += y;
+  for (int k = 0; k < kCompactItems; k++) {
+    if ((flags >> k) & 1u) {
+      const uint64_t u = ct.rank(k);
+      live_key[u] = key[k];
+      live_slot[u] = (uint32_t)ct.pos(k);
     }
-    if (lane == 31) warp_sum[w] = x;
-    __syncthreads();
-    if (w == 0) {
-      uint32_t s = warp_sum[lane];
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        uint32_t y = __shfl_up_sync(0xFFFFFFFFu, s, d);
-        if (lane >= d) s += y;
-      }
-      warp_sum[lane] = s;
-    }
-    __syncthreads();
-    const uint32_t carry = carry_s;
-    const uint32_t incl = x + (w ? warp_sum[w - 1] : 0);
-    if (i < n) out[i] = carry + incl - v;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry_s = carry + incl;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) out[n] = carry_s;
-}
-
-__global__ void __launch_bounds__(256) live_fill_kernel(TableView t, uint32_t m,
-                                                        const uint32_t* __restrict__ tile_off,
-                                                        uint64_t* __restrict__ live_key,
-                                                        uint32_t* __restrict__ live_slot) {
-  __shared__ uint32_t warp_cnt[8];
-  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  uint32_t running = tile_off[blockIdx.x];
-  const uint32_t base = blockIdx.x * kLiveTile;
-#pragma unroll 1
-  for (int k = 0; k < kLiveTile / 256; k++) {
-    const uint32_t p = base + k * 256 + threadIdx.x;
-    const uint64_t key = p < m ? *key_ptr(t, p) : MEEPO_KEY_EMPTY;
-    const bool occ = key != MEEPO_KEY_EMPTY;
-    const unsigned msk = __ballot_sync(0xFFFFFFFFu, occ);
-    if (lane == 0) warp_cnt[w] = __popc(msk);
-    __syncthreads();
-    uint32_t before = 0, total = 0;
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-      const uint32_t c = warp_cnt[j];
-      before += j < (int)w ? c : 0;
-      total += c;
-    }
-    if (occ) {
-      const uint32_t u = running + before + __popc(msk & ((1u << lane) - 1u));
-      live_key[u] = key;
-      live_slot[u] = p;
-    }
-    running += total;
-    __syncthreads();
   }
 }
 
@@ -187,23 +127,22 @@ meepo_status live_size(meepo_table* t, uint64_t* out) {
 meepo_status sorted_live(meepo_table* t, uint64_t n, uint64_t** keys_sorted, uint32_t** slots_sorted,
                          cudaStream_t stream) {
   const uint32_t m = t->v.slots;
-  const uint32_t ntiles = (m + kLiveTile - 1) / kLiveTile;
+  const size_t cbytes = compact_state_bytes(m);
   size_t cub_bytes = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr,
                                   (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n, 0, 64);
   const size_t need = 2 * Workspace::pad(n * 8) + 2 * Workspace::pad(n * 4) + Workspace::pad(cub_bytes) +
-                      2 * Workspace::pad((ntiles + 1) * 4) + 4096;
+                      Workspace::pad(cbytes) + 4096;
   MEEPO_TRY(t->ws.reserve(need, stream));
   uint64_t* k_in = t->ws.take<uint64_t>(n);
   uint64_t* k_out = t->ws.take<uint64_t>(n);
   uint32_t* s_in = t->ws.take<uint32_t>(n);
   uint32_t* s_out = t->ws.take<uint32_t>(n);
   char* tmp = t->ws.take<char>(cub_bytes);
-  uint32_t* tile_count = t->ws.take<uint32_t>(ntiles + 1);
-  uint32_t* tile_off = t->ws.take<uint32_t>(ntiles + 1);
-  live_count_kernel<<<ntiles, 256, 0, stream>>>(t->v, m, tile_count);
-  scan_tiles_kernel<<<1, 1024, 0, stream>>>(tile_count, tile_off, ntiles);
-  live_fill_kernel<<<ntiles, 256, 0, stream>>>(t->v, m, tile_off, k_in, s_in);
+  char* cstate = t->ws.take<char>(cbytes);
+  MEEPO_CUDA_TRY(cudaMemsetAsync(cstate, 0, cbytes, stream));
+  live_compact_kernel<<<compact_tiles(m), kCompactThreads, 0, stream>>>(t->v, m, k_in, s_in,
+                                                                        compact_carve(cstate, t->err_word + kErrLookback));
   MEEPO_CUDA_TRY(cudaGetLastError());
   if (n)
     MEEPO_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, cub_bytes, (const uint64_t*)k_in, k_out, (const uint32_t*)s_in,
@@ -262,6 +201,8 @@ MEEPO_API meepo_status meepo_export_buffers(meepo_table* t, uint64_t* keys, void
                                             uint64_t* scores, uint32_t* steps, uint64_t max_n, uint64_t* n_out) {
   if (!t || !n_out) return fail(MEEPO_EINVAL, "null argument");
   DeviceGuard guard(t->device);
+  VerbScope vs(t, nullptr);
+  MEEPO_TRY(vs.rc);
   uint64_t n = 0;
   MEEPO_TRY(live_size(t, &n));
   *n_out = n;
@@ -294,6 +235,8 @@ MEEPO_API meepo_status meepo_import_buffers(meepo_table* t, const uint64_t* keys
   if (n == 0) return MEEPO_OK;
   DeviceGuard guard(t->device);
   cudaStream_t stream = nullptr;
+  VerbScope vs(t, stream);
+  MEEPO_TRY(vs.rc);
   MEEPO_TRY(t->ws.reserve(2 * Workspace::pad(n * 4) + 1024, stream));
   uint32_t* slot_buf = t->ws.take<uint32_t>(n);
   uint32_t* new_slots = t->ws.take<uint32_t>(n);
@@ -305,6 +248,8 @@ MEEPO_API meepo_status meepo_import_buffers(meepo_table* t, const uint64_t* keys
 MEEPO_API meepo_status meepo_export(meepo_table* t, const char* path) {
   if (!t || !path) return fail(MEEPO_EINVAL, "null argument");
   DeviceGuard guard(t->device);
+  VerbScope vs(t, nullptr);
+  MEEPO_TRY(vs.rc);
   uint64_t n = 0;
   MEEPO_TRY(live_size(t, &n));
   FILE* f = fopen(path, "wb");
@@ -379,6 +324,8 @@ MEEPO_API meepo_status meepo_export(meepo_table* t, const char* path) {
 MEEPO_API meepo_status meepo_import(meepo_table* t, const char* path) {
   if (!t || !path) return fail(MEEPO_EINVAL, "null argument");
   DeviceGuard guard(t->device);
+  VerbScope vs(t, nullptr);
+  MEEPO_TRY(vs.rc);
   FILE* f = fopen(path, "rb");
   if (!f) return fail(MEEPO_EIO, std::string("cannot open ") + path);
   std::unique_ptr<FILE, int (*)(FILE*)> closer(f, fclose);
@@ -389,6 +336,14 @@ MEEPO_API meepo_status meepo_import(meepo_table* t, const char* path) {
       h.state_bytes != t->state_bytes || (int32_t)h.opt != t->cfg.opt)
     return fail(MEEPO_EINVAL, "file does not match table configuration");
   const uint64_t n = h.n, R = t->row_bytes, S = t->state_bytes;
+  {  // the header's n drives every offset below: it must agree with the file size, and the tuples must fit
+    const uint64_t tuple_file = 8 + R + S + 8 + 4;
+    if (fseeko(f, 0, SEEK_END) != 0) return fail(MEEPO_EIO, "seek failed");
+    const off_t fsz = ftello(f);
+    if (fsz < 0 || n > ((uint64_t)fsz - sizeof h) / tuple_file || (uint64_t)fsz != sizeof h + n * tuple_file)
+      return fail(MEEPO_EIO, "file size does not match the tuple count in the header");
+    if (n > 0xFFFFFFFFull) return fail(MEEPO_EINVAL, "file holds more tuples than a table can");
+  }
   if (h.epoch > t->epoch) t->epoch = h.epoch;
   if (n == 0) return MEEPO_OK;
   const uint64_t off_keys = sizeof h, off_rows = off_keys + n * 8, off_state = off_rows + n * R,
@@ -396,12 +351,13 @@ MEEPO_API meepo_status meepo_import(meepo_table* t, const char* path) {
   const uint64_t chunk = 1u << 16;
   const size_t tuple = 8 + R + S + 8 + 4;
   char *d_stage = nullptr, *h_stage = nullptr;
-  MEEPO_CUDA_TRY(cudaMalloc(&d_stage, chunk * tuple + 1024));
-  if (cudaHostAlloc(&h_stage, chunk * tuple + 1024, cudaHostAllocDefault) != cudaSuccess) {
+  MEEPO_CUDA_TRY(cudaMalloc(&d_stage, chunk * (tuple + 1) + 1024));
+  if (cudaHostAlloc(&h_stage, chunk * (tuple + 1) + 1024, cudaHostAllocDefault) != cudaSuccess) {
     cudaFree(d_stage);
     return fail(MEEPO_ENOMEM, "cudaHostAlloc(import bounce)");
   }
   meepo_status rc = MEEPO_OK;
+  uint64_t rejected = 0;  // tuples that found no slot (or carried a reserved key): reported, never dropped silently
   for (uint64_t lo = 0; lo < n && rc == MEEPO_OK; lo += chunk) {
     const uint64_t m = std::min(chunk, n - lo);
     // staging layout (each section 16-byte aligned because chunk is a multiple of 16)
@@ -421,10 +377,20 @@ MEEPO_API meepo_status meepo_import(meepo_table* t, const char* path) {
     }
     rc = meepo_import_buffers(t, reinterpret_cast<uint64_t*>(d_stage + o_k), d_stage + o_r, S ? d_stage + o_s : nullptr,
                               reinterpret_cast<uint64_t*>(d_stage + o_c), reinterpret_cast<uint32_t*>(d_stage + o_t),
-                              m, nullptr);
+                              m, reinterpret_cast<uint8_t*>(d_stage + o_t + chunk * 4));
+    if (rc != MEEPO_OK) break;
+    uint8_t* hst = reinterpret_cast<uint8_t*>(h_stage + o_t + chunk * 4);
+    if (cudaMemcpy(hst, d_stage + o_t + chunk * 4, m, cudaMemcpyDeviceToHost) != cudaSuccess) {
+      rc = fail(MEEPO_ECUDA, "import copy failed");
+      break;
+    }
+    for (uint64_t i = 0; i < m; i++) rejected += hst[i] == MEEPO_KEY_FULL || hst[i] == MEEPO_KEY_INVALID;
   }
   cudaFree(d_stage);
   cudaFreeHost(h_stage);
+  if (rc == MEEPO_OK && rejected)
+    rc = fail(MEEPO_ENOMEM, std::to_string(rejected) + " of " + std::to_string(n) +
+                                " tuples did not fit into the table (full) or carried a reserved key; the rest were imported");
   return rc;
 }
 

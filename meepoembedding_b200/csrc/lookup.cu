@@ -155,6 +155,8 @@ MEEPO_API meepo_status meepo_find_or_insert(meepo_table* t, const uint64_t* keys
                                             void* rows_out, uint8_t* status_out, void* stream) {
   MEEPO_TRY(check_batch(t, keys, n, rows_out));
   DeviceGuard guard(t->device);
+  VerbScope vs(t, (cudaStream_t)stream);
+  MEEPO_TRY(vs.rc);
   return launch_probe_gather(t, keys, n, rows_out, status_out, true, (cudaStream_t)stream);
 }
 
@@ -162,6 +164,8 @@ MEEPO_API meepo_status meepo_lookup(meepo_table* t, const uint64_t* keys, uint64
                                     uint8_t* found_out, void* stream) {
   MEEPO_TRY(check_batch(t, keys, n, rows_out));
   DeviceGuard guard(t->device);
+  VerbScope vs(t, (cudaStream_t)stream);
+  MEEPO_TRY(vs.rc);
   return launch_probe_gather(t, keys, n, rows_out, found_out, false, (cudaStream_t)stream);
 }
 

@@ -45,14 +45,12 @@ constexpr uint32_t kMaxPeers = MEEPO_MAX_PEERS;
 constexpr uint32_t kBlobMagic = 0x4D50454Bu;  // "MPEK"
 constexpr size_t kWindowHeader = 4096;
 
-enum PeerError : uint32_t { PE_TIMEOUT = 1u, PE_REGION_OVERFLOW = 2u };
 
 // A rank's exchange window as seen through a (peer or local) mapping.
 struct PeerWindow {
   unsigned long long* flags;  // [kMaxPeers] barrier sequence number last signalled by each source
   uint32_t* recv_cnt;         // [kMaxPeers] entries source s pushed in the current phase
   uint32_t* recv_reuse;       // [kMaxPeers] source s re-sent the entries of its last forward pass (same positions)
-  uint32_t* error;            // sticky PeerError bits
   uint64_t* recv_keys;        // [world][region]      keys pushed by source s
   uint32_t* recv_occ;         // [world][region]      batch occurrences behind each pushed key
   uint4* recv_grads;          // [world][region][cpr] pre-reduced gradient rows pushed by source s
@@ -63,7 +61,11 @@ struct PeerWindow {
 struct PeerSet {
   PeerWindow w[kMaxPeers];
   uint32_t world, rank, region, cpr;
+  uint32_t* err;  // this table's sticky error words (table.h kErr*): kernels only ever store 1
 };
+__device__ __forceinline__ void raise_error(const PeerSet& ps, int which) {
+  reinterpret_cast<volatile uint32_t*>(ps.err)[which] = 1u;
+}
 
 // Device-resident bookkeeping of the owner side of one phase (filled by the barrier kernel).
 struct PeerWork {
@@ -122,7 +124,6 @@ static void carve_window(char* base, uint32_t world, uint64_t region, uint32_t c
   w.flags = reinterpret_cast<unsigned long long*>(base + off);
   w.recv_cnt = reinterpret_cast<uint32_t*>(base + off + 128);
   w.recv_reuse = reinterpret_cast<uint32_t*>(base + off + 192);
-  w.error = reinterpret_cast<uint32_t*>(base + off + 256);
   off += kWindowHeader;
   const size_t cells = (size_t)world * region;
   w.recv_keys = reinterpret_cast<uint64_t*>(base + off);
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(32) peer_barrier_kernel(const __grid_constant_
     const unsigned long long t0 = global_timer_ns();
     while (ld_acquire_sys(mine) < seq) {
       if (global_timer_ns() - t0 > timeout_ns) {
-        atomicOr(ps.w[ps.rank].error, (uint32_t)PE_TIMEOUT);
+        raise_error(ps, kErrPeerTimeout);
         break;
       }
       __nanosleep(64);
@@ -230,7 +231,7 @@ __global__ void __launch_bounds__(256) push_keys_kernel(const __grid_constant__ 
     const uint32_t o = owner_of(key, ps.world);
     const uint32_t p = claim_position(send_cnt, o, am, lane);
     if (p >= ps.region) {
-      atomicOr(ps.w[ps.rank].error, (uint32_t)PE_REGION_OVERFLOW);
+      raise_error(ps, kErrPeerOverflow);
       loc[u] = kNil;
       continue;
     }
@@ -296,7 +297,7 @@ __global__ void __launch_bounds__(256) assign_grad_rows_kernel(const __grid_cons
     const uint32_t o = owner_of(key, ps.world);
     const uint32_t p = claim_position(send_cnt, o, am, lane);
     if (p >= ps.region) {
-      atomicOr(ps.w[ps.rank].error, (uint32_t)PE_REGION_OVERFLOW);
+      raise_error(ps, kErrPeerOverflow);
       row_ptrs[u] = trash_row;
       loc[u] = kNil;
       continue;
@@ -465,19 +466,6 @@ void destroy_peer(meepo_table* t) {
   t->peer = nullptr;
 }
 
-meepo_status peer_error_check(meepo_table* t) {
-  PeerState* p = t->peer;
-  if (!p || !p->window) return MEEPO_OK;
-  uint32_t err = 0;
-  PeerWindow w;
-  carve_window(p->window, p->world, p->region, t->v.cpr, w, nullptr);
-  MEEPO_CUDA_TRY(cudaMemcpy(&err, w.error, 4, cudaMemcpyDeviceToHost));
-  if (err & PE_TIMEOUT) return fail(MEEPO_ENCCL, "sharded verb: a peer did not reach the barrier (timeout)");
-  if (err & PE_REGION_OVERFLOW)
-    return fail(MEEPO_ENCCL, "sharded verb: more keys for one owner than region_keys; results are incomplete");
-  return MEEPO_OK;
-}
-
 static meepo_status barrier(meepo_table* t, const uint32_t* send_cnt, bool for_apply, cudaStream_t stream) {
   PeerState* p = t->peer;
   ProfScope ps(t, "sharded.barrier", stream);
@@ -502,6 +490,8 @@ static meepo_status sharded_forward(meepo_table* t, const uint64_t* keys, uint64
   MEEPO_TRY(check_sharded(t, keys, n, rows_out));
   DeviceGuard guard(t->device);
   PeerState* p = t->peer;
+  VerbScope vs(t, stream);
+  MEEPO_TRY(vs.rc);
   t->cache_valid = false;
   t->epoch++;
   t->v.epoch = (uint32_t)t->epoch;
@@ -559,6 +549,8 @@ static meepo_status sharded_apply(meepo_table* t, const uint64_t* keys, const vo
   MEEPO_TRY(check_sharded(t, keys, n, grads));
   DeviceGuard guard(t->device);
   PeerState* p = t->peer;
+  VerbScope vs(t, stream);
+  MEEPO_TRY(vs.rc);
   MEEPO_TRY(t->ws.reserve(backward_ws_bytes(t, p), stream));
   uint64_t* ukeys = p->ukeys;
   uint4** row_ptrs = t->ws.take<uint4*>(std::max<uint64_t>(n, 1));
@@ -601,7 +593,7 @@ static meepo_status sharded_apply(meepo_table* t, const uint64_t* keys, const vo
                                                 entry_valid);
     MEEPO_CUDA_TRY(cudaGetLastError());
   }
-  static const char* const names[5] = {"sharded.owner_sort", "sharded.owner_segments(3 kernels)",
+  static const char* const names[5] = {"sharded.owner_sort", "sharded.owner_segments",
                                        "sharded.owner_apply", "sharded.owner_long_leaves", "sharded.owner_long_finish"};
   MEEPO_TRY(run_segmented(t, ow, t->v.slots, p->ps.w[p->rank].recv_grads, t->v.opt, nullptr, stream, nullptr, names));
   return barrier(t, nullptr, false, stream);
@@ -620,6 +612,7 @@ static meepo_status warm_up(meepo_table* t) {
   self.rank = 0;
   self.region = (uint32_t)p->region;
   self.cpr = t->v.cpr;
+  self.err = t->err_word;
   carve_window(p->window, p->world, p->region, t->v.cpr, self.w[0], nullptr);
   p->ps = self;
   p->attached = true;
@@ -664,7 +657,7 @@ MEEPO_API meepo_status meepo_peer_prepare(meepo_table* t, uint32_t rank, uint32_
                                           uint64_t region_keys, void* blob_out) {
   if (!t || !blob_out) return fail(MEEPO_EINVAL, "null argument");
   if (world == 0 || world > kMaxPeers || rank >= world) return fail(MEEPO_EINVAL, "need rank < world <= MEEPO_MAX_PEERS");
-  if (max_batch == 0 || max_batch > 0x7FFFFFFFull) return fail(MEEPO_EINVAL, "bad max_batch");
+  if (max_batch == 0 || max_batch > (1ull << 30)) return fail(MEEPO_EINVAL, "bad max_batch (1 .. 2^30)");
   if (region_keys == 0 || region_keys > max_batch) region_keys = max_batch;
   if ((uint64_t)world * region_keys > 0x7FFFFFFFull) return fail(MEEPO_EINVAL, "world * region_keys must fit in 31 bits");
   if (t->peer) return fail(MEEPO_EINVAL, "meepo_peer_prepare was already called on this table");
@@ -765,6 +758,7 @@ MEEPO_API meepo_status meepo_peer_attach(meepo_table* t, const void* blobs) {
   p->ps.rank = p->rank;
   p->ps.region = (uint32_t)p->region;
   p->ps.cpr = t->v.cpr;
+  p->ps.err = t->err_word;
   for (uint32_t j = 0; j < p->world; j++) {
     PeerBlob b;
     memcpy(&b, (const char*)blobs + (size_t)j * MEEPO_PEER_BLOB_BYTES, sizeof b);

@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(kRsThreads, 4) rs_onesweep_kernel(const uint32
           const uint32_t* q = lookback + (size_t)(prev - 1 - u) * 256 + tid;
           for (uint32_t spin = 0; (x & kFlagMask) == 0; spin++) {
             if (spin > (1u << 24)) {  // a range that never shows up: give up rather than hang
-              atomicExch(error, 1u);
+              *reinterpret_cast<volatile uint32_t*>(error) = 1u;
               x = kFlagInclusive;
               break;
             }
@@ -332,7 +332,7 @@ meepo_status radix_sort_pairs(meepo_table* t, char* temp, const uint32_t* k_in, 
     rs_onesweep_kernel<<<tiles, kRsThreads, 0, stream>>>(src_k, src_v, dst_k, dst_v, n, 8 * p, bits, nsub,
                                                          r.hist + p * 256, r.counters + p,
                                                          r.lookback + (size_t)p * lb_stride * 256,
-                                                         &t->dstate->pad[0]);
+                                                         t->err_word + kErrLookback);
     src_k = dst_k;
     src_v = dst_v;
   }
@@ -354,9 +354,6 @@ extern "C" MEEPO_API meepo_status meepo_internal_sort_pairs(meepo_table* t, cons
   MEEPO_TRY(t->ws.reserve(radix_sort_temp_bytes(n, end_bit), stream));
   char* temp = t->ws.take<char>(radix_sort_temp_bytes(n, end_bit));
   MEEPO_TRY(radix_sort_pairs(t, temp, k_in, k_out, v_in, v_out, (uint32_t)n, end_bit, stream));
-  uint32_t err = 0;
   MEEPO_CUDA_TRY(cudaStreamSynchronize(stream));
-  MEEPO_CUDA_TRY(cudaMemcpy(&err, &t->dstate->pad[0], 4, cudaMemcpyDeviceToHost));
-  if (err) return fail(MEEPO_ECUDA, "radix sort: look-back gave up waiting for a tile");
-  return MEEPO_OK;
+  return sticky_error(t);
 }

@@ -4,59 +4,19 @@
 //   meepo_reduce_duplicates  batch-level dedup (CAS into an L2-resident scratch table) and, for the
 //                            backward path, the fixed-shape pre-reduction of duplicate gradients
 //   meepo_gather_rows        rows_out[i] = rows_in[index[i]], 16-byte vectorised (un-permute/expand)
+#include "compact.cuh"
 #include "table.h"
 
 namespace meepo {
 
 constexpr int kPartTile = 2048;  // keys per CTA in the partition passes
 constexpr int kMaxShards = 32;
-constexpr int kScanTile = 1024;  // elements per CTA in the occupancy passes
 
 // ---------------------------------------------------------------------------------------------
-// single-CTA exclusive scan (n is small: tiles x shards). out[n] = total.
-// `skip` (optional, device): the whole pass is a no-op when *skip != 0 (the sharded backward pass reuses
-// the dedup of the preceding forward pass when the batch is the same; the host cannot know that).
+// single-CTA exclusive scan over the (tile, shard) histogram of the owner partition (compact.cuh)
 __global__ void __launch_bounds__(1024) excl_scan_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
-                                                         uint32_t n, unsigned long long* total64,
-                                                         const uint32_t* __restrict__ skip) {
-  if (skip && *skip) return;
-  __shared__ uint32_t warp_sum[32];
-  __shared__ uint32_t carry_s;
-  if (threadIdx.x == 0) carry_s = 0;
-  __syncthreads();
-  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (uint32_t base = 0; base < n; base += 1024) {
-    const uint32_t i = base + threadIdx.x;
-    const uint32_t v = i < n ? in[i] : 0;
-    uint32_t x = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
-      if (lane >= d) x += y;
-    }
-    if (lane == 31) warp_sum[w] = x;
-    __syncthreads();
-    if (w == 0) {
-      uint32_t s = warp_sum[lane];
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        uint32_t y = __shfl_up_sync(0xFFFFFFFFu, s, d);
-        if (lane >= d) s += y;
-      }
-      warp_sum[lane] = s;
-    }
-    __syncthreads();
-    const uint32_t carry = carry_s;
-    const uint32_t incl = x + (w ? warp_sum[w - 1] : 0);
-    if (i < n) out[i] = carry + incl - v;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry_s = carry + incl;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    out[n] = carry_s;
-    if (total64) *total64 = carry_s;
-  }
+                                                         uint32_t n) {
+  block_excl_scan_1024(in, out, n, nullptr);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -147,52 +107,33 @@ __global__ void __launch_bounds__(256) dedup_insert_kernel(const uint64_t* __res
   }
 }
 
-__global__ void __launch_bounds__(256) occ_count_kernel(const uint64_t* __restrict__ scratch, uint32_t m,
-                                                        uint32_t* __restrict__ tile_count,
-                                                        const uint32_t* __restrict__ skip) {
+// occupied cells of the scratch table, in cell order -> unique ids: one ordered compaction pass (compact.cuh)
+__global__ void __launch_bounds__(kCompactThreads) occ_compact_kernel(const uint64_t* __restrict__ scratch, uint32_t m,
+                                                                      uint32_t* __restrict__ uid_of_slot,
+                                                                      uint64_t* __restrict__ unique_out,
+                                                                      unsigned long long* __restrict__ n_unique,
+                                                                      CompactState cs,
+                                                                      const uint32_t* __restrict__ skip) {
   if (skip && *skip) return;
-  const uint32_t base = blockIdx.x * kScanTile;
-  int total = 0;
+  CompactTile ct = compact_begin(cs, m);
+  unsigned flags = 0;
+  uint64_t key[kCompactItems];
 #pragma unroll
-  for (int k = 0; k < kScanTile / 256; k++) {
-    const uint32_t p = base + k * 256 + threadIdx.x;
-    total += __syncthreads_count(p < m && scratch[p] != MEEPO_KEY_EMPTY);
+  for (int k = 0; k < kCompactItems; k++) {
+    const uint64_t p = ct.pos(k);
+    key[k] = p < m ? scratch[p] : MEEPO_KEY_EMPTY;
+    if (key[k] != MEEPO_KEY_EMPTY) flags |= 1u << k;
   }
-  if (threadIdx.x == 0) tile_count[blockIdx.x] = (uint32_t)total;
-}
-
-__global__ void __launch_bounds__(256) occ_fill_kernel(const uint64_t* __restrict__ scratch, uint32_t m,
-                                                       const uint32_t* __restrict__ tile_off,
-                                                       uint32_t* __restrict__ uid_of_slot,
-                                                       uint64_t* __restrict__ unique_out, const uint32_t* __restrict__ skip) {
-  if (skip && *skip) return;
-  __shared__ uint32_t warp_cnt[8];
-  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  uint32_t running = tile_off[blockIdx.x];
-  const uint32_t base = blockIdx.x * kScanTile;
-#pragma unroll 1
-  for (int k = 0; k < kScanTile / 256; k++) {
-    const uint32_t p = base + k * 256 + threadIdx.x;
-    const uint64_t key = p < m ? scratch[p] : MEEPO_KEY_EMPTY;
-    const bool occ = key != MEEPO_KEY_EMPTY;
-    const unsigned msk = __ballot_sync(0xFFFFFFFFu, occ);
-    if (lane == 0) warp_cnt[w] = __popc(msk);
-    __syncthreads();
-    uint32_t before = 0, total = 0;
+  compact_rank(ct, flags, cs);
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-      const uint32_t c = warp_cnt[j];
-      before += j < (int)w ? c : 0;
-      total += c;
+  for (int k = 0; k < kCompactItems; k++) {
+    if ((flags >> k) & 1u) {
+      const uint32_t u = (uint32_t)ct.rank(k);
+      uid_of_slot[ct.pos(k)] = u;
+      unique_out[u] = key[k];
     }
-    if (occ) {
-      const uint32_t u = running + before + __popc(msk & ((1u << lane) - 1u));
-      uid_of_slot[p] = u;
-      unique_out[u] = key;
-    }
-    running += total;
-    __syncthreads();
   }
+  if (ct.last && threadIdx.x == 0) *n_unique = ct.base + ct.tile_total;
 }
 
 __global__ void __launch_bounds__(256) dedup_inverse_kernel(const uint32_t* __restrict__ pos, uint32_t n,
@@ -251,13 +192,17 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const uint4* __restric
 
 // batch-level dedup (+ optional pre-reduction of the duplicate gradients); scratch comes out of the
 // table workspace, which the caller has reserved for at least dedup_bytes().
-size_t dedup_bytes(const meepo_table* t, uint64_t n, bool with_grads) {
-  if (n == 0) return 256;
+static uint64_t dedup_cells(uint64_t n) {  // scratch cells: a power of two >= 2n
   uint64_t m = 1024;
   while (m < 2 * n) m <<= 1;
-  const uint64_t ntiles = m / kScanTile;
+  return m;
+}
+
+size_t dedup_bytes(const meepo_table* t, uint64_t n, bool with_grads) {
+  if (n == 0) return 256;
+  const uint64_t m = dedup_cells(n);
   size_t need = Workspace::pad((size_t)m * 8) + Workspace::pad(n * 4) + Workspace::pad((size_t)m * 4) +
-                2 * Workspace::pad((ntiles + 1) * 4) + 4096;
+                Workspace::pad(compact_state_bytes(m)) + 4096;
   if (with_grads) need += SegWork::bytes(n, t->v.dim, bits_for((uint32_t)n));
   return need;
 }
@@ -269,24 +214,25 @@ meepo_status dedup_hash(meepo_table* t, const uint64_t* keys, uint64_t n, const 
     MEEPO_CUDA_TRY(cudaMemsetAsync(o.n_unique, 0, 8, stream));
     return MEEPO_OK;
   }
-  uint32_t m = 1024;
-  while (m < 2 * n) m <<= 1;
-  const uint32_t ntiles = m / kScanTile;
+  if (n > (1ull << 30)) return fail(MEEPO_EINVAL, "dedup: batch larger than 2^30 keys");
+  const uint32_t m = (uint32_t)dedup_cells(n);  // <= 2^31
   const int end_bit = bits_for((uint32_t)n);
   uint64_t* scratch = t->ws.take<uint64_t>(m);
   uint32_t* pos = t->ws.take<uint32_t>(n);
   uint32_t* uid_of_slot = t->ws.take<uint32_t>(m);
-  uint32_t* tile_count = t->ws.take<uint32_t>(ntiles + 1);
-  uint32_t* tile_off = t->ws.take<uint32_t>(ntiles + 1);
+  const size_t cbytes = compact_state_bytes(m);
+  char* cstate = t->ws.take<char>(cbytes);
   if (with_grads) w.take(t->ws, n, t->v.dim, end_bit);
-  ProfScope ps(t, "dedup.hash(5 kernels)", stream);
+  ProfScope ps(t, "dedup.hash(3 kernels)", stream);
   MEEPO_CUDA_TRY(cudaMemsetAsync(scratch, 0xFF, (size_t)m * 8, stream));
+  MEEPO_CUDA_TRY(cudaMemsetAsync(cstate, 0, cbytes, stream));
   if (o.occurrences) MEEPO_CUDA_TRY(cudaMemsetAsync(o.occurrences, 0, n * 4, stream));
   const int grid = grid_for(t, (const void*)dedup_insert_kernel, 256, 0, (n + 255) / 256);
   dedup_insert_kernel<<<grid, 256, 0, stream>>>(keys, (uint32_t)n, scratch, m - 1, pos, skip);
-  occ_count_kernel<<<ntiles, 256, 0, stream>>>(scratch, m, tile_count, skip);
-  excl_scan_kernel<<<1, 1024, 0, stream>>>(tile_count, tile_off, ntiles, (unsigned long long*)o.n_unique, skip);
-  occ_fill_kernel<<<ntiles, 256, 0, stream>>>(scratch, m, tile_off, uid_of_slot, o.unique_keys, skip);
+  occ_compact_kernel<<<compact_tiles(m), kCompactThreads, 0, stream>>>(scratch, m, uid_of_slot, o.unique_keys,
+                                                                       (unsigned long long*)o.n_unique,
+                                                                       compact_carve(cstate, t->err_word + kErrLookback),
+                                                                       skip);
   dedup_inverse_kernel<<<grid, 256, 0, stream>>>(pos, (uint32_t)n, uid_of_slot, o.inverse,
                                                  with_grads ? w.sk_in : nullptr, with_grads ? w.sv_in : nullptr,
                                                  o.occurrences, skip);
@@ -299,7 +245,7 @@ meepo_status dedup_hash(meepo_table* t, const uint64_t* keys, uint64_t n, const 
 meepo_status dedup_reduce(meepo_table* t, SegWork& w, const void* grads, uint64_t n, const DedupOut& o,
                           cudaStream_t stream) {
   if (n == 0) return MEEPO_OK;
-  static const char* const names[5] = {"dedup.radix_sort", "dedup.segments(3 kernels)", "dedup.reduce_store",
+  static const char* const names[5] = {"dedup.radix_sort", "dedup.segments", "dedup.reduce_store",
                                        "dedup.long_leaves", "dedup.long_finish"};
   return run_segmented(t, w, (uint32_t)n, grads, kReduceStoreOnly, o.grads_out, stream, nullptr, names, o.grad_rows);
 }
@@ -327,6 +273,8 @@ MEEPO_API meepo_status meepo_shard_partition(meepo_table* t, const uint64_t* key
   if (n && !keys) return fail(MEEPO_EINVAL, "null buffer");
   DeviceGuard guard(t->device);
   cudaStream_t stream = (cudaStream_t)stream_;
+  VerbScope vs(t, stream);
+  MEEPO_TRY(vs.rc);
   if (n == 0) {
     MEEPO_CUDA_TRY(cudaMemsetAsync(counts_out, 0, 8 * num_shards, stream));
     return MEEPO_OK;
@@ -338,7 +286,7 @@ MEEPO_API meepo_status meepo_shard_partition(meepo_table* t, const uint64_t* key
   uint32_t* off = t->ws.take<uint32_t>(cells + 1);
   ProfScope ps(t, "shard.partition(3 kernels)", stream);
   part_hist_kernel<<<ntiles, 256, 0, stream>>>(keys, (uint32_t)n, num_shards, ntiles, hist);
-  excl_scan_kernel<<<1, 1024, 0, stream>>>(hist, off, (uint32_t)cells, nullptr, nullptr);
+  excl_scan_kernel<<<1, 1024, 0, stream>>>(hist, off, (uint32_t)cells);
   part_scatter_kernel<<<ntiles, 256, 0, stream>>>(keys, (uint32_t)n, num_shards, ntiles, off, counts_out, perm_out,
                                                   keys_sorted_out);
   MEEPO_CUDA_TRY(cudaGetLastError());
@@ -349,11 +297,13 @@ MEEPO_API meepo_status meepo_reduce_duplicates(meepo_table* t, const uint64_t* k
                                                uint64_t* unique_keys_out, void* grads_out, uint32_t* inverse_out,
                                                uint64_t* n_unique_out, void* stream_) {
   if (!t || !n_unique_out) return fail(MEEPO_EINVAL, "null argument");
-  if (n > 0x7FFFFFFFull) return fail(MEEPO_EINVAL, "batch too large");
+  if (n > (1ull << 30)) return fail(MEEPO_EINVAL, "batch too large (at most 2^30 keys)");
   if (n && (!keys || !unique_keys_out)) return fail(MEEPO_EINVAL, "null buffer");
   if ((grads == nullptr) != (grads_out == nullptr)) return fail(MEEPO_EINVAL, "grads and grads_out go together");
   DeviceGuard guard(t->device);
   cudaStream_t stream = (cudaStream_t)stream_;
+  VerbScope vs(t, stream);
+  MEEPO_TRY(vs.rc);
   MEEPO_TRY(t->ws.reserve(dedup_bytes(t, n, grads != nullptr), stream));
   return dedup_run(t, keys, grads, n, DedupOut{unique_keys_out, grads_out, inverse_out, n_unique_out, nullptr, nullptr}, stream);
 }
@@ -366,6 +316,8 @@ MEEPO_API meepo_status meepo_gather_rows(meepo_table* t, const void* rows_in, co
   if (n == 0) return MEEPO_OK;
   DeviceGuard guard(t->device);
   cudaStream_t stream = (cudaStream_t)stream_;
+  VerbScope vs(t, stream);
+  MEEPO_TRY(vs.rc);
   ProfScope ps(t, "shard.gather_rows", stream);
   const uint64_t tiles = (n + 31) / 32;
   const int grid = grid_for(t, (const void*)gather_rows_kernel, 256, 0, (tiles + 7) / 8);

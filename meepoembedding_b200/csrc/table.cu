@@ -1,6 +1,7 @@
 // table.cu — life cycle of the CUDA table: create / destroy / stats, workspace, error state.
 // Implements the life-cycle block of include/meepo.h (DERIVED API; the upstream repository has
 // no code to mirror — /root/reference/README.md:1-2).
+#include "compact.cuh"
 #include "table.h"
 
 #include <cstdio>
@@ -28,6 +29,63 @@ meepo_status Workspace::reserve(size_t need, cudaStream_t stream) {
   size_t want = need + need / 4;
   MEEPO_CUDA_TRY(cudaMalloc(&base, want));
   bytes = want;
+  return MEEPO_OK;
+}
+
+CompactState compact_carve(char* p, uint32_t* error) {
+  CompactState cs;
+  cs.ticket = reinterpret_cast<uint32_t*>(p);
+  cs.state = reinterpret_cast<unsigned long long*>(p + 8);
+  cs.error = error;
+  return cs;
+}
+
+meepo_status sticky_error(meepo_table* t) {
+  if (!t->err_host) return MEEPO_OK;
+  if (t->err_host[kErrLookback])
+    return fail(MEEPO_ECUDA, "a look-back (radix sort / compaction) gave up waiting for a tile; the table may be corrupt");
+  if (t->err_host[kErrPeerTimeout])
+    return fail(MEEPO_ENCCL, "sharded verb: a peer did not reach the barrier (timeout)");
+  if (t->err_host[kErrPeerOverflow])
+    return fail(MEEPO_ENCCL, "sharded verb: more keys for one owner than region_keys; results are incomplete");
+  return MEEPO_OK;
+}
+
+meepo_status verb_begin(meepo_table* t, cudaStream_t stream) {
+  MEEPO_TRY(sticky_error(t));
+  if (t->order_valid && stream != t->last_stream) MEEPO_CUDA_TRY(cudaStreamWaitEvent(stream, t->order_ev, 0));
+  return MEEPO_OK;
+}
+void verb_end(meepo_table* t, cudaStream_t stream) {
+  if (cudaEventRecord(t->order_ev, stream) == cudaSuccess) {
+    t->last_stream = stream;
+    t->order_valid = true;
+  }
+}
+
+// meepo_stats: how far from home the live keys sit (one pass over the bucket array)
+__global__ void __launch_bounds__(256) probe_hist_kernel(TableView t, unsigned long long* __restrict__ hist) {
+  uint32_t c[4] = {0, 0, 0, 0};
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < t.slots; s += gridDim.x * blockDim.x) {
+    const uint64_t key = *key_ptr(t, s);
+    if (key == MEEPO_KEY_EMPTY) continue;
+    const uint32_t b = s / kBucket, home = bucket_of(mix64(key), t.num_buckets);
+    const uint32_t d = b >= home ? b - home : b + t.num_buckets - home;
+    c[d < 3 ? d : 3]++;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    c[i] = __reduce_add_sync(0xFFFFFFFFu, c[i]);
+    if ((threadIdx.x & 31u) == 0 && c[i]) atomicAdd(hist + i, (unsigned long long)c[i]);
+  }
+}
+meepo_status probe_histogram(meepo_table* t, uint64_t* out4) {
+  unsigned long long* d = t->dstate->hist;
+  MEEPO_CUDA_TRY(cudaMemset(d, 0, 4 * 8));
+  const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(((uint64_t)t->v.slots + 255) / 256, (uint64_t)t->num_sms * 8));
+  probe_hist_kernel<<<grid, 256>>>(t->v, d);
+  MEEPO_CUDA_TRY(cudaGetLastError());
+  MEEPO_CUDA_TRY(cudaMemcpy(out4, d, 4 * 8, cudaMemcpyDeviceToHost));
   return MEEPO_OK;
 }
 
@@ -123,6 +181,18 @@ MEEPO_API meepo_status meepo_create(const meepo_config* cfg, meepo_table** out) 
   if (v.scores && (e = cudaMemset(v.scores, 0, slots * 8)) != cudaSuccess) return bail(e, "memset");
   if (v.steps && (e = cudaMemset(v.steps, 0, slots * 4)) != cudaSuccess) return bail(e, "memset");
   if ((e = cudaMemset(t->dstate, 0, sizeof(DeviceState))) != cudaSuccess) return bail(e, "memset");
+  {
+    void* eh = nullptr;
+    if ((e = cudaHostAlloc(&eh, kErrWords * 4, cudaHostAllocMapped | cudaHostAllocPortable)) != cudaSuccess)
+      return bail(e, "cudaHostAlloc(error words)");
+    memset(eh, 0, kErrWords * 4);
+    t->err_host = reinterpret_cast<volatile uint32_t*>(eh);
+    void* ed = nullptr;
+    if ((e = cudaHostGetDevicePointer(&ed, eh, 0)) != cudaSuccess) return bail(e, "cudaHostGetDevicePointer");
+    t->err_word = reinterpret_cast<uint32_t*>(ed);
+    if ((e = cudaEventCreateWithFlags(&t->order_ev, cudaEventDisableTiming)) != cudaSuccess)
+      return bail(e, "cudaEventCreate");
+  }
   if (cfg->host_spill_bytes) {
     t->spill_cap_tuples = cfg->host_spill_bytes / t->tuple_bytes();
     if (t->spill_cap_tuples) {
@@ -155,6 +225,8 @@ MEEPO_API meepo_status meepo_destroy(meepo_table* t) {
   cudaFree(t->cache.keys);
   cudaFree(t->cache.slots);
   if (t->spill_ring) cudaFreeHost(t->spill_ring);
+  if (t->err_host) cudaFreeHost(const_cast<uint32_t*>(t->err_host));
+  if (t->order_ev) cudaEventDestroy(t->order_ev);
   delete t;
   return MEEPO_OK;
 }
@@ -183,10 +255,8 @@ MEEPO_API meepo_status meepo_stats(meepo_table* t, meepo_stats_t* out) {
   out->epoch = t->epoch;
   out->row_bytes = t->row_bytes;
   out->state_bytes = t->state_bytes;
-  uint32_t sort_err = 0;
-  MEEPO_CUDA_TRY(cudaMemcpy(&sort_err, &t->dstate->pad[0], 4, cudaMemcpyDeviceToHost));
-  if (sort_err) return fail(MEEPO_ECUDA, "radix sort: look-back gave up waiting for a tile; results are wrong");
-  return peer_error_check(t);
+  MEEPO_TRY(probe_histogram(t, out->probe_hist));
+  return sticky_error(t);
 }
 
 }  // extern "C"

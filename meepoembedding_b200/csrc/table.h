@@ -52,7 +52,7 @@ struct DeviceState {
   uint32_t num_segments;   // apply_gradients scratch
   uint32_t num_long, num_leaves;
   uint32_t evict_count;
-  uint32_t pad[2];         // pad[0]: sticky "radix sort gave up waiting for a tile" flag
+  uint32_t pad[2];
   unsigned long long scratch64[8];
   unsigned long long hist[256];  // evict: radix-select histogram
 };
@@ -231,6 +231,16 @@ struct meepo_table {
   meepo::SlotCache cache{nullptr, nullptr};
   uint64_t cache_cap = 0, cache_n = 0, cache_off = 0;
   bool cache_valid = false, cache_enabled = true;
+  // Sticky device-side errors, in mapped pinned host memory so that every verb can test them without a
+  // synchronisation: [0] a look-back (radix sort / compaction) gave up waiting for a tile, [1] a peer missed a
+  // barrier, [2] a (sender, owner) lane of the exchange window overflowed. Kernels only ever store 1.
+  volatile uint32_t* err_host = nullptr;
+  uint32_t* err_word = nullptr;  // the same words as the device sees them
+  // Verbs of one table may be issued on different streams: each verb's stream first waits for the event the
+  // previous verb recorded (workspace, slot cache and scratch counters are shared by all verbs of a table).
+  cudaEvent_t order_ev = nullptr;
+  cudaStream_t last_stream = nullptr;
+  bool order_valid = false;
   uint64_t slot_gen = 0;  // bumped whenever slots may change owners outside the sharded verbs (evict, import, ...)
   uint64_t epoch = 0;
   struct meepo::Profiler* prof = nullptr;  // per-kernel event timing, off unless enabled
@@ -264,6 +274,24 @@ struct DeviceGuard {
   int want;
 };
 
+// Every verb: fail fast on a sticky device-side error, order after the previous verb of this table.
+meepo_status verb_begin(meepo_table* t, cudaStream_t stream);
+void verb_end(meepo_table* t, cudaStream_t stream);
+struct VerbScope {
+  meepo_table* t;
+  cudaStream_t s;
+  meepo_status rc;
+  VerbScope(meepo_table* t_, cudaStream_t s_) : t(t_), s(s_), rc(verb_begin(t_, s_)) {}
+  ~VerbScope() {
+    if (rc == MEEPO_OK) verb_end(t, s);
+  }
+};
+enum : int { kErrLookback = 0, kErrPeerTimeout = 1, kErrPeerOverflow = 2, kErrWords = 4 };
+meepo_status sticky_error(meepo_table* t);
+meepo_status probe_histogram(meepo_table* t, uint64_t* out4);
+struct CompactState;
+CompactState compact_carve(char* p, uint32_t* error);
+
 // kernels' host launchers (defined across the .cu files)
 meepo_status launch_probe_gather(meepo_table* t, const uint64_t* keys, uint64_t n, void* rows_out,
                                  uint8_t* status_out, bool insert, cudaStream_t stream);
@@ -277,12 +305,12 @@ meepo_status launch_apply_gradients(meepo_table* t, const uint64_t* keys, const 
                                     cudaStream_t stream, cudaEvent_t grads_ready = nullptr);
 // Scratch of one sort + segment + reduce pipeline (update.cu); carved out of the table workspace.
 struct SegWork {
-  uint32_t *sk_in, *sk_out, *sv_in, *sv_out, *tile_count, *tile_off, *seg_start;
-  char *cub_tmp, *long_seg;
+  uint32_t *sk_in, *sk_out, *sv_in, *sv_out, *seg_start;
+  char *cub_tmp, *long_seg, *cstate;  // cstate: ticket + per-tile look-back words of the segment-head compaction
   uint2* leaf_desc;
   uint4* seg_desc;
   float* partial;
-  size_t cub_bytes, max_long, max_leaves;
+  size_t cub_bytes, max_long, max_leaves, cstate_bytes;
   uint32_t n, ntiles;
   int end_bit;
   static size_t bytes(uint64_t n, uint32_t dim, int end_bit);
@@ -322,8 +350,6 @@ void destroy_host_pipe(meepo_table* t);
 void destroy_profiler(meepo_table* t);
 void prof_add_host(meepo_table* t, const char* name, double ms);
 void destroy_peer(meepo_table* t);
-// sticky device-side errors of the sharded verbs (barrier timeout, region overflow) -> status
-meepo_status peer_error_check(meepo_table* t);
 // lookup.cu: write the tags of the slots listed in slots[0..n) (kNil cells skipped) and fold their
 // number into the size
 meepo_status publish_slots(meepo_table* t, const uint32_t* slots, uint64_t n, cudaStream_t stream);

@@ -13,6 +13,7 @@
 
 #include <map>
 
+#include "compact.cuh"
 #include "optimizer.cuh"
 #include "table.h"
 
@@ -23,7 +24,6 @@ constexpr uint32_t kLeaf = MEEPO_REDUCE_LEAF;
 // has the same normative order either way): a 256-term chain in one group of lanes is a long
 // latency-bound tail, whereas leaves run one per group with 8 row loads in flight.
 constexpr uint32_t kLongSeg = 32;
-constexpr int kSegTile = 1024;  // sorted positions per CTA in the segment-head passes
 
 struct LongSeg {
   uint32_t seg, base, nleaf, pad;
@@ -57,65 +57,38 @@ __global__ void __launch_bounds__(256) grad_slots_kernel(TableView t, const uint
 }
 
 // ---------------------------------------------------------------------------------------------
-// A3: segment heads of the sorted slot array -> seg_start[0..U] (compaction by a 3-pass scan)
-__device__ __forceinline__ bool is_head(const uint32_t* __restrict__ sk, uint32_t i) {
-  return i == 0 || sk[i] != sk[i - 1];
-}
-
-__global__ void __launch_bounds__(256) seg_count_kernel(const uint32_t* __restrict__ sk, uint32_t n,
-                                                        uint32_t* __restrict__ tile_count) {
-  const uint32_t base = blockIdx.x * kSegTile;
-  int total = 0;
+// A3: segment heads of the sorted slot array -> seg_start[0..U], seg_desc[0..U], U: one ordered
+// compaction pass (compact.cuh). The CTA of the last tile closes the lists, publishes U and resets the
+// long-segment counters.
+__global__ void __launch_bounds__(kCompactThreads) segments_kernel(const uint32_t* __restrict__ sk,
+                                                                   const uint32_t* __restrict__ sv, uint32_t n,
+                                                                   uint32_t* __restrict__ seg_start,
+                                                                   uint4* __restrict__ seg_desc, uint32_t miss_key,
+                                                                   DeviceState* ds, int count_updates,
+                                                                   CompactState cs) {
+  CompactTile ct = compact_begin(cs, n);
+  unsigned flags = 0;
+  uint32_t key[kCompactItems];
 #pragma unroll
-  for (int k = 0; k < kSegTile / 256; k++) {
-    const uint32_t i = base + k * 256 + threadIdx.x;
-    total += __syncthreads_count(i < n && is_head(sk, i));
-  }
-  if (threadIdx.x == 0) tile_count[blockIdx.x] = (uint32_t)total;
-}
-
-// single CTA: exclusive scan of tile counts; publishes U and resets the long-segment counters
-__global__ void __launch_bounds__(1024) seg_scan_kernel(const uint32_t* __restrict__ tile_count,
-                                                        uint32_t ntiles, uint32_t* __restrict__ tile_off,
-                                                        uint32_t* __restrict__ seg_start,
-                                                        uint4* __restrict__ seg_desc, uint32_t n,
-                                                        const uint32_t* __restrict__ sk, uint32_t miss_key,
-                                                        DeviceState* ds, int count_updates) {
-  __shared__ uint32_t warp_sum[32];
-  __shared__ uint32_t carry_s;
-  if (threadIdx.x == 0) carry_s = 0;
-  __syncthreads();
-  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (uint32_t base = 0; base < ntiles; base += 1024) {
-    const uint32_t i = base + threadIdx.x;
-    const uint32_t v = i < ntiles ? tile_count[i] : 0;
-    uint32_t x = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
-      if (lane >= d) x += y;
+  for (int k = 0; k < kCompactItems; k++) {
+    const uint64_t i = ct.pos(k);
+    key[k] = 0;
+    if (i < n) {
+      key[k] = sk[i];
+      if (i == 0 || sk[i - 1] != key[k]) flags |= 1u << k;
     }
-    if (lane == 31) warp_sum[w] = x;
-    __syncthreads();
-    if (w == 0) {
-      uint32_t s = warp_sum[lane];
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        uint32_t y = __shfl_up_sync(0xFFFFFFFFu, s, d);
-        if (lane >= d) s += y;
-      }
-      warp_sum[lane] = s;  // inclusive over warps
-    }
-    __syncthreads();
-    const uint32_t carry = carry_s;
-    const uint32_t incl = x + (w ? warp_sum[w - 1] : 0);
-    if (i < ntiles) tile_off[i] = carry + incl - v;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry_s = carry + incl;
-    __syncthreads();
   }
-  if (threadIdx.x == 0) {
-    const uint32_t U = carry_s;
+  compact_rank(ct, flags, cs);
+#pragma unroll
+  for (int k = 0; k < kCompactItems; k++) {
+    if ((flags >> k) & 1u) {
+      const uint32_t i = (uint32_t)ct.pos(k), u = (uint32_t)ct.rank(k);
+      seg_start[u] = i;
+      seg_desc[u] = make_uint4(i, key[k], sv[i], 0);  // {first sorted position, sort key, first batch index}
+    }
+  }
+  if (ct.last && threadIdx.x == 0) {
+    const uint32_t U = (uint32_t)ct.base + ct.tile_total;
     seg_start[U] = n;
     seg_desc[U] = make_uint4(n, kNil, 0, 0);
     ds->num_segments = U;
@@ -125,40 +98,6 @@ __global__ void __launch_bounds__(1024) seg_scan_kernel(const uint32_t* __restri
     if (applied && count_updates) atomicAdd(ds->counters + C_UPDATES, (unsigned long long)applied);
   }
 }
-
-__global__ void __launch_bounds__(256) seg_fill_kernel(const uint32_t* __restrict__ sk, uint32_t n,
-                                                       const uint32_t* __restrict__ sv,
-                                                       const uint32_t* __restrict__ tile_off,
-                                                       uint32_t* __restrict__ seg_start,
-                                                       uint4* __restrict__ seg_desc) {
-  __shared__ uint32_t warp_cnt[8];
-  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  uint32_t running = tile_off[blockIdx.x];
-  const uint32_t base = blockIdx.x * kSegTile;
-#pragma unroll 1
-  for (int k = 0; k < kSegTile / 256; k++) {
-    const uint32_t i = base + k * 256 + threadIdx.x;
-    const bool head = i < n && is_head(sk, i);
-    const unsigned m = __ballot_sync(0xFFFFFFFFu, head);
-    if (lane == 0) warp_cnt[w] = __popc(m);
-    __syncthreads();
-    uint32_t before = 0, total = 0;
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-      const uint32_t c = warp_cnt[j];
-      before += j < (int)w ? c : 0;
-      total += c;
-    }
-    if (head) {
-      const uint32_t u = running + before + __popc(m & ((1u << lane) - 1u));
-      seg_start[u] = i;
-      seg_desc[u] = make_uint4(i, sk[i], sv[i], 0);  // {first sorted position, sort key, first batch index}
-    }
-    running += total;
-    __syncthreads();
-  }
-}
-
 
 template <bool BF16, int UNROLL = 4>
 __device__ __forceinline__ void reduce_tail(const uint4* __restrict__ grads, const uint32_t* __restrict__ sidx,
@@ -545,9 +484,8 @@ size_t SegWork::bytes(uint64_t n, uint32_t dim, int end_bit_) {
   cub::DeviceRadixSort::SortPairs(nullptr, cub, (const uint32_t*)nullptr, (uint32_t*)nullptr,
                                   (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n, 0, end_bit_);
   if (radix_sort_supported(n, end_bit_)) cub = std::max(cub, radix_sort_temp_bytes(n, end_bit_));
-  const size_t ntiles_ = (n + kSegTile - 1) / kSegTile;
   const size_t max_long_ = n / (kLongSeg + 1) + 1, max_leaves_ = n / kLongSeg + 2;
-  return 4 * Workspace::pad(n * 4) + Workspace::pad(cub) + 2 * Workspace::pad(ntiles_ * 4) +
+  return 4 * Workspace::pad(n * 4) + Workspace::pad(cub) + Workspace::pad(compact_state_bytes(n)) +
          Workspace::pad((n + 2) * 4) + Workspace::pad((n + 2) * 16) + Workspace::pad(max_long_ * sizeof(LongSeg)) +
          Workspace::pad(max_leaves_ * 8) + Workspace::pad(max_leaves_ * dim * 4) + 4096;
 }
@@ -559,7 +497,7 @@ void SegWork::take(Workspace& ws, uint64_t n_, uint32_t dim, int end_bit_) {
   cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
                                   (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n, 0, end_bit);
   if (radix_sort_supported(n_, end_bit)) cub_bytes = std::max(cub_bytes, radix_sort_temp_bytes(n_, end_bit));
-  ntiles = (n + kSegTile - 1) / kSegTile;
+  ntiles = compact_tiles(n_);
   max_long = n_ / (kLongSeg + 1) + 1;
   max_leaves = n_ / kLongSeg + 2;
   sk_in = ws.take<uint32_t>(n_);
@@ -567,8 +505,8 @@ void SegWork::take(Workspace& ws, uint64_t n_, uint32_t dim, int end_bit_) {
   sv_in = ws.take<uint32_t>(n_);
   sv_out = ws.take<uint32_t>(n_);
   cub_tmp = ws.take<char>(cub_bytes);
-  tile_count = ws.take<uint32_t>(ntiles);
-  tile_off = ws.take<uint32_t>(ntiles);
+  cstate_bytes = compact_state_bytes(n_);
+  cstate = ws.take<char>(cstate_bytes);
   seg_start = ws.take<uint32_t>(n_ + 2);
   seg_desc = ws.take<uint4>(n_ + 2);
   long_seg = ws.take<char>(max_long * sizeof(LongSeg));
@@ -609,10 +547,10 @@ meepo_status run_segmented(meepo_table* t, SegWork& w, uint32_t limit, const voi
   }
   {
     ProfScope ps(t, names[1], stream);
-    seg_count_kernel<<<w.ntiles, 256, 0, stream>>>(w.sk_out, n32, w.tile_count);
-    seg_scan_kernel<<<1, 1024, 0, stream>>>(w.tile_count, w.ntiles, w.tile_off, w.seg_start, w.seg_desc, n32, w.sk_out,
-                                            limit, t->dstate, mode != kStoreOnly);
-    seg_fill_kernel<<<w.ntiles, 256, 0, stream>>>(w.sk_out, n32, w.sv_out, w.tile_off, w.seg_start, w.seg_desc);
+    MEEPO_CUDA_TRY(cudaMemsetAsync(w.cstate, 0, w.cstate_bytes, stream));
+    segments_kernel<<<w.ntiles, kCompactThreads, 0, stream>>>(w.sk_out, w.sv_out, n32, w.seg_start, w.seg_desc, limit,
+                                                              t->dstate, mode != kStoreOnly,
+                                                              compact_carve(w.cstate, t->err_word + kErrLookback));
     MEEPO_CUDA_TRY(cudaGetLastError());
   }
   ApplyArgs a;
@@ -684,7 +622,7 @@ meepo_status launch_apply_gradients(meepo_table* t, const uint64_t* keys, const 
     grad_slots_kernel<<<grid, 256, 0, stream>>>(t->v, keys, (uint32_t)n, w.sk_in, w.sv_in, t->cache, cache_n);
     MEEPO_CUDA_TRY(cudaGetLastError());
   }
-  static const char* const names[5] = {"apply.radix_sort", "apply.segments(3 kernels)",
+  static const char* const names[5] = {"apply.radix_sort", "apply.segments",
                                        "apply.reduce_optimizer", "apply.long_leaves", "apply.long_finish"};
   return run_segmented(t, w, t->v.slots, grads, t->v.opt, nullptr, stream, grads_ready, names);
 }
@@ -699,5 +637,7 @@ extern "C" MEEPO_API meepo_status meepo_apply_gradients(meepo_table* t, const ui
   if (n > 0xFFFFFFFFull) return fail(MEEPO_EINVAL, "batch too large (n must fit in 32 bits)");
   if (n && (!keys || !grads)) return fail(MEEPO_EINVAL, "null buffer");
   DeviceGuard guard(t->device);
+  VerbScope vs(t, (cudaStream_t)stream);
+  MEEPO_TRY(vs.rc);
   return launch_apply_gradients(t, keys, grads, n, (cudaStream_t)stream);
 }

@@ -206,6 +206,30 @@ class Table:
             rc = self.lib.apply_gradients(self._h, _ptr(keys), _ptr(grads), n, stream)
         self.lib.check(rc)
 
+    # -- asynchronous host verbs (numpy buffers; include/meepo.h "Asynchronous forms") ----------
+    def find_or_insert_async(self, keys, rows_out, status_out=None, n=None) -> int:
+        """Enqueue; returns a ticket. The buffers must stay alive and untouched until wait(ticket)."""
+        tk = C.c_uint64(0)
+        self.lib.check(self.lib.find_or_insert_host_async(self._h, _ptr(keys), self._n(keys, n), _ptr(rows_out),
+                                                          _ptr(status_out), C.byref(tk)))
+        return int(tk.value)
+
+    def lookup_async(self, keys, rows_out, found_out=None, n=None) -> int:
+        tk = C.c_uint64(0)
+        self.lib.check(self.lib.lookup_host_async(self._h, _ptr(keys), self._n(keys, n), _ptr(rows_out),
+                                                  _ptr(found_out), C.byref(tk)))
+        return int(tk.value)
+
+    def apply_gradients_async(self, keys, grads, n=None) -> int:
+        tk = C.c_uint64(0)
+        self.lib.check(self.lib.apply_gradients_host_async(self._h, _ptr(keys), _ptr(grads), self._n(keys, n),
+                                                           C.byref(tk)))
+        return int(tk.value)
+
+    def wait(self, ticket: int = 0):
+        """Block until `ticket` is complete (0 = everything issued so far)."""
+        self.lib.check(self.lib.wait(self._h, int(ticket)))
+
     # -- capacity management ----------------------------------------------------
     def evict(self, policy: str = "lfu", target_load: float = 0.8, stream=None) -> int:
         out = C.c_uint64(0)
