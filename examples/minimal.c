@@ -48,6 +48,13 @@ int main(void) {
   CHECK(meepo_apply_gradients_host(t, keys, grads, N));         /* duplicates summed, one Adagrad step per key */
   CHECK(meepo_lookup_host(t, keys, N, rows, status));           /* status == MEEPO_KEY_FOUND */
 
+  /* the asynchronous forms: issue, overlap, wait. Two calls in flight execute in issue order. */
+  uint64_t t_rows = 0, t_upd = 0;
+  CHECK(meepo_find_or_insert_host_async(t, keys, N, rows, status, &t_rows));
+  CHECK(meepo_apply_gradients_host_async(t, keys, grads, N, &t_upd));
+  CHECK(meepo_wait(t, t_rows));                                 /* rows/status are valid from here on */
+  CHECK(meepo_wait(t, 0));                                      /* everything issued so far */
+
   uint64_t evicted = 0;
   CHECK(meepo_evict(t, MEEPO_LFU, 0.02, &evicted, NULL));       /* lowest-frequency keys go to the host spill tier */
   CHECK(meepo_spill_readmit(t, keys, 1000, status));            /* ... and come back with row, state and score */

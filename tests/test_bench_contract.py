@@ -23,7 +23,7 @@ def test_reference_arm_line():
     assert line["metric"].startswith("find_or_insert+update keys/s")
     assert line["value"] > 0 and line["steps"] == 2 and line["warmup"] == 1 and line["vs_baseline"] is None
     cb = line["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "authored" in cb["sample"]
+    assert cb["kind"] == "authored" and cb["cores"] >= 1 and cb["value"] == line["value"] and "authored" in cb["sample"]
     assert line["e2e"] == {"value": line["value"], "unit": "keys/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in line["config"] and "model" not in line["config"]
 
