@@ -837,7 +837,7 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    numa_note = pin_to_gpu_numa_node(local_rank) if world > 1 else "single rank: no placement"
+    numa_note = pin_to_gpu_numa_node(local_rank)
     dist_ = None
     if world > 1:
         import torch.distributed as dist_
