@@ -320,9 +320,11 @@ class GpuRun:
                 # one (sender, owner) lane holds the unique keys one rank sends one owner: B/world on average
                 region = min(w["batch"], int(w["batch"] / self.world * 1.25) + 4096)
                 self.sharded = PeerShardedTable(self.table, self.dist_.group.WORLD, dev, max_batch=w["batch"],
-                                                region_keys=region)
+                                                region_keys=region, out_buffers=4)
+                self.next_out = 0
                 self.config["exchange"] = ("fused peer-memory verbs over NVLink (cudaIpc windows, device-side "
-                                           f"barriers, no NCCL on the data path); region_keys={region}")
+                                           f"barriers, no NCCL on the data path); region_keys={region}; rows_out in "
+                                           "the window's output area: owners store rows straight into it")
             else:
                 self.sharded = ShardedTable(self.table, self.dist_.group.WORLD, dev)
                 self.config["exchange"] = "NCCL all_to_all_single (torch.distributed)"
@@ -364,6 +366,9 @@ class GpuRun:
         """Output rows of a forward verb. On the sharded path they live in the table's exchange window when the
         library offers one, so that owners store rows straight into them over NVLink."""
         torch = self.torch
+        if self.sharded is not None and self.args.exchange == "peer" and self.next_out < 4 and not self.args.no_direct:
+            self.next_out += 1
+            return self.sharded.output_buffer(self.next_out - 1, n)
         return torch.empty((n, self.w["dim"]), dtype=self.tdt, device=self.dev)
 
     def step(self, i):
@@ -441,7 +446,7 @@ class GpuRun:
             alg["sharded.owner_find_or_insert"] = kr * (16 + 2 * R)
             alg["sharded.owner_apply"] = gr * R + self.U_avg * (2 * R + 2 * w["dim"] * 4)
             alg["dedup.reduce_store"] = B * R + gr * R  # reads every gradient row, stores the unique sums to the owners
-            alg["sharded.expand"] = B * 2 * R
+            alg["sharded.finish(expand)"] = B * 2 * R
         kernels = {}
         for name, (cnt, ms) in self.prof.items():
             avg = ms / max(cnt, 1)
@@ -775,6 +780,8 @@ def main():
                     help="override a workload field (experiments), e.g. --set track_scores=False")
     ap.add_argument("--force-sharded", action="store_true",
                     help="N=1 only: run the step through the sharded peer-memory verbs (world 1) — profiling aid")
+    ap.add_argument("--no-direct", action="store_true",
+                    help="sharded: plain output tensors instead of the exchange window's output buffers")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N>1: fused peer-memory verbs (csrc/peer.cu) or the NCCL all-to-all composition")
     args = ap.parse_args()

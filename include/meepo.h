@@ -310,8 +310,8 @@ MEEPO_API meepo_status meepo_gather_rows(meepo_table* t, const void* rows_in, co
  * One table per GPU (one process per GPU, or several tables driven by one
  * process), rank r owns the keys with meepo_owner(key, world) == r. Set-up:
  *   1. every rank: meepo_peer_prepare(t, rank, world, max_batch, region_keys,
- *      blob) allocates this rank's exchange window and fills `blob`
- *      (MEEPO_PEER_BLOB_BYTES, opaque; carries a CUDA IPC handle);
+ *      out_buffers, blob) allocates this rank's exchange window and fills
+ *      `blob` (MEEPO_PEER_BLOB_BYTES, opaque; carries a CUDA IPC handle);
  *   2. the caller all-gathers the blobs (any transport; they are plain bytes);
  *   3. every rank: meepo_peer_attach(t, blobs) with the world blobs in rank
  *      order maps the peers' windows.
@@ -329,7 +329,17 @@ MEEPO_API meepo_status meepo_gather_rows(meepo_table* t, const void* rows_in, co
  *                keys; 0 = max_batch (always sufficient). A smaller value
  *                (e.g. 1.25 * max_batch / world) saves window memory
  *                (2 * world * region_keys * row_bytes); exceeding it is
- *                reported by meepo_stats as MEEPO_ENCCL, never a memory error.
+ *                reported by meepo_stats (and by every following verb) as
+ *                MEEPO_ENCCL, never a memory error.
+ *   out_buffers  number of OUTPUT BUFFERS (max_batch rows each) to place inside
+ *                the window; meepo_peer_output(t, i, &ptr, &rows) returns the
+ *                i-th. A sharded find_or_insert / lookup whose rows_out lies in
+ *                one of them has the owners store every row straight into it
+ *                over NVLink (one row per unique key, at one of the key's
+ *                occurrences; the other occurrences are filled by a local copy)
+ *                instead of going through a return region and a full expansion
+ *                pass. Any other rows_out works too, just slower. Results are
+ *                identical either way.
  * A rank that does not reach a barrier within MEEPO_PEER_TIMEOUT_MS (env,
  * default 20000) makes its peers give up and report MEEPO_ENCCL from
  * meepo_stats instead of hanging the GPU. All ranks must have finished (e.g. a
@@ -338,7 +348,8 @@ MEEPO_API meepo_status meepo_gather_rows(meepo_table* t, const void* rows_in, co
  * checker for the sharded verbs is ONE oracle table fed the concatenated
  * batches (tests/test_gpu_peer.py). */
 MEEPO_API meepo_status meepo_peer_prepare(meepo_table* t, uint32_t rank, uint32_t world, uint64_t max_batch,
-                                          uint64_t region_keys, void* blob_out);
+                                          uint64_t region_keys, uint32_t out_buffers, void* blob_out);
+MEEPO_API meepo_status meepo_peer_output(meepo_table* t, uint32_t index, void** rows_out, uint64_t* max_rows);
 MEEPO_API meepo_status meepo_peer_attach(meepo_table* t, const void* blobs);
 MEEPO_API meepo_status meepo_peer_detach(meepo_table* t);
 MEEPO_API meepo_status meepo_sharded_find_or_insert(meepo_table* t, const uint64_t* keys, uint64_t n,

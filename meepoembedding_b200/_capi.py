@@ -114,7 +114,8 @@ SIGNATURES = {
     "meepo_shard_partition": (C.c_int, [_P, _P, _U64, _U32, _P, _P, _P, _P]),
     "meepo_reduce_duplicates": (C.c_int, [_P, _P, _P, _U64, _P, _P, _P, _P, _P]),
     "meepo_gather_rows": (C.c_int, [_P, _P, _P, _U64, _P, _P]),
-    "meepo_peer_prepare": (C.c_int, [_P, _U32, _U32, _U64, _U64, _P]),
+    "meepo_peer_prepare": (C.c_int, [_P, _U32, _U32, _U64, _U64, _U32, _P]),
+    "meepo_peer_output": (C.c_int, [_P, _U32, C.POINTER(_P), C.POINTER(_U64)]),
     "meepo_peer_attach": (C.c_int, [_P, _P]),
     "meepo_peer_detach": (C.c_int, [_P]),
     "meepo_sharded_find_or_insert": (C.c_int, [_P, _P, _U64, _P, _P, _P]),

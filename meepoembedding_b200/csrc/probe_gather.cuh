@@ -17,29 +17,42 @@
 
 namespace meepo {
 
-template <int CPR>
+// SCATTER: the rows of a tile do not go to one contiguous block but each to its own destination: lane j
+// holds the address of key j's output row in `dst` (the sharded owner stores rows straight into the
+// requester's output tensor, one row per unique key, wherever that key first occurs in the batch).
+template <bool SCATTER>
+__device__ __forceinline__ uint4* tile_dst(uint4* __restrict__ out_tile, unsigned long long dst, uint32_t j,
+                                           uint32_t off, uint32_t c) {
+  if constexpr (SCATTER)
+    return reinterpret_cast<uint4*>(__shfl_sync(0xFFFFFFFFu, dst, j)) + off;
+  else
+    return out_tile + c;
+}
+
+template <int CPR, bool SCATTER = false>
 __device__ __forceinline__ void gather_tile_fast(const TableView& t, uint32_t slot, uint32_t tile_keys,
-                                                 uint4* __restrict__ out_tile, uint32_t lane) {
+                                                 uint4* __restrict__ out_tile, uint32_t lane,
+                                                 unsigned long long dst = 0) {
   constexpr int UNROLL = CPR >= 8 ? 8 : CPR;
   // chunk c = it*32 + lane; key j = c / CPR; offset = c % CPR
 #pragma unroll 1
   for (int it0 = 0; it0 < CPR; it0 += UNROLL) {
     uint4 v[UNROLL];
     uint32_t jj[UNROLL];
+    uint4* dd[UNROLL];
 #pragma unroll
     for (int u = 0; u < UNROLL; u++) {
       const uint32_t c = (uint32_t)(it0 + u) * 32u + lane;
       const uint32_t j = c / CPR, off = c % CPR;
       const uint32_t s = __shfl_sync(0xFFFFFFFFu, slot, j);
+      dd[u] = tile_dst<SCATTER>(out_tile, dst, j, off, c);
       jj[u] = j;
       v[u] = make_uint4(0, 0, 0, 0);
       if (s != kNil) v[u] = ld_stream(t.rows + (size_t)s * CPR + off);
     }
 #pragma unroll
-    for (int u = 0; u < UNROLL; u++) {
-      const uint32_t c = (uint32_t)(it0 + u) * 32u + lane;
-      if (jj[u] < tile_keys) st_stream(out_tile + c, v[u]);
-    }
+    for (int u = 0; u < UNROLL; u++)
+      if (jj[u] < tile_keys) st_stream(dd[u], v[u]);
   }
 }
 
@@ -47,9 +60,9 @@ __device__ __forceinline__ void gather_tile_fast(const TableView& t, uint32_t sl
 // masked out there): one key at a time, the lanes cover its chunks. A chunk of a new row is computed
 // (init_chunk is a pure function of key and column), never loaded; the CAS winner also writes it —
 // and the initial optimizer state — to the arenas.
-template <int CPR>
+template <int CPR, bool SCATTER = false>
 __device__ __forceinline__ void fixup_fresh(const TableView& t, uint64_t key, const Probe& pr, uint32_t tile_keys,
-                                            uint4* __restrict__ out_tile, uint32_t lane) {
+                                            uint4* __restrict__ out_tile, uint32_t lane, unsigned long long dst = 0) {
   unsigned m = __ballot_sync(0xFFFFFFFFu, pr.status == MEEPO_KEY_INSERTED);
   while (m) {
     const int j = __ffs(m) - 1;
@@ -57,11 +70,13 @@ __device__ __forceinline__ void fixup_fresh(const TableView& t, uint64_t key, co
     const uint32_t s = __shfl_sync(0xFFFFFFFFu, pr.slot, j);
     const bool win = __shfl_sync(0xFFFFFFFFu, (int)pr.winner, j);
     const uint64_t kj = __shfl_sync(0xFFFFFFFFu, key, j);
+    uint4* orow = out_tile + (size_t)j * CPR;
+    if constexpr (SCATTER) orow = reinterpret_cast<uint4*>(__shfl_sync(0xFFFFFFFFu, dst, j));
     if ((uint32_t)j >= tile_keys) continue;
     for (uint32_t off = lane; off < (uint32_t)CPR; off += 32) {
       const uint4 v = init_chunk(t, kj, off);
       if (win) t.rows[(size_t)s * CPR + off] = v;
-      st_stream(out_tile + (size_t)j * CPR + off, v);
+      st_stream(orow + off, v);
     }
     if (win) {
       const uint4 sv = init_state_chunk(t);
@@ -71,15 +86,18 @@ __device__ __forceinline__ void fixup_fresh(const TableView& t, uint64_t key, co
 }
 
 // Generic-width version (any cpr): the fallback for row widths without a specialised kernel.
+template <bool SCATTER = false>
 __device__ __forceinline__ void gather_tile_slow(const TableView& t, uint64_t key, const Probe& pr,
                                                  uint32_t tile_keys, uint4* __restrict__ out_tile,
-                                                 uint32_t lane) {
+                                                 uint32_t lane, unsigned long long dst = 0) {
   const uint32_t cpr = t.cpr;
   for (uint32_t j = 0; j < tile_keys; j++) {
     const uint32_t s = __shfl_sync(0xFFFFFFFFu, pr.slot, j);
     const uint32_t st = __shfl_sync(0xFFFFFFFFu, pr.status, j);
     const bool win = __shfl_sync(0xFFFFFFFFu, (int)pr.winner, j);
     const uint64_t kj = __shfl_sync(0xFFFFFFFFu, key, j);
+    uint4* orow = out_tile + (size_t)j * cpr;
+    if constexpr (SCATTER) orow = reinterpret_cast<uint4*>(__shfl_sync(0xFFFFFFFFu, dst, j));
     for (uint32_t off = lane; off < cpr; off += 32) {
       uint4 v = make_uint4(0, 0, 0, 0);
       if (st == MEEPO_KEY_INSERTED) {
@@ -88,7 +106,7 @@ __device__ __forceinline__ void gather_tile_slow(const TableView& t, uint64_t ke
       } else if (s != kNil) {
         v = ld_stream(t.rows + (size_t)s * cpr + off);
       }
-      st_stream(out_tile + (size_t)j * cpr + off, v);
+      st_stream(orow + off, v);
     }
     if (win) {
       const uint4 sv = init_state_chunk(t);
@@ -147,12 +165,13 @@ static_assert(kScoreCells == 1u << 9, "score_cache_add hashes to 9 bits");
 // output cells (may be null; new_out = this element's cell of the NewList). occurrences = how many batch occurrences this key stands for (1, or
 // the sender's duplicate count on the sharded path): added to the hit/miss counters and to the key's
 // LFU score.
-template <int CPR, bool INSERT>
+// SCATTER: out_tile is ignored, this lane's row goes to (uint4*)dst (see tile_dst).
+template <int CPR, bool INSERT, bool SCATTER = false>
 __device__ __forceinline__ void probe_gather_tile(const TableView& t, uint64_t key, bool valid, uint32_t tile_keys,
                                                   uint4* __restrict__ out_tile, uint8_t* status_out,
                                                   uint32_t* slot_out, uint64_t* key_out, uint32_t occurrences,
                                                   uint32_t* new_out, TileCounts& cnt, const ScoreCache& sc,
-                                                  uint32_t lane) {
+                                                  uint32_t lane, unsigned long long dst = 0) {
   Probe pr{kNil, MEEPO_KEY_INVALID, false};
   if (INSERT) {
     pr = probe_find_or_insert(t, key);
@@ -181,10 +200,11 @@ __device__ __forceinline__ void probe_gather_tile(const TableView& t, uint64_t k
     fresh = __any_sync(0xFFFFFFFFu, pr.status == MEEPO_KEY_INSERTED);
   }
   if (CPR > 0) {
-    gather_tile_fast<(CPR > 0 ? CPR : 1)>(t, pr.status == MEEPO_KEY_INSERTED ? kNil : pr.slot, tile_keys, out_tile, lane);
-    if (fresh) fixup_fresh<(CPR > 0 ? CPR : 1)>(t, key, pr, tile_keys, out_tile, lane);
+    gather_tile_fast<(CPR > 0 ? CPR : 1), SCATTER>(t, pr.status == MEEPO_KEY_INSERTED ? kNil : pr.slot, tile_keys,
+                                                   out_tile, lane, dst);
+    if (fresh) fixup_fresh<(CPR > 0 ? CPR : 1), SCATTER>(t, key, pr, tile_keys, out_tile, lane, dst);
   } else {
-    gather_tile_slow(t, key, pr, tile_keys, out_tile, lane);
+    gather_tile_slow<SCATTER>(t, key, pr, tile_keys, out_tile, lane, dst);
   }
 }
 

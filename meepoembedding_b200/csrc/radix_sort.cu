@@ -35,10 +35,11 @@ struct RsTemp {
 
 // Digit counts of every pass in one read of the keys (16-byte loads). The last block to finish turns
 // the counts into exclusive bin bases in place, which saves a launch.
-__global__ void __launch_bounds__(256) rs_hist_kernel(const uint32_t* __restrict__ keys, uint32_t n, int passes,
-                                                      int end_bit, uint32_t* __restrict__ hist,
-                                                      uint32_t* __restrict__ blocks_done) {
+__global__ void __launch_bounds__(256) rs_hist_kernel(const uint32_t* __restrict__ keys, uint32_t n,
+                                                      const uint32_t* __restrict__ n_dev, int passes, int end_bit,
+                                                      uint32_t* __restrict__ hist, uint32_t* __restrict__ blocks_done) {
   __shared__ uint32_t sh[4][256];
+  if (n_dev) n = min(n, __ldg(n_dev));  // the host only knows an upper bound
   __shared__ uint32_t warp_tot[8];
   __shared__ bool last;
   for (int p = 0; p < passes; p++) sh[p][threadIdx.x] = 0;
@@ -106,7 +107,8 @@ __device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
 __global__ void __launch_bounds__(kRsThreads, 4) rs_onesweep_kernel(const uint32_t* __restrict__ k_in,
                                                                     const uint32_t* __restrict__ v_in,
                                                                     uint32_t* __restrict__ k_out,
-                                                                    uint32_t* __restrict__ v_out, uint32_t n, int shift,
+                                                                    uint32_t* __restrict__ v_out, uint32_t n,
+                                                                    const uint32_t* __restrict__ n_dev, int shift,
                                                                     int bits, uint32_t nsub,
                                                                     const uint32_t* __restrict__ bin_base,
                                                                     uint32_t* __restrict__ tile_counter,
@@ -122,11 +124,15 @@ __global__ void __launch_bounds__(kRsThreads, 4) rs_onesweep_kernel(const uint32
   __shared__ uint32_t s_tile;
   const uint32_t tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
   const uint32_t dmask = (1u << bits) - 1u;
+  if (n_dev) n = min(n, __ldg(n_dev));
+  // ranges are handed out in order, so the CTAs past the end (grid sized for the host's upper bound) are the
+  // ones nobody waits for: they leave at once
   if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
   s_hist[tid] = 0;
   __syncthreads();
   const uint32_t tile = s_tile;
   const uint32_t range0 = tile * (nsub * kRsTile);
+  if (range0 >= n) return;
   const uint32_t range_n = min(nsub * kRsTile, n - range0);
 
   // A. digit counts of the whole range -> publish -> look back -> global cursor of every digit
@@ -310,8 +316,10 @@ size_t radix_sort_temp_bytes(uint64_t n, int end_bit) {
 }
 
 // (k_in, v_in) -> (k_out, v_out), stable, on key bits [0, end_bit). temp: radix_sort_temp_bytes(), 256-byte aligned.
+// n_dev (optional, device): the true number of pairs, <= n; grids and scratch are sized for n.
 meepo_status radix_sort_pairs(meepo_table* t, char* temp, const uint32_t* k_in, uint32_t* k_out,
-                              const uint32_t* v_in, uint32_t* v_out, uint32_t n, int end_bit, cudaStream_t stream) {
+                              const uint32_t* v_in, uint32_t* v_out, uint32_t n, int end_bit, cudaStream_t stream,
+                              const uint32_t* n_dev) {
   const int passes = (end_bit + 7) / 8;
   const uint32_t nsub = sub_tiles(t, n);
   const uint32_t tiles = (n + nsub * kRsTile - 1) / (nsub * kRsTile);
@@ -320,7 +328,7 @@ meepo_status radix_sort_pairs(meepo_table* t, char* temp, const uint32_t* k_in, 
   // histogram + counters + look-back state are one contiguous zero-filled block
   MEEPO_CUDA_TRY(cudaMemsetAsync(r.hist, 0, (char*)r.k_tmp - (char*)r.hist, stream));
   const int hgrid = (int)std::max<uint64_t>(1, std::min<uint64_t>(((uint64_t)n + 1023) / 1024, (uint64_t)t->num_sms * 4));
-  rs_hist_kernel<<<hgrid, 256, 0, stream>>>(k_in, n, passes, end_bit, r.hist, r.counters + 4);
+  rs_hist_kernel<<<hgrid, 256, 0, stream>>>(k_in, n, n_dev, passes, end_bit, r.hist, r.counters + 4);
   // ping-pong so that the last pass lands in the caller's output arrays
   const uint32_t* src_k = k_in;
   const uint32_t* src_v = v_in;
@@ -329,7 +337,7 @@ meepo_status radix_sort_pairs(meepo_table* t, char* temp, const uint32_t* k_in, 
     uint32_t* dst_k = to_out ? k_out : r.k_tmp;
     uint32_t* dst_v = to_out ? v_out : r.v_tmp;
     const int bits = std::min(8, end_bit - 8 * p);
-    rs_onesweep_kernel<<<tiles, kRsThreads, 0, stream>>>(src_k, src_v, dst_k, dst_v, n, 8 * p, bits, nsub,
+    rs_onesweep_kernel<<<tiles, kRsThreads, 0, stream>>>(src_k, src_v, dst_k, dst_v, n, n_dev, 8 * p, bits, nsub,
                                                          r.hist + p * 256, r.counters + p,
                                                          r.lookback + (size_t)p * lb_stride * 256,
                                                          t->err_word + kErrLookback);
@@ -353,7 +361,7 @@ extern "C" MEEPO_API meepo_status meepo_internal_sort_pairs(meepo_table* t, cons
   cudaStream_t stream = (cudaStream_t)stream_;
   MEEPO_TRY(t->ws.reserve(radix_sort_temp_bytes(n, end_bit), stream));
   char* temp = t->ws.take<char>(radix_sort_temp_bytes(n, end_bit));
-  MEEPO_TRY(radix_sort_pairs(t, temp, k_in, k_out, v_in, v_out, (uint32_t)n, end_bit, stream));
+  MEEPO_TRY(radix_sort_pairs(t, temp, k_in, k_out, v_in, v_out, (uint32_t)n, end_bit, stream, nullptr));
   MEEPO_CUDA_TRY(cudaStreamSynchronize(stream));
   return sticky_error(t);
 }

@@ -84,7 +84,8 @@ __global__ void __launch_bounds__(256) part_scatter_kernel(const uint64_t* __res
 // batch-level dedup
 __global__ void __launch_bounds__(256) dedup_insert_kernel(const uint64_t* __restrict__ keys, uint32_t n,
                                                            uint64_t* __restrict__ scratch, uint32_t mask,
-                                                           uint32_t* __restrict__ pos, const uint32_t* __restrict__ skip) {
+                                                           uint32_t* __restrict__ pos, uint32_t* __restrict__ canon_cell,
+                                                           const uint32_t* __restrict__ skip) {
   if (skip && *skip) return;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint64_t key = __ldg(keys + i);
@@ -97,6 +98,9 @@ __global__ void __launch_bounds__(256) dedup_insert_kernel(const uint64_t* __res
           old = atomicCAS(reinterpret_cast<unsigned long long*>(scratch + h), (unsigned long long)MEEPO_KEY_EMPTY,
                           (unsigned long long)key);
         if (old == MEEPO_KEY_EMPTY || old == key) {
+          // the occurrence whose CAS created the cell is the key's canonical one (where a sharded forward pass
+          // has the owner deliver the row; the other occurrences copy it locally)
+          if (old == MEEPO_KEY_EMPTY && canon_cell) canon_cell[h] = i;
           p = h;
           break;
         }
@@ -111,6 +115,8 @@ __global__ void __launch_bounds__(256) dedup_insert_kernel(const uint64_t* __res
 __global__ void __launch_bounds__(kCompactThreads) occ_compact_kernel(const uint64_t* __restrict__ scratch, uint32_t m,
                                                                       uint32_t* __restrict__ uid_of_slot,
                                                                       uint64_t* __restrict__ unique_out,
+                                                                      const uint32_t* __restrict__ canon_cell,
+                                                                      uint32_t* __restrict__ canon_out,
                                                                       unsigned long long* __restrict__ n_unique,
                                                                       CompactState cs,
                                                                       const uint32_t* __restrict__ skip) {
@@ -131,6 +137,7 @@ __global__ void __launch_bounds__(kCompactThreads) occ_compact_kernel(const uint
       const uint32_t u = (uint32_t)ct.rank(k);
       uid_of_slot[ct.pos(k)] = u;
       unique_out[u] = key[k];
+      if (canon_out) canon_out[u] = canon_cell[ct.pos(k)];
     }
   }
   if (ct.last && threadIdx.x == 0) *n_unique = ct.base + ct.tile_total;
@@ -201,7 +208,7 @@ static uint64_t dedup_cells(uint64_t n) {  // scratch cells: a power of two >= 2
 size_t dedup_bytes(const meepo_table* t, uint64_t n, bool with_grads) {
   if (n == 0) return 256;
   const uint64_t m = dedup_cells(n);
-  size_t need = Workspace::pad((size_t)m * 8) + Workspace::pad(n * 4) + Workspace::pad((size_t)m * 4) +
+  size_t need = Workspace::pad((size_t)m * 8) + Workspace::pad(n * 4) + 2 * Workspace::pad((size_t)m * 4) +
                 Workspace::pad(compact_state_bytes(m)) + 4096;
   if (with_grads) need += SegWork::bytes(n, t->v.dim, bits_for((uint32_t)n));
   return need;
@@ -220,6 +227,7 @@ meepo_status dedup_hash(meepo_table* t, const uint64_t* keys, uint64_t n, const 
   uint64_t* scratch = t->ws.take<uint64_t>(m);
   uint32_t* pos = t->ws.take<uint32_t>(n);
   uint32_t* uid_of_slot = t->ws.take<uint32_t>(m);
+  uint32_t* canon_cell = o.canon ? t->ws.take<uint32_t>(m) : nullptr;
   const size_t cbytes = compact_state_bytes(m);
   char* cstate = t->ws.take<char>(cbytes);
   if (with_grads) w.take(t->ws, n, t->v.dim, end_bit);
@@ -228,8 +236,9 @@ meepo_status dedup_hash(meepo_table* t, const uint64_t* keys, uint64_t n, const 
   MEEPO_CUDA_TRY(cudaMemsetAsync(cstate, 0, cbytes, stream));
   if (o.occurrences) MEEPO_CUDA_TRY(cudaMemsetAsync(o.occurrences, 0, n * 4, stream));
   const int grid = grid_for(t, (const void*)dedup_insert_kernel, 256, 0, (n + 255) / 256);
-  dedup_insert_kernel<<<grid, 256, 0, stream>>>(keys, (uint32_t)n, scratch, m - 1, pos, skip);
+  dedup_insert_kernel<<<grid, 256, 0, stream>>>(keys, (uint32_t)n, scratch, m - 1, pos, canon_cell, skip);
   occ_compact_kernel<<<compact_tiles(m), kCompactThreads, 0, stream>>>(scratch, m, uid_of_slot, o.unique_keys,
+                                                                       canon_cell, o.canon,
                                                                        (unsigned long long*)o.n_unique,
                                                                        compact_carve(cstate, t->err_word + kErrLookback),
                                                                        skip);
@@ -305,7 +314,7 @@ MEEPO_API meepo_status meepo_reduce_duplicates(meepo_table* t, const uint64_t* k
   VerbScope vs(t, stream);
   MEEPO_TRY(vs.rc);
   MEEPO_TRY(t->ws.reserve(dedup_bytes(t, n, grads != nullptr), stream));
-  return dedup_run(t, keys, grads, n, DedupOut{unique_keys_out, grads_out, inverse_out, n_unique_out, nullptr, nullptr}, stream);
+  return dedup_run(t, keys, grads, n, DedupOut{unique_keys_out, grads_out, inverse_out, n_unique_out, nullptr, nullptr, nullptr}, stream);
 }
 
 MEEPO_API meepo_status meepo_gather_rows(meepo_table* t, const void* rows_in, const uint32_t* index, uint64_t n,

@@ -93,7 +93,8 @@ int grid_for(const meepo_table* t, const void* kernel, int block, size_t smem, u
   int per_sm = 1;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem) != cudaSuccess || per_sm < 1)
     per_sm = 1;
-  uint64_t cap = (uint64_t)t->num_sms * per_sm;
+  uint64_t cap = (uint64_t)((double)t->num_sms * per_sm * t->grid_scale);
+  if (cap < (uint64_t)t->num_sms) cap = t->num_sms;
   uint64_t g = blocks_needed < cap ? blocks_needed : cap;
   return (int)(g < 1 ? 1 : g);
 }

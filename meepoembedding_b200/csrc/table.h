@@ -49,8 +49,7 @@ struct Workspace {
 struct DeviceState {
   unsigned long long counters[16];
   uint32_t reserved_new[2];
-  uint32_t num_segments;   // apply_gradients scratch
-  uint32_t num_long, num_leaves;
+  uint32_t unused0[3];
   uint32_t evict_count;
   uint32_t pad[2];
   unsigned long long scratch64[8];
@@ -238,6 +237,7 @@ struct meepo_table {
   uint32_t* err_word = nullptr;  // the same words as the device sees them
   // Verbs of one table may be issued on different streams: each verb's stream first waits for the event the
   // previous verb recorded (workspace, slot cache and scratch counters are shared by all verbs of a table).
+  float grid_scale = 1.0f;  // < 1 while two pipelines of this table share the GPU (sharded backward pass)
   cudaEvent_t order_ev = nullptr;
   cudaStream_t last_stream = nullptr;
   bool order_valid = false;
@@ -303,6 +303,14 @@ meepo_status probe_gather_end(meepo_table* t, uint64_t n_total, bool insert, cud
 // the gradients with the probe / sort / segment passes that only need the keys.
 meepo_status launch_apply_gradients(meepo_table* t, const uint64_t* keys, const void* grads, uint64_t n,
                                     cudaStream_t stream, cudaEvent_t grads_ready = nullptr);
+// Device-side counters of one sort + segment + reduce pipeline: every pipeline in flight has its own (the owner
+// side of a sharded backward pass runs on another stream than the sender side).
+struct SegScratch {
+  uint32_t num_segments, num_long, num_leaves, pad;
+};
+struct SegRange {  // which segments a reduce pass takes, by sort key, and how a sort key maps to its output row
+  uint32_t key_lo, key_hi, key_mask;
+};
 // Scratch of one sort + segment + reduce pipeline (update.cu); carved out of the table workspace.
 struct SegWork {
   uint32_t *sk_in, *sk_out, *sv_in, *sv_out, *seg_start;
@@ -310,6 +318,7 @@ struct SegWork {
   uint2* leaf_desc;
   uint4* seg_desc;
   float* partial;
+  SegScratch* sc;
   size_t cub_bytes, max_long, max_leaves, cstate_bytes;
   uint32_t n, ntiles;
   int end_bit;
@@ -322,7 +331,13 @@ int bits_for(uint32_t max_value);
 bool radix_sort_supported(uint64_t n, int end_bit);
 size_t radix_sort_temp_bytes(uint64_t n, int end_bit);
 meepo_status radix_sort_pairs(meepo_table* t, char* temp, const uint32_t* k_in, uint32_t* k_out, const uint32_t* v_in,
-                              uint32_t* v_out, uint32_t n, int end_bit, cudaStream_t stream);
+                              uint32_t* v_out, uint32_t n, int end_bit, cudaStream_t stream,
+                              const uint32_t* n_dev = nullptr);
+meepo_status seg_sort_heads(meepo_table* t, SegWork& w, uint32_t miss_key, bool count_updates, const uint32_t* n_dev,
+                            cudaStream_t stream, const char* const* names);
+meepo_status seg_reduce(meepo_table* t, SegWork& w, const void* grads, int mode, const SegRange& r, void* reduce_out,
+                        void* const* reduce_rows, cudaStream_t stream, cudaEvent_t grads_ready,
+                        const char* const* names, bool again);
 meepo_status run_segmented(meepo_table* t, SegWork& w, uint32_t limit, const void* grads, int mode,
                            void* reduce_out, cudaStream_t stream, cudaEvent_t grads_ready,
                            const char* const* names, void* const* reduce_rows = nullptr);
@@ -336,6 +351,7 @@ struct DedupOut {
   uint64_t* n_unique;
   uint32_t* occurrences;
   void* const* grad_rows;  // optional: destination row of unique key u instead of grads_out[u]
+  uint32_t* canon;         // optional: batch index of one (arbitrary but fixed) occurrence of unique key u
 };
 struct SegWork;
 size_t dedup_bytes(const meepo_table* t, uint64_t n, bool with_grads);

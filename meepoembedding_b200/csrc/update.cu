@@ -64,9 +64,12 @@ __global__ void __launch_bounds__(kCompactThreads) segments_kernel(const uint32_
                                                                    const uint32_t* __restrict__ sv, uint32_t n,
                                                                    uint32_t* __restrict__ seg_start,
                                                                    uint4* __restrict__ seg_desc, uint32_t miss_key,
-                                                                   DeviceState* ds, int count_updates,
+                                                                   SegScratch* sc, unsigned long long* counters,
+                                                                   int count_updates, const uint32_t* __restrict__ n_dev,
                                                                    CompactState cs) {
+  if (n_dev) n = min(n, __ldg(n_dev));
   CompactTile ct = compact_begin(cs, n);
+  if ((uint64_t)ct.tile * kCompactTile >= n && !(n == 0 && ct.tile == 0)) return;  // tiles past a device-side n
   unsigned flags = 0;
   uint32_t key[kCompactItems];
 #pragma unroll
@@ -91,11 +94,11 @@ __global__ void __launch_bounds__(kCompactThreads) segments_kernel(const uint32_
     const uint32_t U = (uint32_t)ct.base + ct.tile_total;
     seg_start[U] = n;
     seg_desc[U] = make_uint4(n, kNil, 0, 0);
-    ds->num_segments = U;
-    ds->num_long = 0;
-    ds->num_leaves = 0;
-    const uint32_t applied = U - (n && sk[n - 1] == miss_key ? 1u : 0u);
-    if (applied && count_updates) atomicAdd(ds->counters + C_UPDATES, (unsigned long long)applied);
+    sc->num_segments = U;
+    sc->num_long = 0;
+    sc->num_leaves = 0;
+    const uint32_t applied = U - (n && sk[n - 1] >= miss_key ? 1u : 0u);
+    if (applied && count_updates) atomicAdd(counters + C_UPDATES, (unsigned long long)applied);
   }
 }
 
@@ -147,12 +150,15 @@ struct ApplyArgs {
   const uint32_t* sorted_idx;
   const uint32_t* seg_start;
   const uint4* seg_desc;  // [U+1] {first sorted position, sort key (slot), first batch index, -}
-  DeviceState* ds;
+  SegScratch* sc;
   LongSeg* long_seg;
   uint2* leaf_desc;
   float* partial;  // [leaves][dim]
   uint32_t group_lanes;  // power of two <= min(cpr, 32)
-  uint32_t limit;        // sort keys >= limit form the "absent key" segment and are skipped
+  uint32_t key_lo, key_hi;  // only segments whose sort key lies in [key_lo, key_hi) are processed: keys >= the table's
+                            // slot count / the batch size are the "absent key" segment, and a sharded sender reduces
+                            // its unique keys chunk by chunk (the chunk index sits above the unique id)
+  uint32_t key_mask;        // kStoreOnly: sort key & key_mask = index of the destination row
   uint4* reduce_out;         // kStoreOnly: [unique][cpr] ...
   uint4* const* reduce_rows;  // ... or one destination row pointer per sort key (may point into a peer's window)
 };
@@ -161,6 +167,7 @@ struct ApplyArgs {
 template <int OPT>
 __device__ __forceinline__ uint4* reduce_row_of(const ApplyArgs& a, uint32_t key, uint32_t cpr) {
   if constexpr (OPT != kStoreOnly) return nullptr;
+  key &= a.key_mask;
   if (a.reduce_rows)
     return reinterpret_cast<uint4*>(__ldg(reinterpret_cast<const unsigned long long*>(a.reduce_rows) + key));
   return a.reduce_out + (size_t)key * cpr;
@@ -177,18 +184,18 @@ __global__ void __launch_bounds__(256) apply_kernel(TableView t, ApplyArgs a) {
   const uint32_t groups_per_block = blockDim.x / GL;
   const uint32_t group = blockIdx.x * groups_per_block + threadIdx.x / GL;
   const uint32_t ngroups = gridDim.x * groups_per_block;
-  const uint32_t U = a.ds->num_segments;
+  const uint32_t U = a.sc->num_segments;
   for (uint32_t u = group; u < U; u += ngroups) {
     const uint32_t s0 = a.seg_start[u], s1 = a.seg_start[u + 1];
     const uint32_t slot = a.sorted_slot[s0];
-    if (slot >= a.limit) continue;  // the segment of absent / invalid keys
+    if (slot < a.key_lo || slot >= a.key_hi) continue;  // absent / invalid keys, or another chunk
     const uint32_t cnt = s1 - s0;
     if (cnt > kLongSeg) {  // hand over to the leaf kernels
       const uint32_t nleaf = (cnt + kLeaf - 1) / kLeaf;
       uint32_t base = 0;
       if (gl == 0) {
-        const uint32_t li = atomicAdd(&a.ds->num_long, 1u);
-        base = atomicAdd(&a.ds->num_leaves, nleaf);
+        const uint32_t li = atomicAdd(&a.sc->num_long, 1u);
+        base = atomicAdd(&a.sc->num_leaves, nleaf);
         a.long_seg[li] = LongSeg{u, base, nleaf, 0};
       }
       base = __shfl_sync(gmask, base, lane & ~(GL - 1));
@@ -217,7 +224,7 @@ __global__ void __launch_bounds__(256) apply_pipelined_kernel(TableView t, Apply
   const uint32_t groups_per_block = blockDim.x / GL;
   const uint32_t group = blockIdx.x * groups_per_block + threadIdx.x / GL;
   const uint32_t stride = gridDim.x * groups_per_block * 2;
-  const uint32_t U = a.ds->num_segments;
+  const uint32_t U = a.sc->num_segments;
   const uint32_t cpr = t.cpr;
   const uint4 nil = make_uint4(0, kNil, 0, 0);
   auto desc = [&](uint32_t i) { return i <= U ? __ldg(a.seg_desc + i) : nil; };
@@ -230,7 +237,8 @@ __global__ void __launch_bounds__(256) apply_pipelined_kernel(TableView t, Apply
     const uint4 na = desc(un), nb = desc(un + 1);
     const uint32_t nc = desc(un + 2).x;
     const uint32_t cntA = db.x - da.x, cntB = ec - db.x;
-    const bool liveA = da.y < a.limit, liveB = (u + 1 < U) && db.y < a.limit;
+    const bool liveA = da.y >= a.key_lo && da.y < a.key_hi;
+    const bool liveB = (u + 1 < U) && db.y >= a.key_lo && db.y < a.key_hi;
     const bool okA = liveA && cntA <= kLongSeg, okB = liveB && cntB <= kLongSeg;
     uint4 gA = make_uint4(0, 0, 0, 0), gB = gA;
     OptIn<BF16, OPT> inA, inB;
@@ -250,8 +258,8 @@ __global__ void __launch_bounds__(256) apply_pipelined_kernel(TableView t, Apply
         const uint32_t nleaf = (cnt + kLeaf - 1) / kLeaf;
         uint32_t base = 0;
         if (q == 0) {
-          const uint32_t li = atomicAdd(&a.ds->num_long, 1u);
-          base = atomicAdd(&a.ds->num_leaves, nleaf);
+          const uint32_t li = atomicAdd(&a.sc->num_long, 1u);
+          base = atomicAdd(&a.sc->num_leaves, nleaf);
           a.long_seg[li] = LongSeg{u + h, base, nleaf, 0};
         }
         base = __shfl_sync(gmask, base, lane & ~(GL - 1));
@@ -338,7 +346,7 @@ __global__ void __launch_bounds__(256) leaf_kernel(TableView t, ApplyArgs a, uin
   const uint32_t W = t.cpr * 4 / V;  // pieces per row
   const uint32_t sub = threadIdx.x / tpl, wi = threadIdx.x % tpl;
   const uint32_t lpc = blockDim.x / tpl;  // leaves per CTA
-  const uint32_t nleaves = a.ds->num_leaves;
+  const uint32_t nleaves = a.sc->num_leaves;
   const typename P::T* g = reinterpret_cast<const typename P::T*>(a.grads);
   for (uint32_t l = blockIdx.x * lpc + sub; l < nleaves; l += gridDim.x * lpc) {
     const uint2 d = a.leaf_desc[l];
@@ -401,7 +409,7 @@ __global__ void __launch_bounds__(256) long_finish_kernel(TableView t, ApplyArgs
   constexpr int D = 32;
   extern __shared__ float sum_s[];  // [dim]
   __shared__ float alpha_s;
-  const uint32_t nlong = a.ds->num_long;
+  const uint32_t nlong = a.sc->num_long;
   for (uint32_t li = blockIdx.x; li < nlong; li += gridDim.x) {
     const LongSeg ls = a.long_seg[li];
     const uint32_t slot = a.sorted_slot[a.seg_start[ls.seg]];
@@ -487,7 +495,8 @@ size_t SegWork::bytes(uint64_t n, uint32_t dim, int end_bit_) {
   const size_t max_long_ = n / (kLongSeg + 1) + 1, max_leaves_ = n / kLongSeg + 2;
   return 4 * Workspace::pad(n * 4) + Workspace::pad(cub) + Workspace::pad(compact_state_bytes(n)) +
          Workspace::pad((n + 2) * 4) + Workspace::pad((n + 2) * 16) + Workspace::pad(max_long_ * sizeof(LongSeg)) +
-         Workspace::pad(max_leaves_ * 8) + Workspace::pad(max_leaves_ * dim * 4) + 4096;
+         Workspace::pad(max_leaves_ * 8) + Workspace::pad(max_leaves_ * dim * 4) + Workspace::pad(sizeof(SegScratch)) +
+         4096;
 }
 
 void SegWork::take(Workspace& ws, uint64_t n_, uint32_t dim, int end_bit_) {
@@ -512,6 +521,7 @@ void SegWork::take(Workspace& ws, uint64_t n_, uint32_t dim, int end_bit_) {
   long_seg = ws.take<char>(max_long * sizeof(LongSeg));
   leaf_desc = ws.take<uint2>(max_leaves);
   partial = ws.take<float>(max_leaves * dim);
+  sc = ws.take<SegScratch>(1);
 }
 
 // "<prefix>(N kernels)" for the hand-written sort (histogram/scan + one kernel per digit), "<prefix>(cub)" else;
@@ -529,41 +539,54 @@ int bits_for(uint32_t max_value) {
   return b;
 }
 
-// sort (sk_in, sv_in) by key, find the segments, reduce each segment's gradient rows in the
-// normative order and hand the sum to the optimizer `mode` (MEEPO_SGD/ADAGRAD/ADAM) or store it
-// (kStoreOnly -> reduce_out[sort key]).
-meepo_status run_segmented(meepo_table* t, SegWork& w, uint32_t limit, const void* grads, int mode,
-                           void* reduce_out, cudaStream_t stream, cudaEvent_t grads_ready,
-                           const char* const* names, void* const* reduce_rows) {
+// Phase 1: stable sort of (sk_in, sv_in) by key, then the segment heads. n_dev (optional, device memory): the
+// true number of pairs (<= w.n, which sizes grids and scratch). Keys >= miss_key are "absent".
+meepo_status seg_sort_heads(meepo_table* t, SegWork& w, uint32_t miss_key, bool count_updates, const uint32_t* n_dev,
+                            cudaStream_t stream, const char* const* names) {
   const uint32_t n32 = w.n;
   {
     ProfScope ps(t, sort_scope_name(names[0], radix_sort_supported(n32, w.end_bit) ? (w.end_bit + 7) / 8 + 1 : 0), stream);
-    if (radix_sort_supported(n32, w.end_bit))  // hand-written onesweep (radix_sort.cu); CUB only beyond 2^30 pairs
-      MEEPO_TRY(radix_sort_pairs(t, w.cub_tmp, w.sk_in, w.sk_out, w.sv_in, w.sv_out, n32, w.end_bit, stream));
-    else
+    if (radix_sort_supported(n32, w.end_bit)) {  // hand-written onesweep (radix_sort.cu); CUB only beyond 2^30 pairs
+      MEEPO_TRY(radix_sort_pairs(t, w.cub_tmp, w.sk_in, w.sk_out, w.sv_in, w.sv_out, n32, w.end_bit, stream, n_dev));
+    } else {
+      if (n_dev) return fail(MEEPO_EINVAL, "a device-side pair count needs the hand-written sort (< 2^30 pairs)");
       MEEPO_CUDA_TRY(cub::DeviceRadixSort::SortPairs(w.cub_tmp, w.cub_bytes, (const uint32_t*)w.sk_in, w.sk_out,
                                                    (const uint32_t*)w.sv_in, w.sv_out, (int)n32, 0, w.end_bit,
                                                    stream));
+    }
   }
   {
     ProfScope ps(t, names[1], stream);
     MEEPO_CUDA_TRY(cudaMemsetAsync(w.cstate, 0, w.cstate_bytes, stream));
-    segments_kernel<<<w.ntiles, kCompactThreads, 0, stream>>>(w.sk_out, w.sv_out, n32, w.seg_start, w.seg_desc, limit,
-                                                              t->dstate, mode != kStoreOnly,
+    segments_kernel<<<w.ntiles, kCompactThreads, 0, stream>>>(w.sk_out, w.sv_out, n32, w.seg_start, w.seg_desc, miss_key,
+                                                              w.sc, t->v.counters, count_updates ? 1 : 0, n_dev,
                                                               compact_carve(w.cstate, t->err_word + kErrLookback));
     MEEPO_CUDA_TRY(cudaGetLastError());
   }
+  return MEEPO_OK;
+}
+
+// Phase 2: reduce the gradient rows of every segment whose sort key lies in [r.key_lo, r.key_hi) in the normative
+// order and hand the sum to the optimizer `mode` (MEEPO_SGD/ADAGRAD/ADAM) or store it (kStoreOnly) to
+// reduce_out[key & mask] / *reduce_rows[key & mask]. May be called several times over one phase-1 result with
+// disjoint key ranges (`again` = not the first call: the long-segment lists are reset first).
+meepo_status seg_reduce(meepo_table* t, SegWork& w, const void* grads, int mode, const SegRange& r, void* reduce_out,
+                        void* const* reduce_rows, cudaStream_t stream, cudaEvent_t grads_ready,
+                        const char* const* names, bool again) {
+  const uint32_t n32 = w.n;
   ApplyArgs a;
   a.grads = reinterpret_cast<const uint4*>(grads);
   a.sorted_slot = w.sk_out;
   a.sorted_idx = w.sv_out;
   a.seg_start = w.seg_start;
   a.seg_desc = w.seg_desc;
-  a.ds = t->dstate;
+  a.sc = w.sc;
   a.long_seg = reinterpret_cast<LongSeg*>(w.long_seg);
   a.leaf_desc = w.leaf_desc;
   a.partial = w.partial;
-  a.limit = limit;
+  a.key_lo = r.key_lo;
+  a.key_hi = r.key_hi;
+  a.key_mask = r.key_mask;
   a.reduce_out = reinterpret_cast<uint4*>(reduce_out);
   a.reduce_rows = reinterpret_cast<uint4* const*>(reduce_rows);
   uint32_t gl = 1;
@@ -583,6 +606,7 @@ meepo_status run_segmented(meepo_table* t, SegWork& w, uint32_t limit, const voi
   void* args[] = {&t->v, &a};
   const uint64_t groups_per_block = 256 / gl;
   if (grads_ready) MEEPO_CUDA_TRY(cudaStreamWaitEvent(stream, grads_ready, 0));
+  if (again) MEEPO_CUDA_TRY(cudaMemsetAsync(&w.sc->num_long, 0, 8, stream));  // num_long, num_leaves
   {
     ProfScope ps(t, names[2], stream);
     const uint64_t per_block = groups_per_block * (pipelined ? 2 : 1);
@@ -606,6 +630,15 @@ meepo_status run_segmented(meepo_table* t, SegWork& w, uint32_t limit, const voi
     MEEPO_CUDA_TRY(cudaLaunchKernel(k_finish, dim3(grid2), dim3(256), args, smem, stream));
   }
   return MEEPO_OK;
+}
+
+// both phases over every key below `limit`
+meepo_status run_segmented(meepo_table* t, SegWork& w, uint32_t limit, const void* grads, int mode,
+                           void* reduce_out, cudaStream_t stream, cudaEvent_t grads_ready,
+                           const char* const* names, void* const* reduce_rows) {
+  MEEPO_TRY(seg_sort_heads(t, w, limit, mode != kStoreOnly, nullptr, stream, names));
+  return seg_reduce(t, w, grads, mode, SegRange{0u, limit, 0xFFFFFFFFu}, reduce_out, reduce_rows, stream, grads_ready,
+                    names, false);
 }
 
 meepo_status launch_apply_gradients(meepo_table* t, const uint64_t* keys, const void* grads, uint64_t n,

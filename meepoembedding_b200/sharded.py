@@ -31,6 +31,24 @@ def owner_np(keys: np.ndarray, num_shards: int) -> np.ndarray:
     return ((hi * g + ((lo * g) >> np.uint64(32))) >> np.uint64(32)).astype(np.int64)
 
 
+def output_rows(table, index: int, rows: int | None = None, device=None):
+    """The index-th output buffer of `table`'s exchange window (meepo_peer_output) as a [rows, dim] torch tensor of
+    the table dtype, without a copy. A sharded forward verb whose rows_out is (a prefix of) such a buffer has the
+    owners store the rows into it directly over NVLink."""
+    ptr, max_rows = table.peer_output(index)
+    rows = max_rows if rows is None else int(rows)
+    assert 0 < rows <= max_rows
+    nbytes = rows * table.row_bytes
+
+    class _Raw:  # torch maps any object exposing the CUDA array interface without copying
+        __cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+    dev = torch.device(device) if device is not None else torch.device("cuda", table.device)
+    raw = torch.as_tensor(_Raw(), device=dev)
+    dt = torch.float32 if table.dtype == capi.F32 else torch.bfloat16
+    return raw.view(dt).view(rows, table.dim)
+
+
 class ShardedTable:
     def __init__(self, table, group=None, device=None):
         self.t = table
@@ -133,13 +151,14 @@ class PeerShardedTable:
     synchronisation, no staging copy. Verbs are collective: every rank calls them in the same order.
     """
 
-    def __init__(self, table, group=None, device=None, max_batch=1 << 20, region_keys=0):
+    def __init__(self, table, group=None, device=None, max_batch=1 << 20, region_keys=0, out_buffers=0):
         self.t = table
         self.group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.group)
         self.rank = dist.get_rank(self.group)
         self.device = torch.device(device) if device is not None else torch.device("cuda", table.device)
-        blob = table.peer_prepare(self.rank, self.world, max_batch, region_keys)
+        self.out_buffers = out_buffers
+        blob = table.peer_prepare(self.rank, self.world, max_batch, region_keys, out_buffers)
         mine = torch.frombuffer(bytearray(blob), dtype=torch.uint8)
         backend = dist.get_backend(self.group)
         if backend == "nccl":
@@ -151,6 +170,11 @@ class PeerShardedTable:
 
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
+
+    def output_buffer(self, index: int, rows: int | None = None):
+        """The index-th output buffer of the exchange window as a [rows, dim] tensor of the table dtype. A forward
+        verb whose rows_out is (a prefix of) such a buffer has the owners store the rows into it directly."""
+        return output_rows(self.t, index, rows, self.device)
 
     def find_or_insert(self, keys, rows_out, status_out=None):
         return self.t.sharded_find_or_insert(keys, rows_out, status_out, n=keys.numel(), stream=self._stream())

@@ -305,11 +305,18 @@ class Table:
         self.lib.check(self.lib.gather_rows(self._h, _ptr(rows_in), _ptr(index), n, _ptr(rows_out), stream))
 
     # -- sharded verbs over NVLink peer memory (collective; include/meepo.h) -------------------
-    def peer_prepare(self, rank: int, world: int, max_batch: int, region_keys: int = 0) -> bytes:
+    def peer_prepare(self, rank: int, world: int, max_batch: int, region_keys: int = 0, out_buffers: int = 0) -> bytes:
         """Allocate this rank's exchange window; returns the opaque blob to all-gather."""
         buf = C.create_string_buffer(capi.PEER_BLOB_BYTES)
-        self.lib.check(self.lib.peer_prepare(self._h, int(rank), int(world), int(max_batch), int(region_keys), buf))
+        self.lib.check(self.lib.peer_prepare(self._h, int(rank), int(world), int(max_batch), int(region_keys),
+                                             int(out_buffers), buf))
         return buf.raw
+
+    def peer_output(self, index: int):
+        """(device pointer, rows) of the index-th output buffer inside the exchange window."""
+        ptr, rows = C.c_void_p(), C.c_uint64(0)
+        self.lib.check(self.lib.peer_output(self._h, int(index), C.byref(ptr), C.byref(rows)))
+        return int(ptr.value), int(rows.value)
 
     def peer_attach(self, blobs: bytes):
         """`blobs` = the world blobs concatenated in rank order."""

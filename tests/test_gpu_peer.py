@@ -26,6 +26,12 @@ from util import export_sorted, grads_for, make_keys, table_kwargs
 
 pytestmark = pytest.mark.gpu
 
+
+def output_rows(*a, **kw):
+    from meepoembedding_b200.sharded import output_rows as f
+
+    return f(*a, **kw)
+
 os.environ.setdefault("MEEPO_PEER_TIMEOUT_MS", "8000")
 
 
@@ -66,15 +72,21 @@ def _gpu_export(t, dev):
             scores.cpu().numpy().view(np.uint64), steps.cpu().numpy().view(np.uint32))
 
 
-@pytest.mark.parametrize("world,dtype,dim,optimizer,scores", [
-    (1, "f32", 16, "adagrad", False),
-    (2, "f32", 128, "adagrad", False),
-    (2, "bf16", 128, "adam", True),
-    (3, "f32", 24, "sgd", True),
-    (4, "bf16", 64, "adagrad", False),
+@pytest.mark.parametrize("world,dtype,dim,optimizer,scores,chunks", [
+    (1, "f32", 16, "adagrad", False, 3),
+    (1, "bf16", 128, "adam", True, 2),
+    (1, "f32", 128, "sgd", True, 1),
+    (2, "f32", 128, "adagrad", False, 1),
+    (2, "bf16", 128, "adam", True, 3),
+    (3, "f32", 24, "sgd", True, 2),
+    (4, "bf16", 64, "adagrad", False, 3),
 ])
-def test_peer_single_process(oracle_lib, cuda_lib, world, dtype, dim, optimizer, scores):
+def test_peer_single_process(oracle_lib, cuda_lib, monkeypatch, world, dtype, dim, optimizer, scores, chunks):
+    """`chunks`: the backward pass split into that many pipelined chunks (sender side on the caller's stream, owner
+    side on the table's own stream underneath it); results must not depend on it."""
     import torch
+
+    monkeypatch.setenv("MEEPO_PEER_CHUNKS", str(chunks))
 
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs: ranks that wait on one another must not share a device")
@@ -87,7 +99,8 @@ def test_peer_single_process(oracle_lib, cuda_lib, world, dtype, dim, optimizer,
     ref = Table(lib=oracle_lib, **dict(kw, capacity=cap * world))
     max_batch = 6000
     region = 0 if world < 3 else 4000  # also exercise a lane smaller than the batch
-    blobs = b"".join(t.peer_prepare(r, world, max_batch, region) for r, t in enumerate(tables))
+    # two output buffers inside every window: odd steps have the owners store rows straight into them
+    blobs = b"".join(t.peer_prepare(r, world, max_batch, region, 2) for r, t in enumerate(tables))
     for t in tables:
         t.peer_attach(blobs)
     streams = [torch.cuda.Stream(device=devs[r]) for r in range(world)]
@@ -111,7 +124,10 @@ def test_peer_single_process(oracle_lib, cuda_lib, world, dtype, dim, optimizer,
                 k[rng.choice(n, 300, replace=False)] = np.uint64(4242)
             per_keys.append(k)
         dk = [put(k.view(np.int64), r) for r, k in enumerate(per_keys)]
-        rows = [torch.empty((max(k.size, 1), dim), dtype=tdt, device=f"cuda:{devs[r]}") for r, k in enumerate(per_keys)]
+        if step % 2:
+            rows = [output_rows(tables[r], step // 2 % 2, max(k.size, 1), f"cuda:{devs[r]}") for r, k in enumerate(per_keys)]
+        else:
+            rows = [torch.empty((max(k.size, 1), dim), dtype=tdt, device=f"cuda:{devs[r]}") for r, k in enumerate(per_keys)]
         st = [torch.full((max(k.size, 1),), 99, dtype=torch.uint8, device=f"cuda:{devs[r]}") for r, k in enumerate(per_keys)]
         sync()
         for r in range(world):
@@ -135,7 +151,10 @@ def test_peer_single_process(oracle_lib, cuda_lib, world, dtype, dim, optimizer,
 
         lk = [make_keys(rng, 700, 8000, invalid=True) for _ in range(world)]
         dlk = [put(k.view(np.int64), r) for r, k in enumerate(lk)]
-        lrows = [torch.empty((700, dim), dtype=tdt, device=f"cuda:{devs[r]}") for r in range(world)]
+        if step % 2 == 0:  # lookups into the window's output area on the other steps
+            lrows = [output_rows(tables[r], 1, 700, f"cuda:{devs[r]}") for r in range(world)]
+        else:
+            lrows = [torch.empty((700, dim), dtype=tdt, device=f"cuda:{devs[r]}") for r in range(world)]
         lst = [torch.empty(700, dtype=torch.uint8, device=f"cuda:{devs[r]}") for r in range(world)]
         sync()
         for r in range(world):
@@ -250,7 +269,7 @@ def _ipc_worker(rank, world, port, dtype, q):
         dev = f"cuda:{rank}"
         tdt = torch.float32 if dtype == "f32" else torch.bfloat16
         local = Table(device=rank, **table_kwargs(dim=dim, capacity=1 << 15, dtype=dtype, optimizer="adagrad"))
-        sh = PeerShardedTable(local, dist.group.WORLD, dev, max_batch=20000)
+        sh = PeerShardedTable(local, dist.group.WORLD, dev, max_batch=20000, out_buffers=1)
         out = []
         for step in range(3):
             rng = np.random.default_rng([step, rank])
@@ -260,11 +279,12 @@ def _ipc_worker(rank, world, port, dtype, q):
             dk = torch.from_numpy(keys.view(np.int64)).to(dev)
             dg = torch.from_numpy(g.view(np.int16) if dtype == "bf16" else g).to(dev)
             dg = dg.view(tdt) if dtype == "bf16" else dg
-            rows = torch.empty((n, dim), dtype=tdt, device=dev)
+            rows = sh.output_buffer(0, n) if step != 1 else torch.empty((n, dim), dtype=tdt, device=dev)
             st = torch.empty(n, dtype=torch.uint8, device=dev)
             sh.find_or_insert(dk, rows, st)
+            rows = rows.clone()  # the buffer is reused below
             sh.apply_gradients(dk, dg)
-            rows2 = torch.empty((n, dim), dtype=tdt, device=dev)
+            rows2 = sh.output_buffer(0, n) if step == 1 else torch.empty((n, dim), dtype=tdt, device=dev)
             st2 = torch.empty(n, dtype=torch.uint8, device=dev)
             sh.lookup(dk, rows2, st2)
             torch.cuda.synchronize()
