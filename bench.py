@@ -468,11 +468,13 @@ class GpuRun:
         if world > 1 and self.args.exchange == "peer":
             # the NVLink-bound kernels store (world-1)/world of their rows (+ 8-byte keys) into peers' windows
             out = {}
-            for name, rows_per_launch in (("sharded.owner_find_or_insert", kr), ("dedup.reduce_store", gr)):
+            for name, rows_per_step in (("sharded.owner_find_or_insert", kr), ("dedup.reduce_store", gr)):
                 if name in kernels:
-                    b = rows_per_launch * (world - 1) / world * (R + 8)
-                    out[name] = {"bytes_out_per_launch": b, "avg_ms": kernels[name]["avg_ms"],
-                                 "achieved_gbs": b / (kernels[name]["avg_ms"] * 1e-3) / 1e9}
+                    # a chunked backward pass launches the kernel several times per step: bytes and time per STEP
+                    b = rows_per_step * (world - 1) / world * (R + 8)
+                    ms = kernels[name]["avg_ms"] * kernels[name]["launches"] / self.steps
+                    out[name] = {"bytes_out_per_launch": b, "avg_ms": ms, "launches_per_step": kernels[name]["launches"] / self.steps,
+                                 "achieved_gbs": b / (ms * 1e-3) / 1e9}
             if out:
                 topn = max(out, key=lambda k: out[k]["avg_ms"])
                 step_out = sum(o["bytes_out_per_launch"] for o in out.values())

@@ -241,18 +241,30 @@ __global__ void __launch_bounds__(32) peer_barrier_kernel(const __grid_constant_
 }
 
 // --- requester: push -----------------------------------------------------------------------------
+// Both passes walk the BATCH (not the unique-key list) and take the canonical occurrence of every key, so that
+// the positions one CTA claims in an owner's lane belong to 2048 consecutive batch elements: when the owner later
+// stores the rows of 32 consecutive positions straight into the requester's output tensor, they land within ~1 MB
+// of one another (scattering them over the whole 2 GB tensor costs an address translation per row over NVLink:
+// measured 10x slower).
+__device__ __forceinline__ bool canonical(const uint32_t* __restrict__ inverse, const uint32_t* __restrict__ canon,
+                                          uint32_t i, uint32_t& u) {
+  u = __ldg(inverse + i);
+  return u != kNil && __ldg(canon + u) == i;
+}
 // Pass 1: unique keys per (owner, chunk) bin.
 __global__ void __launch_bounds__(256) owner_hist_kernel(const __grid_constant__ PeerSet ps,
-                                                         const uint64_t* __restrict__ ukeys,
-                                                         const unsigned long long* __restrict__ n_unique,
+                                                         const uint64_t* __restrict__ keys,
+                                                         const uint32_t* __restrict__ inverse,
+                                                         const uint32_t* __restrict__ canon, uint32_t n,
                                                          uint32_t* __restrict__ hist, const uint32_t* __restrict__ skip) {
   if (skip && *skip) return;
   __shared__ uint32_t sh[kMaxBins];
   if (threadIdx.x < kMaxBins) sh[threadIdx.x] = 0;
   __syncthreads();
-  const uint32_t n = (uint32_t)*n_unique;
-  for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n; u += gridDim.x * blockDim.x) {
-    const uint64_t h = mix64(__ldg(ukeys + u) ^ MEEPO_OWNER_SALT);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    uint32_t u;
+    if (!canonical(inverse, canon, i, u)) continue;
+    const uint64_t h = mix64(__ldg(keys + i) ^ MEEPO_OWNER_SALT);
     const uint32_t bin = (uint32_t)__umul64hi(h, (uint64_t)ps.world) * ps.chunks + chunk_of_hash(h, ps.chunks);
     atomicAdd(&sh[bin], 1u);
   }
@@ -260,13 +272,13 @@ __global__ void __launch_bounds__(256) owner_hist_kernel(const __grid_constant__
   if (threadIdx.x < kMaxBins && sh[threadIdx.x]) atomicAdd(hist + threadIdx.x, sh[threadIdx.x]);
 }
 
-// Pass 2: a CTA sorts its tile of unique keys by bin in shared memory, claims one position range per bin and
-// stores every run contiguously into the owner's window. Inside a (sender, owner) lane the chunks are
+// Pass 2: a CTA sorts the unique keys of its tile of the batch by bin in shared memory, claims one position range
+// per bin and stores every run contiguously into the owner's window. Inside a (sender, owner) lane the chunks are
 // consecutive runs: chunk c = [base[o][c], base[o][c+1]). loc[u] = owner * region + position (kNil: lane full).
 constexpr int kPushThreads = 256, kPushItems = 8, kPushTile = kPushThreads * kPushItems;
 __global__ void __launch_bounds__(kPushThreads) push_scatter_kernel(
-    const __grid_constant__ PeerSet ps, const uint64_t* __restrict__ ukeys, const uint32_t* __restrict__ uocc,
-    const uint32_t* __restrict__ canon, const unsigned long long* __restrict__ n_unique,
+    const __grid_constant__ PeerSet ps, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ inverse,
+    const uint32_t* __restrict__ canon, const uint32_t* __restrict__ uocc, uint32_t n,
     const uint32_t* __restrict__ hist, uint32_t* __restrict__ cursor, uint32_t* __restrict__ chunk_cnt,
     uint32_t* __restrict__ loc, const uint32_t* __restrict__ skip) {
   if (skip && *skip) return;
@@ -274,8 +286,8 @@ __global__ void __launch_bounds__(kPushThreads) push_scatter_kernel(
   __shared__ uint32_t s_occ[kPushTile], s_dest[kPushTile], s_uid[kPushTile];
   __shared__ uint8_t s_bin[kPushTile];
   __shared__ uint32_t s_base[kMaxBins], s_cnt[kMaxBins], s_start[kMaxBins], s_gbase[kMaxBins];
+  __shared__ uint32_t s_total;
   const uint32_t tid = threadIdx.x, K = ps.chunks, nbins = ps.world * K;
-  const uint32_t n = (uint32_t)*n_unique;
   if (tid < kMaxBins) {
     uint32_t base = 0;
     if (tid < nbins) {
@@ -289,15 +301,16 @@ __global__ void __launch_bounds__(kPushThreads) push_scatter_kernel(
     if (tid < kMaxBins) s_cnt[tid] = 0;
     __syncthreads();
     uint64_t key[kPushItems];
-    uint32_t bin[kPushItems], rank[kPushItems];
+    uint32_t bin[kPushItems], rank[kPushItems], uid[kPushItems];
 #pragma unroll
     for (int k = 0; k < kPushItems; k++) {
-      const uint32_t u = tile0 + k * kPushThreads + tid;
+      const uint32_t i = tile0 + k * kPushThreads + tid;
       bin[k] = kNil;
       key[k] = 0;
       rank[k] = 0;
-      if (u < n) {
-        key[k] = __ldg(ukeys + u);
+      uid[k] = kNil;
+      if (i < n && canonical(inverse, canon, i, uid[k])) {
+        key[k] = __ldg(keys + i);
         const uint64_t h = mix64(key[k] ^ MEEPO_OWNER_SALT);
         bin[k] = (uint32_t)__umul64hi(h, (uint64_t)ps.world) * K + chunk_of_hash(h, K);
         rank[k] = atomicAdd(&s_cnt[bin[k]], 1u);
@@ -313,22 +326,22 @@ __global__ void __launch_bounds__(kPushThreads) push_scatter_kernel(
         if (tid >= (uint32_t)d) incl += y;
       }
       s_start[tid] = incl - x;
+      if (tid == 31) s_total = incl;
       if (x) s_gbase[tid] = s_base[tid] + atomicAdd(cursor + tid, x);
     }
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < kPushItems; k++) {
       if (bin[k] == kNil) continue;
-      const uint32_t u = tile0 + k * kPushThreads + tid;
       const uint32_t j = s_start[bin[k]] + rank[k];
       s_key[j] = key[k];
-      s_occ[j] = uocc ? __ldg(uocc + u) : 1u;
-      s_dest[j] = canon ? __ldg(canon + u) : 0u;
-      s_uid[j] = u;
+      s_occ[j] = uocc ? __ldg(uocc + uid[k]) : 1u;
+      s_dest[j] = tile0 + k * kPushThreads + tid;
+      s_uid[j] = uid[k];
       s_bin[j] = (uint8_t)bin[k];
     }
     __syncthreads();
-    const uint32_t tile_n = min((uint32_t)kPushTile, n - tile0);
+    const uint32_t tile_n = s_total;
     for (uint32_t j = tid; j < tile_n; j += kPushThreads) {
       const uint32_t b = s_bin[j], o = b / K;
       const uint32_t p = s_gbase[b] + (j - s_start[b]);
@@ -592,18 +605,17 @@ static meepo_status check_sharded(meepo_table* t, const void* keys, uint64_t n, 
 }
 
 // keys -> their owners' windows (two kernels); leaves loc[] and chunk_cnt[][]. `skip`: device flag, no-op when set.
-static meepo_status push_keys(meepo_table* t, const uint32_t* uocc, const uint32_t* canon, uint64_t n,
+static meepo_status push_keys(meepo_table* t, const uint64_t* keys, const uint32_t* uocc, uint64_t n,
                               const uint32_t* skip, cudaStream_t stream) {
   PeerState* p = t->peer;
   ProfScope ps(t, "sharded.push_keys(2 kernels)", stream);
   MEEPO_CUDA_TRY(cudaMemsetAsync(p->hist, 0, 2 * kMaxBins * 4, stream));  // hist + cursor
   const uint64_t n1 = std::max<uint64_t>(n, 1);
   const int g1 = grid_for(t, (const void*)owner_hist_kernel, 256, 0, (n1 + 1023) / 1024);
-  owner_hist_kernel<<<g1, 256, 0, stream>>>(p->ps, p->ukeys, (const unsigned long long*)p->n_unique, p->hist, skip);
+  owner_hist_kernel<<<g1, 256, 0, stream>>>(p->ps, keys, p->inverse, p->canon, (uint32_t)n, p->hist, skip);
   const int g2 = grid_for(t, (const void*)push_scatter_kernel, kPushThreads, 0, (n1 + kPushTile - 1) / kPushTile);
-  push_scatter_kernel<<<g2, kPushThreads, 0, stream>>>(p->ps, p->ukeys, uocc, canon,
-                                                       (const unsigned long long*)p->n_unique, p->hist, p->cursor,
-                                                       p->chunk_cnt, p->loc, skip);
+  push_scatter_kernel<<<g2, kPushThreads, 0, stream>>>(p->ps, keys, p->inverse, p->canon, uocc, (uint32_t)n, p->hist,
+                                                       p->cursor, p->chunk_cnt, p->loc, skip);
   MEEPO_CUDA_TRY(cudaGetLastError());
   return MEEPO_OK;
 }
@@ -632,7 +644,7 @@ static meepo_status sharded_forward(meepo_table* t, const uint64_t* keys, uint64
   const unsigned long long out_off = direct ? (unsigned long long)(ro - p->out_base) : kNoOutput;
   MEEPO_TRY(dedup_run(t, keys, nullptr, n, DedupOut{p->ukeys, nullptr, p->inverse, p->n_unique, uocc, nullptr, p->canon},
                       stream));
-  MEEPO_TRY(push_keys(t, uocc, p->canon, n, nullptr, stream));
+  MEEPO_TRY(push_keys(t, keys, uocc, n, nullptr, stream));
   PeerWork* fwork = p->work + kMaxChunks;
   MEEPO_TRY(barrier(t, p->chunk_cnt + (p->chunks - 1) * kMaxPeers, fwork, nullptr, false, nullptr, true, out_off, stream));
   {
@@ -692,10 +704,10 @@ static meepo_status sharded_apply(meepo_table* t, const uint64_t* keys, const vo
       same_batch_kernel<<<grid, 256, 0, stream>>>(keys, p->fwd_keys, (uint32_t)n, p->reuse_flag);
     }
   }
-  DedupOut dd{p->ukeys, nullptr, p->inverse, p->n_unique, nullptr, reinterpret_cast<void* const*>(row_ptrs), nullptr};
+  DedupOut dd{p->ukeys, nullptr, p->inverse, p->n_unique, nullptr, reinterpret_cast<void* const*>(row_ptrs), p->canon};
   SegWork unused;
   MEEPO_TRY(dedup_hash(t, keys, n, dd, false, unused, stream, p->reuse_flag));  // no-op when the flag is set
-  MEEPO_TRY(push_keys(t, nullptr, nullptr, n, p->reuse_flag, stream));          // likewise
+  MEEPO_TRY(push_keys(t, keys, nullptr, n, p->reuse_flag, stream));             // likewise
   static const char* const snames[5] = {"dedup.radix_sort", "dedup.segments", "dedup.reduce_store", "dedup.long_leaves",
                                         "dedup.long_finish"};
   static const char* const onames[5] = {"sharded.owner_sort", "sharded.owner_segments", "sharded.owner_apply",
@@ -709,7 +721,7 @@ static meepo_status sharded_apply(meepo_table* t, const uint64_t* keys, const vo
                                                  sw.sv_in);
       MEEPO_CUDA_TRY(cudaGetLastError());
     }
-    MEEPO_TRY(seg_sort_heads(t, sw, K << ubits, false, nullptr, stream, snames));
+    MEEPO_TRY(seg_sort_heads(t, sw, K << ubits, false, nullptr, stream, snames, 0, K > 1 ? ubits : -1));
   }
   // The owner side of chunk c runs on its own stream underneath the sender side of chunk c + 1.
   const bool overlap = K > 1;
@@ -718,7 +730,7 @@ static meepo_status sharded_apply(meepo_table* t, const uint64_t* keys, const vo
   for (uint32_t c = 0; c < K; c++) {
     if (n) {
       t->grid_scale = overlap ? p->sender_share : 1.0f;
-      const SegRange r{c << ubits, (c + 1) << ubits, (1u << ubits) - 1u};
+      const SegRange r{c << ubits, (c + 1) << ubits, (1u << ubits) - 1u, K > 1 ? (int)c : -1};
       meepo_status rc = seg_reduce(t, sw, grads, kReduceStoreOnly, r, nullptr, reinterpret_cast<void* const*>(row_ptrs),
                                    stream, nullptr, snames, c > 0);  // summed rows land in the owners' windows
       t->grid_scale = 1.0f;
@@ -738,9 +750,10 @@ static meepo_status sharded_apply(meepo_table* t, const uint64_t* keys, const vo
       recv_slots_kernel<<<grid, 256, 0, T>>>(t->v, p->ps, p->work + c, ow.sk_in, ow.sv_in, p->entry_slot, entry_valid);
       if (cudaGetLastError() != cudaSuccess) rc = fail(MEEPO_ECUDA, "recv_slots launch failed");
     }
-    if (rc == MEEPO_OK) rc = seg_sort_heads(t, ow, t->v.slots, true, &p->work[c].total, T, onames);
     if (rc == MEEPO_OK)
-      rc = seg_reduce(t, ow, p->ps.w[p->rank].recv_grads, t->v.opt, SegRange{0u, t->v.slots, 0xFFFFFFFFu}, nullptr,
+      rc = seg_sort_heads(t, ow, t->v.slots, true, &p->work[c].total, T, onames, (uint32_t)(n_pad / K), -1);
+    if (rc == MEEPO_OK)
+      rc = seg_reduce(t, ow, p->ps.w[p->rank].recv_grads, t->v.opt, SegRange{0u, t->v.slots, 0xFFFFFFFFu, -1}, nullptr,
                       nullptr, T, nullptr, onames, false);
     t->grid_scale = 1.0f;
     MEEPO_TRY(rc);

@@ -319,9 +319,11 @@ size_t radix_sort_temp_bytes(uint64_t n, int end_bit) {
 // n_dev (optional, device): the true number of pairs, <= n; grids and scratch are sized for n.
 meepo_status radix_sort_pairs(meepo_table* t, char* temp, const uint32_t* k_in, uint32_t* k_out,
                               const uint32_t* v_in, uint32_t* v_out, uint32_t n, int end_bit, cudaStream_t stream,
-                              const uint32_t* n_dev) {
+                              const uint32_t* n_dev, uint32_t expect_n) {
   const int passes = (end_bit + 7) / 8;
-  const uint32_t nsub = sub_tiles(t, n);
+  // sub-tiles per CTA from the number of pairs the caller expects (a device-side count may be far below n:
+  // the CTAs past the end leave at once, the others should still fill the GPU)
+  const uint32_t nsub = sub_tiles(t, expect_n ? std::min(expect_n, n) : n);
   const uint32_t tiles = (n + nsub * kRsTile - 1) / (nsub * kRsTile);
   const uint32_t lb_stride = (n + kRsTile - 1) / kRsTile;  // look-back entries reserved per pass
   RsTemp r = carve(temp, n, passes);
@@ -361,7 +363,7 @@ extern "C" MEEPO_API meepo_status meepo_internal_sort_pairs(meepo_table* t, cons
   cudaStream_t stream = (cudaStream_t)stream_;
   MEEPO_TRY(t->ws.reserve(radix_sort_temp_bytes(n, end_bit), stream));
   char* temp = t->ws.take<char>(radix_sort_temp_bytes(n, end_bit));
-  MEEPO_TRY(radix_sort_pairs(t, temp, k_in, k_out, v_in, v_out, (uint32_t)n, end_bit, stream, nullptr));
+  MEEPO_TRY(radix_sort_pairs(t, temp, k_in, k_out, v_in, v_out, (uint32_t)n, end_bit, stream, nullptr, 0));
   MEEPO_CUDA_TRY(cudaStreamSynchronize(stream));
   return sticky_error(t);
 }

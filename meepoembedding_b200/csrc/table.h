@@ -307,9 +307,11 @@ meepo_status launch_apply_gradients(meepo_table* t, const uint64_t* keys, const 
 // side of a sharded backward pass runs on another stream than the sender side).
 struct SegScratch {
   uint32_t num_segments, num_long, num_leaves, pad;
+  uint32_t chunk_first[8];  // first segment of chunk c (kNil: the chunk is empty); only with a chunked sort key
 };
 struct SegRange {  // which segments a reduce pass takes, by sort key, and how a sort key maps to its output row
   uint32_t key_lo, key_hi, key_mask;
+  int chunk = -1;  // >= 0: the segments of this chunk only (SegScratch::chunk_first), instead of a scan of all
 };
 // Scratch of one sort + segment + reduce pipeline (update.cu); carved out of the table workspace.
 struct SegWork {
@@ -332,9 +334,12 @@ bool radix_sort_supported(uint64_t n, int end_bit);
 size_t radix_sort_temp_bytes(uint64_t n, int end_bit);
 meepo_status radix_sort_pairs(meepo_table* t, char* temp, const uint32_t* k_in, uint32_t* k_out, const uint32_t* v_in,
                               uint32_t* v_out, uint32_t n, int end_bit, cudaStream_t stream,
-                              const uint32_t* n_dev = nullptr);
+                              const uint32_t* n_dev = nullptr, uint32_t expect_n = 0);
+// chunk_shift >= 0: the sort key carries a chunk index above bit chunk_shift; the first segment of every chunk is
+// recorded (SegScratch::chunk_first) so that seg_reduce can take one chunk's segments without visiting the others
 meepo_status seg_sort_heads(meepo_table* t, SegWork& w, uint32_t miss_key, bool count_updates, const uint32_t* n_dev,
-                            cudaStream_t stream, const char* const* names);
+                            cudaStream_t stream, const char* const* names, uint32_t expect_n = 0,
+                            int chunk_shift = -1);
 meepo_status seg_reduce(meepo_table* t, SegWork& w, const void* grads, int mode, const SegRange& r, void* reduce_out,
                         void* const* reduce_rows, cudaStream_t stream, cudaEvent_t grads_ready,
                         const char* const* names, bool again);

@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(kCompactThreads) segments_kernel(const uint32_
                                                                    uint4* __restrict__ seg_desc, uint32_t miss_key,
                                                                    SegScratch* sc, unsigned long long* counters,
                                                                    int count_updates, const uint32_t* __restrict__ n_dev,
-                                                                   CompactState cs) {
+                                                                   int chunk_shift, CompactState cs) {
   if (n_dev) n = min(n, __ldg(n_dev));
   CompactTile ct = compact_begin(cs, n);
   if ((uint64_t)ct.tile * kCompactTile >= n && !(n == 0 && ct.tile == 0)) return;  // tiles past a device-side n
@@ -88,6 +88,8 @@ __global__ void __launch_bounds__(kCompactThreads) segments_kernel(const uint32_
       const uint32_t i = (uint32_t)ct.pos(k), u = (uint32_t)ct.rank(k);
       seg_start[u] = i;
       seg_desc[u] = make_uint4(i, key[k], sv[i], 0);  // {first sorted position, sort key, first batch index}
+      if (chunk_shift >= 0 && (i == 0 || (sk[i - 1] >> chunk_shift) != (key[k] >> chunk_shift)))
+        sc->chunk_first[min(key[k] >> chunk_shift, 7u)] = u;
     }
   }
   if (ct.last && threadIdx.x == 0) {
@@ -159,9 +161,27 @@ struct ApplyArgs {
                             // slot count / the batch size are the "absent key" segment, and a sharded sender reduces
                             // its unique keys chunk by chunk (the chunk index sits above the unique id)
   uint32_t key_mask;        // kStoreOnly: sort key & key_mask = index of the destination row
+  int chunk;                // >= 0: visit only the segments [first segment of this chunk, first of the next)
   uint4* reduce_out;         // kStoreOnly: [unique][cpr] ...
   uint4* const* reduce_rows;  // ... or one destination row pointer per sort key (may point into a peer's window)
 };
+
+// Segment index range of this pass: everything, or one chunk of a chunked sort key.
+__device__ __forceinline__ void segment_range(const ApplyArgs& a, uint32_t U, uint32_t& lo, uint32_t& hi) {
+  lo = 0;
+  hi = U;
+  if (a.chunk < 0) return;
+  lo = U;
+  for (int c = 7; c >= a.chunk; c--) {  // first non-empty chunk at or after a.chunk
+    const uint32_t f = a.sc->chunk_first[c];
+    if (f != kNil) lo = f;
+  }
+  for (int c = 7; c > a.chunk; c--) {
+    const uint32_t f = a.sc->chunk_first[c];
+    if (f != kNil) hi = f;
+  }
+  hi = max(hi, lo);
+}
 
 // kStoreOnly: where the summed row of sort key `key` goes.
 template <int OPT>
@@ -185,7 +205,9 @@ __global__ void __launch_bounds__(256) apply_kernel(TableView t, ApplyArgs a) {
   const uint32_t group = blockIdx.x * groups_per_block + threadIdx.x / GL;
   const uint32_t ngroups = gridDim.x * groups_per_block;
   const uint32_t U = a.sc->num_segments;
-  for (uint32_t u = group; u < U; u += ngroups) {
+  uint32_t u_lo, u_hi;
+  segment_range(a, U, u_lo, u_hi);
+  for (uint32_t u = u_lo + group; u < u_hi; u += ngroups) {
     const uint32_t s0 = a.seg_start[u], s1 = a.seg_start[u + 1];
     const uint32_t slot = a.sorted_slot[s0];
     if (slot < a.key_lo || slot >= a.key_hi) continue;  // absent / invalid keys, or another chunk
@@ -229,10 +251,12 @@ __global__ void __launch_bounds__(256) apply_pipelined_kernel(TableView t, Apply
   const uint4 nil = make_uint4(0, kNil, 0, 0);
   auto desc = [&](uint32_t i) { return i <= U ? __ldg(a.seg_desc + i) : nil; };
 
-  uint32_t u = group * 2;
+  uint32_t u_lo, u_hi;
+  segment_range(a, U, u_lo, u_hi);
+  uint32_t u = u_lo + group * 2;
   uint4 da = desc(u), db = desc(u + 1);
   uint32_t ec = desc(u + 2).x;
-  while (u < U) {
+  while (u < u_hi) {
     const uint32_t un = u + stride;
     const uint4 na = desc(un), nb = desc(un + 1);
     const uint32_t nc = desc(un + 2).x;
@@ -542,12 +566,13 @@ int bits_for(uint32_t max_value) {
 // Phase 1: stable sort of (sk_in, sv_in) by key, then the segment heads. n_dev (optional, device memory): the
 // true number of pairs (<= w.n, which sizes grids and scratch). Keys >= miss_key are "absent".
 meepo_status seg_sort_heads(meepo_table* t, SegWork& w, uint32_t miss_key, bool count_updates, const uint32_t* n_dev,
-                            cudaStream_t stream, const char* const* names) {
+                            cudaStream_t stream, const char* const* names, uint32_t expect_n, int chunk_shift) {
   const uint32_t n32 = w.n;
   {
     ProfScope ps(t, sort_scope_name(names[0], radix_sort_supported(n32, w.end_bit) ? (w.end_bit + 7) / 8 + 1 : 0), stream);
     if (radix_sort_supported(n32, w.end_bit)) {  // hand-written onesweep (radix_sort.cu); CUB only beyond 2^30 pairs
-      MEEPO_TRY(radix_sort_pairs(t, w.cub_tmp, w.sk_in, w.sk_out, w.sv_in, w.sv_out, n32, w.end_bit, stream, n_dev));
+      MEEPO_TRY(radix_sort_pairs(t, w.cub_tmp, w.sk_in, w.sk_out, w.sv_in, w.sv_out, n32, w.end_bit, stream, n_dev,
+                                 expect_n));
     } else {
       if (n_dev) return fail(MEEPO_EINVAL, "a device-side pair count needs the hand-written sort (< 2^30 pairs)");
       MEEPO_CUDA_TRY(cub::DeviceRadixSort::SortPairs(w.cub_tmp, w.cub_bytes, (const uint32_t*)w.sk_in, w.sk_out,
@@ -558,8 +583,9 @@ meepo_status seg_sort_heads(meepo_table* t, SegWork& w, uint32_t miss_key, bool 
   {
     ProfScope ps(t, names[1], stream);
     MEEPO_CUDA_TRY(cudaMemsetAsync(w.cstate, 0, w.cstate_bytes, stream));
+    if (chunk_shift >= 0) MEEPO_CUDA_TRY(cudaMemsetAsync(w.sc->chunk_first, 0xFF, sizeof w.sc->chunk_first, stream));
     segments_kernel<<<w.ntiles, kCompactThreads, 0, stream>>>(w.sk_out, w.sv_out, n32, w.seg_start, w.seg_desc, miss_key,
-                                                              w.sc, t->v.counters, count_updates ? 1 : 0, n_dev,
+                                                              w.sc, t->v.counters, count_updates ? 1 : 0, n_dev, chunk_shift,
                                                               compact_carve(w.cstate, t->err_word + kErrLookback));
     MEEPO_CUDA_TRY(cudaGetLastError());
   }
@@ -587,6 +613,7 @@ meepo_status seg_reduce(meepo_table* t, SegWork& w, const void* grads, int mode,
   a.key_lo = r.key_lo;
   a.key_hi = r.key_hi;
   a.key_mask = r.key_mask;
+  a.chunk = r.chunk;
   a.reduce_out = reinterpret_cast<uint4*>(reduce_out);
   a.reduce_rows = reinterpret_cast<uint4* const*>(reduce_rows);
   uint32_t gl = 1;
@@ -637,7 +664,7 @@ meepo_status run_segmented(meepo_table* t, SegWork& w, uint32_t limit, const voi
                            void* reduce_out, cudaStream_t stream, cudaEvent_t grads_ready,
                            const char* const* names, void* const* reduce_rows) {
   MEEPO_TRY(seg_sort_heads(t, w, limit, mode != kStoreOnly, nullptr, stream, names));
-  return seg_reduce(t, w, grads, mode, SegRange{0u, limit, 0xFFFFFFFFu}, reduce_out, reduce_rows, stream, grads_ready,
+  return seg_reduce(t, w, grads, mode, SegRange{0u, limit, 0xFFFFFFFFu, -1}, reduce_out, reduce_rows, stream, grads_ready,
                     names, false);
 }
 
