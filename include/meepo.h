@@ -38,7 +38,7 @@
  *             z ^= z >> 30; z *= 0xBF58476D1CE4E5B9; z ^= z >> 27;
  *             z *= 0x94D049BB133111EB; z ^= z >> 31.
  *           bf16 tables store round-to-nearest-even(v).
- *           Optimizer state of a new row: Adagrad accumulator = init_accum,
+ *           Optimizer state of a new row: Adagrad accumulator(s) = init_accum,
  *           Adam m = v = 0 and step = 0.
  * Status    find_or_insert reports per key: MEEPO_KEY_FOUND if the key was in
  *           the table when the call started; MEEPO_KEY_INSERTED if it was not
@@ -59,6 +59,16 @@
  *           individually (no fused multiply-add), w = row, g = G:
  *             SGD      w = w - lr*g
  *             ADAGRAD  a = a + g*g ;  w = w - (lr*g) / (sqrt(a) + eps)
+ *             ADAGRAD_ROWWISE  ONE fp32 accumulator per row (state = 16 bytes per
+ *                      row: {a, 0, 0, 0}) fed the mean square of the row's gradient,
+ *                      whose summation order is fixed as follows (a "chunk" is 16
+ *                      bytes of the row: 4 fp32 or 8 bf16 elements):
+ *                        c_q = ((g_0*g_0 + g_1*g_1) + g_2*g_2) + ...  over the
+ *                              elements of chunk q, in order
+ *                        s_r = sum of c_q over the chunks with q mod 32 == r, in
+ *                              increasing q (r = 0..31; 0 if there is none)
+ *                        for d = 16, 8, 4, 2, 1:  s_r = s_r + s_{r+d}  (r < d)
+ *                      a = a + s_0 / dim ;  w = w - (lr*g) / (sqrt(a) + eps)
  *             ADAM     t = t+1 (per row); m = beta1*m + (1-beta1)*g ;
  *                      v = beta2*v + (1-beta2)*(g*g) ;
  *                      w = w - (lr * sqrt(1-beta2^t)/(1-beta1^t)) * m
@@ -123,7 +133,7 @@ typedef enum {
 } meepo_status;
 
 typedef enum { MEEPO_F32 = 0, MEEPO_BF16 = 1 } meepo_dtype;
-typedef enum { MEEPO_SGD = 0, MEEPO_ADAGRAD = 1, MEEPO_ADAM = 2 } meepo_opt;
+typedef enum { MEEPO_SGD = 0, MEEPO_ADAGRAD = 1, MEEPO_ADAM = 2, MEEPO_ADAGRAD_ROWWISE = 3 } meepo_opt;
 typedef enum { MEEPO_LRU = 0, MEEPO_LFU = 1 } meepo_policy;
 
 /* per-key status bytes */

@@ -20,7 +20,7 @@ PRODUCT_LIB = os.path.join(HERE, "libmeepo.so")
 # enums (include/meepo.h)
 OK, EINVAL, ENOMEM, ECUDA, ENCCL, EIO = range(6)
 F32, BF16 = 0, 1
-SGD, ADAGRAD, ADAM = 0, 1, 2
+SGD, ADAGRAD, ADAM, ADAGRAD_ROWWISE = 0, 1, 2, 3
 LRU, LFU = 0, 1
 KEY_MISS, KEY_FOUND, KEY_INSERTED, KEY_FULL, KEY_INVALID = range(5)
 FLAG_TRACK_SCORES = 1

@@ -240,6 +240,7 @@ __device__ __forceinline__ uint4 init_chunk(const TableView& t, uint64_t key, ui
   return out;
 }
 __device__ __forceinline__ uint4 init_state_chunk(const TableView& t) {
+  if (t.opt == MEEPO_ADAGRAD_ROWWISE) return make_uint4(__float_as_uint(t.init_accum), 0u, 0u, 0u);
   uint32_t a = __float_as_uint(t.opt == MEEPO_ADAGRAD ? t.init_accum : 0.0f);
   return make_uint4(a, a, a, a);
 }

@@ -172,10 +172,10 @@ meepo_status import_device(meepo_table* t, const uint64_t* keys, const void* row
                                                             reinterpret_cast<const uint4*>(rows),
                                                             make_uint4(0, 0, 0, 0), 0);
   if (t->v.scpr) {
-    const uint32_t a = float_bits(t->v.opt == MEEPO_ADAGRAD ? t->v.init_accum : 0.0f);
+    const uint32_t a = float_bits(t->v.opt == MEEPO_ADAGRAD || t->v.opt == MEEPO_ADAGRAD_ROWWISE ? t->v.init_accum : 0.0f);
+    const uint4 fill = t->v.opt == MEEPO_ADAGRAD_ROWWISE ? make_uint4(a, 0, 0, 0) : make_uint4(a, a, a, a);
     arena_scatter_kernel<<<warp_grid(t, n), 256, 0, stream>>>(t->v.state, slot_buf, (uint32_t)n, t->v.scpr,
-                                                              reinterpret_cast<const uint4*>(state),
-                                                              make_uint4(a, a, a, a), state == nullptr);
+                                                              reinterpret_cast<const uint4*>(state), fill, state == nullptr);
   }
   import_meta_kernel<<<grid, 256, 0, stream>>>(t->v, slot_buf, (uint32_t)n, scores, steps);
   MEEPO_CUDA_TRY(cudaGetLastError());

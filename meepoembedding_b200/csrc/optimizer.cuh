@@ -30,7 +30,7 @@ __device__ __forceinline__ void widen(const uint4& raw, float (&g)[Chunk<BF16>::
   }
 }
 
-constexpr int kStoreOnly = 3;  // "optimizer" of meepo_reduce_duplicates: round + store the sum
+constexpr int kStoreOnly = 15;  // "optimizer" of meepo_reduce_duplicates: round + store the sum (not a meepo_opt)
 
 template <bool BF16>
 __device__ __forceinline__ uint4 narrow(const float (&w)[Chunk<BF16>::E]) {
@@ -49,7 +49,7 @@ __device__ __forceinline__ uint4 narrow(const float (&w)[Chunk<BF16>::E]) {
 template <bool BF16, int OPT>
 struct OptIn {
   static constexpr int SQ = Chunk<BF16>::E / 4;  // state uint4s per chunk
-  static constexpr int NS = OPT == MEEPO_ADAGRAD ? SQ : (OPT == MEEPO_ADAM ? 2 * SQ : 1);
+  static constexpr int NS = OPT == MEEPO_ADAGRAD ? SQ : (OPT == MEEPO_ADAM ? 2 * SQ : 1);  // row-wise Adagrad: 1
   uint4 row;
   uint4 st[NS];
 };
@@ -71,7 +71,23 @@ __device__ __forceinline__ void opt_issue(const TableView& t, uint32_t slot, uin
       in.st[k] = ld_stream(mp + k);
       in.st[SQ + k] = ld_stream(vp + k);
     }
+  } else if constexpr (OPT == MEEPO_ADAGRAD_ROWWISE) {
+    in.st[0] = ld_stream(t.state + (size_t)slot);  // the row's one accumulator: every lane of the group reads it
   }
+}
+
+// meepo.h "ADAGRAD_ROWWISE": c_q of this lane's chunk, and the reduction of the chunk sums of a group of GL lanes
+// that hold chunks 0..GL-1 (GL a power of two <= 32 = the whole row): the halving tree, as a butterfly.
+template <bool BF16>
+__device__ __forceinline__ float chunk_sumsq(const float (&g)[Chunk<BF16>::E]) {
+  float c = __fmul_rn(g[0], g[0]);
+#pragma unroll
+  for (int e = 1; e < Chunk<BF16>::E; e++) c = __fadd_rn(c, __fmul_rn(g[e], g[e]));
+  return c;
+}
+__device__ __forceinline__ float group_tree_sum(float v, uint32_t GL, unsigned gmask) {
+  for (uint32_t d = GL >> 1; d >= 1; d >>= 1) v = __fadd_rn(v, __shfl_xor_sync(gmask, v, d));
+  return v;
 }
 
 __device__ __forceinline__ void unpack4(const uint4& raw, float* f) {
@@ -84,6 +100,7 @@ __device__ __forceinline__ uint4 pack4(const float* f) {
   return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
 }
 
+// alpha: Adam's scalar step size; row-wise Adagrad: the mean square of the row's gradient (s_0 / dim).
 template <bool BF16, int OPT>
 __device__ __forceinline__ void opt_finish(const TableView& t, uint32_t slot, uint32_t q,
                                            const OptIn<BF16, OPT>& in, const float (&g)[Chunk<BF16>::E],
@@ -113,6 +130,12 @@ __device__ __forceinline__ void opt_finish(const TableView& t, uint32_t slot, ui
     }
 #pragma unroll
     for (int k = 0; k < SQ; k++) st_stream(sp + k, pack4(a + 4 * k));
+  } else if constexpr (OPT == MEEPO_ADAGRAD_ROWWISE) {
+    const float a = __fadd_rn(__uint_as_float(in.st[0].x), alpha);
+    const float den = __fadd_rn(__fsqrt_rn(a), t.eps);
+#pragma unroll
+    for (int e = 0; e < E; e++) w[e] = __fsub_rn(w[e], __fdiv_rn(__fmul_rn(t.lr, g[e]), den));
+    if (q == 0) st_stream(t.state + (size_t)slot, make_uint4(__float_as_uint(a), 0u, 0u, 0u));
   } else {
     uint4* mp = t.state + (size_t)slot * t.scpr + (size_t)q * SQ;
     uint4* vp = mp + (size_t)t.cpr * SQ;

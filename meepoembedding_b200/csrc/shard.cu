@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(256) dedup_insert_kernel(const uint64_t* __res
         if (old == MEEPO_KEY_EMPTY || old == key) {
           // the occurrence whose CAS created the cell is the key's canonical one (where a sharded forward pass
           // has the owner deliver the row; the other occurrences copy it locally)
-          if (old == MEEPO_KEY_EMPTY && canon_cell) canon_cell[h] = i;
+          if (old == MEEPO_KEY_EMPTY) canon_cell[h] = i;
           p = h;
           break;
         }
@@ -111,33 +111,38 @@ __global__ void __launch_bounds__(256) dedup_insert_kernel(const uint64_t* __res
   }
 }
 
-// occupied cells of the scratch table, in cell order -> unique ids: one ordered compaction pass (compact.cuh)
-__global__ void __launch_bounds__(kCompactThreads) occ_compact_kernel(const uint64_t* __restrict__ scratch, uint32_t m,
-                                                                      uint32_t* __restrict__ uid_of_slot,
-                                                                      uint64_t* __restrict__ unique_out,
+// Unique ids in BATCH order: element i is the canonical occurrence of its key if its CAS created the key's
+// scratch cell; the canonical occurrences, compacted in batch order (compact.cuh), number the unique keys. So
+// unique id order == order of first... of canonical appearance in the batch, which is also the order in which the
+// sharded push hands out positions in the owners' lanes: everything downstream that walks the unique keys in id
+// order (the sender-side pre-reduction storing into the owners' windows) then walks remote memory forwards.
+__global__ void __launch_bounds__(kCompactThreads) uid_compact_kernel(const uint64_t* __restrict__ keys, uint32_t n,
+                                                                      const uint32_t* __restrict__ pos,
                                                                       const uint32_t* __restrict__ canon_cell,
+                                                                      uint32_t* __restrict__ uid_of_cell,
+                                                                      uint64_t* __restrict__ unique_out,
                                                                       uint32_t* __restrict__ canon_out,
                                                                       unsigned long long* __restrict__ n_unique,
                                                                       CompactState cs,
                                                                       const uint32_t* __restrict__ skip) {
   if (skip && *skip) return;
-  CompactTile ct = compact_begin(cs, m);
+  CompactTile ct = compact_begin(cs, n);
   unsigned flags = 0;
-  uint64_t key[kCompactItems];
+  uint32_t cell[kCompactItems];
 #pragma unroll
   for (int k = 0; k < kCompactItems; k++) {
-    const uint64_t p = ct.pos(k);
-    key[k] = p < m ? scratch[p] : MEEPO_KEY_EMPTY;
-    if (key[k] != MEEPO_KEY_EMPTY) flags |= 1u << k;
+    const uint64_t i = ct.pos(k);
+    cell[k] = i < n ? pos[i] : kNil;
+    if (cell[k] != kNil && canon_cell[cell[k]] == (uint32_t)i) flags |= 1u << k;
   }
   compact_rank(ct, flags, cs);
 #pragma unroll
   for (int k = 0; k < kCompactItems; k++) {
     if ((flags >> k) & 1u) {
-      const uint32_t u = (uint32_t)ct.rank(k);
-      uid_of_slot[ct.pos(k)] = u;
-      unique_out[u] = key[k];
-      if (canon_out) canon_out[u] = canon_cell[ct.pos(k)];
+      const uint32_t u = (uint32_t)ct.rank(k), i = (uint32_t)ct.pos(k);
+      uid_of_cell[cell[k]] = u;
+      unique_out[u] = keys[i];
+      if (canon_out) canon_out[u] = i;
     }
   }
   if (ct.last && threadIdx.x == 0) *n_unique = ct.base + ct.tile_total;
@@ -209,7 +214,7 @@ size_t dedup_bytes(const meepo_table* t, uint64_t n, bool with_grads) {
   if (n == 0) return 256;
   const uint64_t m = dedup_cells(n);
   size_t need = Workspace::pad((size_t)m * 8) + Workspace::pad(n * 4) + 2 * Workspace::pad((size_t)m * 4) +
-                Workspace::pad(compact_state_bytes(m)) + 4096;
+                Workspace::pad(compact_state_bytes(n)) + 4096;
   if (with_grads) need += SegWork::bytes(n, t->v.dim, bits_for((uint32_t)n));
   return need;
 }
@@ -227,8 +232,8 @@ meepo_status dedup_hash(meepo_table* t, const uint64_t* keys, uint64_t n, const 
   uint64_t* scratch = t->ws.take<uint64_t>(m);
   uint32_t* pos = t->ws.take<uint32_t>(n);
   uint32_t* uid_of_slot = t->ws.take<uint32_t>(m);
-  uint32_t* canon_cell = o.canon ? t->ws.take<uint32_t>(m) : nullptr;
-  const size_t cbytes = compact_state_bytes(m);
+  uint32_t* canon_cell = t->ws.take<uint32_t>(m);
+  const size_t cbytes = compact_state_bytes(n);
   char* cstate = t->ws.take<char>(cbytes);
   if (with_grads) w.take(t->ws, n, t->v.dim, end_bit);
   ProfScope ps(t, "dedup.hash(3 kernels)", stream);
@@ -237,8 +242,8 @@ meepo_status dedup_hash(meepo_table* t, const uint64_t* keys, uint64_t n, const 
   if (o.occurrences) MEEPO_CUDA_TRY(cudaMemsetAsync(o.occurrences, 0, n * 4, stream));
   const int grid = grid_for(t, (const void*)dedup_insert_kernel, 256, 0, (n + 255) / 256);
   dedup_insert_kernel<<<grid, 256, 0, stream>>>(keys, (uint32_t)n, scratch, m - 1, pos, canon_cell, skip);
-  occ_compact_kernel<<<compact_tiles(m), kCompactThreads, 0, stream>>>(scratch, m, uid_of_slot, o.unique_keys,
-                                                                       canon_cell, o.canon,
+  uid_compact_kernel<<<compact_tiles(n), kCompactThreads, 0, stream>>>(keys, (uint32_t)n, pos, canon_cell, uid_of_slot,
+                                                                       o.unique_keys, o.canon,
                                                                        (unsigned long long*)o.n_unique,
                                                                        compact_carve(cstate, t->err_word + kErrLookback),
                                                                        skip);

@@ -117,7 +117,7 @@ MEEPO_API meepo_status meepo_destroy(meepo_table* t);
 MEEPO_API meepo_status meepo_create(const meepo_config* cfg, meepo_table** out) {
   if (!cfg || !out) return fail(MEEPO_EINVAL, "null argument");
   if (cfg->dtype != MEEPO_F32 && cfg->dtype != MEEPO_BF16) return fail(MEEPO_EINVAL, "bad dtype");
-  if (cfg->opt < MEEPO_SGD || cfg->opt > MEEPO_ADAM) return fail(MEEPO_EINVAL, "bad optimizer");
+  if (cfg->opt < MEEPO_SGD || cfg->opt > MEEPO_ADAGRAD_ROWWISE) return fail(MEEPO_EINVAL, "bad optimizer");
   const uint32_t esz = cfg->dtype == MEEPO_F32 ? 4 : 2;
   if (cfg->dim == 0 || ((uint64_t)cfg->dim * esz) % 16 != 0)
     return fail(MEEPO_EINVAL, "row bytes must be a positive multiple of 16");
@@ -140,7 +140,10 @@ MEEPO_API meepo_status meepo_create(const meepo_config* cfg, meepo_table** out) 
   t->num_sms = prop.multiProcessorCount;
   const uint64_t slots = (cfg->capacity + kBucket - 1) / kBucket * kBucket;
   t->row_bytes = cfg->dim * esz;
-  t->state_bytes = cfg->opt == MEEPO_SGD ? 0 : (cfg->opt == MEEPO_ADAGRAD ? cfg->dim * 4 : cfg->dim * 8);
+  t->state_bytes = cfg->opt == MEEPO_SGD              ? 0
+                   : cfg->opt == MEEPO_ADAGRAD        ? cfg->dim * 4
+                   : cfg->opt == MEEPO_ADAGRAD_ROWWISE ? 16  // one accumulator + padding to a 16-byte chunk
+                                                       : cfg->dim * 8;
   TableView& v = t->v;
   v.slots = (uint32_t)slots;
   v.num_buckets = (uint32_t)(slots / kBucket);

@@ -327,7 +327,7 @@ struct SegWork {
   static size_t bytes(uint64_t n, uint32_t dim, int end_bit);
   void take(Workspace& ws, uint64_t n, uint32_t dim, int end_bit);
 };
-constexpr int kReduceStoreOnly = 3;
+constexpr int kReduceStoreOnly = 15;  // == kStoreOnly (optimizer.cuh): not a meepo_opt
 int bits_for(uint32_t max_value);
 // radix_sort.cu: stable LSD sort of (u32 key, u32 value) pairs on key bits [0, end_bit)
 bool radix_sort_supported(uint64_t n, int end_bit);

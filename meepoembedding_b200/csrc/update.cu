@@ -224,11 +224,33 @@ __global__ void __launch_bounds__(256) apply_kernel(TableView t, ApplyArgs a) {
       for (uint32_t c = gl; c < nleaf; c += GL) a.leaf_desc[base + c] = make_uint2(u, c);
       continue;
     }
-    const float alpha = adam_alpha<OPT>(t, slot, gmask, gl == 0);
+    float alpha = adam_alpha<OPT>(t, slot, gmask, gl == 0);
+    uint32_t accum = 0;  // row-wise Adagrad: the accumulator as it was before this step
+    if constexpr (OPT == MEEPO_ADAGRAD_ROWWISE) {
+      // meepo.h: s_r over this lane's chunk classes r = gl + m * GL, the halving tree inside the lane for the
+      // distances >= GL, then across the lanes of the group. A first pass over the gradients (the update
+      // below reduces them again: this is the fallback kernel for rows that are not <= 32 chunks, a power of two)
+      const uint32_t M = 32u / GL;
+      float cls[32];
+      for (uint32_t m = 0; m < M; m++) cls[m] = 0.0f;
+      uint32_t j = 0;
+      for (uint32_t q = gl; q < t.cpr; q += GL, j++) {
+        float acc[E];
+        reduce_positions<BF16>(a.grads, a.sorted_idx, s0, s1, t.cpr, q, acc);
+        cls[j % M] = __fadd_rn(cls[j % M], chunk_sumsq<BF16>(acc));
+      }
+      for (uint32_t h = M >> 1; h >= 1; h >>= 1)
+        for (uint32_t m = 0; m < h; m++) cls[m] = __fadd_rn(cls[m], cls[m + h]);
+      alpha = __fdiv_rn(group_tree_sum(cls[0], GL, gmask), (float)t.dim);
+      accum = __shfl_sync(gmask, t.state[slot].x, lane & ~(GL - 1));  // read before any lane of the group stores it
+    }
     for (uint32_t q = gl; q < t.cpr; q += GL) {
       float acc[E];
       reduce_positions<BF16>(a.grads, a.sorted_idx, s0, s1, t.cpr, q, acc);
-      optimizer_chunk<BF16, OPT>(t, slot, q, acc, alpha, reduce_row_of<OPT>(a, slot, t.cpr));
+      OptIn<BF16, OPT> in;
+      opt_issue<BF16, OPT>(t, slot, q, in);
+      if constexpr (OPT == MEEPO_ADAGRAD_ROWWISE) in.st[0].x = accum;
+      opt_finish<BF16, OPT>(t, slot, q, in, acc, alpha, reduce_row_of<OPT>(a, slot, t.cpr));
     }
   }
 }
@@ -291,17 +313,25 @@ __global__ void __launch_bounds__(256) apply_pipelined_kernel(TableView t, Apply
       }
     }
     if (okA) {
-      const float alpha = adam_alpha<OPT>(t, da.y, gmask, q == 0);
+      float alpha = adam_alpha<OPT>(t, da.y, gmask, q == 0);
       float acc[E];
       widen<BF16>(gA, acc);
       if (cntA > 1) reduce_tail<BF16>(a.grads, a.sorted_idx, da.x + 1, da.x + cntA, cpr, q, acc);
+      if constexpr (OPT == MEEPO_ADAGRAD_ROWWISE) {  // lane q holds chunk q: the tree is a butterfly over the group
+        alpha = __fdiv_rn(group_tree_sum(chunk_sumsq<BF16>(acc), GL, gmask), (float)t.dim);
+        inA.st[0].x = __shfl_sync(gmask, inA.st[0].x, lane & ~(GL - 1));  // the value lane 0 (the writer) loaded
+      }
       opt_finish<BF16, OPT>(t, da.y, q, inA, acc, alpha, reduce_row_of<OPT>(a, da.y, cpr));
     }
     if (okB) {
-      const float alpha = adam_alpha<OPT>(t, db.y, gmask, q == 0);
+      float alpha = adam_alpha<OPT>(t, db.y, gmask, q == 0);
       float acc[E];
       widen<BF16>(gB, acc);
       if (cntB > 1) reduce_tail<BF16>(a.grads, a.sorted_idx, db.x + 1, db.x + cntB, cpr, q, acc);
+      if constexpr (OPT == MEEPO_ADAGRAD_ROWWISE) {
+        alpha = __fdiv_rn(group_tree_sum(chunk_sumsq<BF16>(acc), GL, gmask), (float)t.dim);
+        inB.st[0].x = __shfl_sync(gmask, inB.st[0].x, lane & ~(GL - 1));
+      }
       opt_finish<BF16, OPT>(t, db.y, q, inB, acc, alpha, reduce_row_of<OPT>(a, db.y, cpr));
     }
     da = na;
@@ -433,6 +463,7 @@ __global__ void __launch_bounds__(256) long_finish_kernel(TableView t, ApplyArgs
   constexpr int D = 32;
   extern __shared__ float sum_s[];  // [dim]
   __shared__ float alpha_s;
+  __shared__ uint32_t accum_s;  // row-wise Adagrad: the accumulator before this step
   const uint32_t nlong = a.sc->num_long;
   for (uint32_t li = blockIdx.x; li < nlong; li += gridDim.x) {
     const LongSeg ls = a.long_seg[li];
@@ -469,11 +500,30 @@ __global__ void __launch_bounds__(256) long_finish_kernel(TableView t, ApplyArgs
       }
     }
     __syncthreads();
+    if constexpr (OPT == MEEPO_ADAGRAD_ROWWISE) {
+      if (threadIdx.x == 0) {  // meepo.h: chunk sums, classes q mod 32 in increasing q, halving tree (a few hundred flops)
+        float cls[32];
+        for (int r = 0; r < 32; r++) cls[r] = 0.0f;
+        for (uint32_t q = 0; q < t.cpr; q++) {
+          float c = __fmul_rn(sum_s[q * E], sum_s[q * E]);
+          for (int e = 1; e < E; e++) c = __fadd_rn(c, __fmul_rn(sum_s[q * E + e], sum_s[q * E + e]));
+          cls[q & 31u] = __fadd_rn(cls[q & 31u], c);
+        }
+        for (int d = 16; d >= 1; d >>= 1)
+          for (int r = 0; r < d; r++) cls[r] = __fadd_rn(cls[r], cls[r + d]);
+        alpha_s = __fdiv_rn(cls[0], (float)t.dim);
+        accum_s = t.state[slot].x;
+      }
+      __syncthreads();
+    }
     for (uint32_t q = threadIdx.x; q < t.cpr; q += blockDim.x) {
       float acc[E];
 #pragma unroll
       for (int e = 0; e < E; e++) acc[e] = sum_s[q * E + e];
-      optimizer_chunk<BF16, OPT>(t, slot, q, acc, alpha_s, reduce_row_of<OPT>(a, slot, t.cpr));
+      OptIn<BF16, OPT> in;
+      opt_issue<BF16, OPT>(t, slot, q, in);
+      if constexpr (OPT == MEEPO_ADAGRAD_ROWWISE) in.st[0].x = accum_s;
+      opt_finish<BF16, OPT>(t, slot, q, in, acc, alpha_s, reduce_row_of<OPT>(a, slot, t.cpr));
     }
     __syncthreads();
   }
@@ -486,6 +536,7 @@ static void pick_apply(int opt, bool pipelined, const void*& apply, const void*&
       case MEEPO_SGD: apply = (const void*)apply_pipelined_kernel<BF16, MEEPO_SGD>; break;
       case MEEPO_ADAGRAD: apply = (const void*)apply_pipelined_kernel<BF16, MEEPO_ADAGRAD>; break;
       case MEEPO_ADAM: apply = (const void*)apply_pipelined_kernel<BF16, MEEPO_ADAM>; break;
+      case MEEPO_ADAGRAD_ROWWISE: apply = (const void*)apply_pipelined_kernel<BF16, MEEPO_ADAGRAD_ROWWISE>; break;
       default: apply = (const void*)apply_pipelined_kernel<BF16, kStoreOnly>;
     }
   }
@@ -502,6 +553,10 @@ static void pick_apply(int opt, bool pipelined, const void*& apply, const void*&
     case MEEPO_ADAM:
       plain = (const void*)apply_kernel<BF16, MEEPO_ADAM>;
       finish = (const void*)long_finish_kernel<BF16, MEEPO_ADAM>;
+      break;
+    case MEEPO_ADAGRAD_ROWWISE:
+      plain = (const void*)apply_kernel<BF16, MEEPO_ADAGRAD_ROWWISE>;
+      finish = (const void*)long_finish_kernel<BF16, MEEPO_ADAGRAD_ROWWISE>;
       break;
     default:
       plain = (const void*)apply_kernel<BF16, kStoreOnly>;

@@ -17,7 +17,7 @@ import numpy as np
 from . import _capi as capi
 
 _DTYPES = {"f32": capi.F32, "fp32": capi.F32, "float32": capi.F32, "bf16": capi.BF16, "bfloat16": capi.BF16}
-_OPTS = {"sgd": capi.SGD, "adagrad": capi.ADAGRAD, "adam": capi.ADAM}
+_OPTS = {"sgd": capi.SGD, "adagrad": capi.ADAGRAD, "adam": capi.ADAM, "adagrad_rowwise": capi.ADAGRAD_ROWWISE}
 _POLICIES = {"lru": capi.LRU, "lfu": capi.LFU}
 
 

@@ -26,6 +26,8 @@ CASES = {
     "f32_adagrad": dict(dim=8, capacity=512, dtype="f32", optimizer="adagrad"),
     "bf16_adam": dict(dim=16, capacity=512, dtype="bf16", optimizer="adam"),
     "f32_sgd": dict(dim=4, capacity=256, dtype="f32", optimizer="sgd"),
+    "f32_rowwise": dict(dim=24, capacity=512, dtype="f32", optimizer="adagrad_rowwise"),
+    "bf16_rowwise": dict(dim=264, capacity=512, dtype="bf16", optimizer="adagrad_rowwise"),  # 33 chunks: two classes share r = 0
 }
 STEPS = 4
 

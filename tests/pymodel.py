@@ -66,7 +66,25 @@ class Model:
             return np.zeros(0, dtype=F)
         if self.opt == capi.ADAGRAD:
             return np.full(self.dim, self.init_accum, dtype=F)
+        if self.opt == capi.ADAGRAD_ROWWISE:
+            return np.array([self.init_accum, 0, 0, 0], dtype=F)  # one accumulator + 12 bytes of padding
         return np.zeros(2 * self.dim, dtype=F)
+
+    def _row_mean_square(self, g):
+        """include/meepo.h ADAGRAD_ROWWISE: chunk sums in element order, classes q mod 32, halving tree."""
+        E = 4 if self.dtype == capi.F32 else 8
+        cls = [F(0.0)] * 32
+        for q in range(self.dim // E):
+            c = g[q * E] * g[q * E]
+            for e in range(1, E):
+                c = F(c + g[q * E + e] * g[q * E + e])
+            cls[q & 31] = F(cls[q & 31] + c)
+        d = 16
+        while d >= 1:
+            for r in range(d):
+                cls[r] = F(cls[r] + cls[r + d])
+            d //= 2
+        return F(cls[0] / F(self.dim))
 
     @staticmethod
     def valid(k):
@@ -134,6 +152,10 @@ class Model:
                 a = self.state[k] + g * g
                 w = w - (self.lr * g) / (np.sqrt(a) + self.eps)
                 self.state[k] = a
+            elif self.opt == capi.ADAGRAD_ROWWISE:
+                a = F(self.state[k][0] + self._row_mean_square(g))
+                w = w - (self.lr * g) / F(np.sqrt(a) + self.eps)
+                self.state[k] = np.array([a, 0, 0, 0], dtype=F)
             else:
                 self.step[k] += 1
                 t = self.step[k]

@@ -11,7 +11,7 @@ import pytest
 from meepoembedding_b200 import Table, keygen
 from meepoembedding_b200 import _capi as capi
 
-from util import grads_for, make_keys, rows_as_f32, table_kwargs
+from util import export_sorted, grads_for, make_keys, rows_as_f32, table_kwargs
 
 pytestmark = pytest.mark.gpu
 
@@ -56,7 +56,7 @@ def test_find_or_insert_and_lookup_bit_exact(oracle_lib, cuda_lib, dtype, dim):
 
 
 @pytest.mark.parametrize("dtype", ["f32", "bf16"])
-@pytest.mark.parametrize("optimizer", ["sgd", "adagrad", "adam"])
+@pytest.mark.parametrize("optimizer", ["sgd", "adagrad", "adam", "adagrad_rowwise"])
 def test_apply_gradients_parity(oracle_lib, cuda_lib, dtype, optimizer):
     from gpu_util import gpu_apply, gpu_foi
 
@@ -79,6 +79,28 @@ def test_apply_gradients_parity(oracle_lib, cuda_lib, dtype, optimizer):
     assert min(exact) > 0.999, exact
     gs, os_ = g.stats(), o.stats()
     assert gs["updates"] == os_["updates"] and gs["grad_dropped"] == os_["grad_dropped"]
+
+
+@pytest.mark.parametrize("dtype,dim", [("f32", 128), ("bf16", 128), ("f32", 4), ("f32", 24), ("bf16", 48), ("f32", 256),
+                                       ("bf16", 1024), ("f32", 520)])
+def test_rowwise_adagrad_shapes(oracle_lib, cuda_lib, dtype, dim):
+    """Row-wise Adagrad (one accumulator per row, include/meepo.h): the mean square of the row's gradient follows a
+    fixed summation tree, so every kernel shape — the pipelined kernel (<= 32 chunks, a power of two), the
+    fallback kernel (any chunk count, classes of chunks per lane) and the long-segment finish — must agree with
+    the oracle bit for bit, state included."""
+    from gpu_util import gpu_apply, gpu_export, gpu_foi
+
+    rng = np.random.default_rng(dim)
+    g, o = pair(oracle_lib, cuda_lib, dim=dim, capacity=4096, dtype=dtype, optimizer="adagrad_rowwise")
+    assert g.state_bytes == 16 == o.state_bytes
+    for step in range(4):
+        keys = make_keys(rng, 1500, 900, dup_frac=0.5)
+        keys[rng.choice(1500, size=300, replace=False)] = np.uint64(777)  # a long segment: leaves + finish kernel
+        gpu_foi(g, keys, dtype), o.find_or_insert(keys)
+        gr = grads_for(dtype, rng.normal(0, 0.3, size=(keys.size, dim)))
+        gpu_apply(g, keys, gr, dtype), o.apply_gradients(keys, gr)
+        for name, a, b in zip(("keys", "rows", "state"), gpu_export(g), export_sorted(o)):
+            np.testing.assert_array_equal(a, b, err_msg=f"{name}, step {step}")
 
 
 @pytest.mark.parametrize("dtype", ["f32", "bf16"])

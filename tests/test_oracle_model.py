@@ -38,7 +38,7 @@ def check_table_equal(t, m, dtype):
 
 
 @pytest.mark.parametrize("dtype", ["f32", "bf16"])
-@pytest.mark.parametrize("optimizer", ["sgd", "adagrad", "adam"])
+@pytest.mark.parametrize("optimizer", ["sgd", "adagrad", "adam", "adagrad_rowwise"])
 def test_stream_matches_model(oracle_lib, dtype, optimizer):
     rng = np.random.default_rng(42)
     t, m = make_pair(oracle_lib, dim=16, capacity=2048, dtype=dtype, optimizer=optimizer, track_scores=True)
@@ -194,7 +194,7 @@ def test_bad_arguments(oracle_lib):
 @settings(max_examples=40, deadline=None)
 @given(st.lists(st.tuples(st.sampled_from(["foi", "lookup", "grad", "evict"]),
                           st.lists(st.integers(0, 40), min_size=0, max_size=60)), min_size=1, max_size=8),
-       st.sampled_from(["f32", "bf16"]), st.sampled_from(["sgd", "adagrad", "adam"]))
+       st.sampled_from(["f32", "bf16"]), st.sampled_from(["sgd", "adagrad", "adam", "adagrad_rowwise"]))
 def test_hypothesis_streams(oracle_lib, ops, dtype, optimizer):
     special = {38: capi.KEY_EMPTY, 39: capi.KEY_RESERVED, 40: capi.KEY_RESERVED - 1, 0: 0}
     t, m = make_pair(oracle_lib, dim=8, capacity=32, dtype=dtype, optimizer=optimizer, track_scores=True)

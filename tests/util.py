@@ -5,7 +5,7 @@ from meepoembedding_b200 import Table, keygen
 from meepoembedding_b200 import _capi as capi
 
 DT = {"f32": capi.F32, "bf16": capi.BF16}
-OPT = {"sgd": capi.SGD, "adagrad": capi.ADAGRAD, "adam": capi.ADAM}
+OPT = {"sgd": capi.SGD, "adagrad": capi.ADAGRAD, "adam": capi.ADAM, "adagrad_rowwise": capi.ADAGRAD_ROWWISE}
 
 
 def rows_as_f32(rows: np.ndarray, dtype: str) -> np.ndarray:
