@@ -112,7 +112,7 @@ extern "C" {
 #define MEEPO_API
 #endif
 
-#define MEEPO_ABI_VERSION 2u
+#define MEEPO_ABI_VERSION 3u
 #define MEEPO_KEY_EMPTY 0xFFFFFFFFFFFFFFFFull
 #define MEEPO_KEY_RESERVED 0xFFFFFFFFFFFFFFFEull
 #define MEEPO_REDUCE_LEAF 256u
@@ -145,7 +145,7 @@ enum {
   MEEPO_KEY_INVALID = 4
 };
 
-enum { MEEPO_FLAG_TRACK_SCORES = 1u };
+enum { MEEPO_FLAG_TRACK_SCORES = 1u, MEEPO_FLAG_TRACK_DIRTY = 2u };
 
 typedef struct {
   uint32_t dim;          /* elements per row */
@@ -282,6 +282,21 @@ MEEPO_API meepo_status meepo_import_buffers(meepo_table* t, const uint64_t* keys
  * files for identical tables. */
 MEEPO_API meepo_status meepo_export(meepo_table* t, const char* path);
 MEEPO_API meepo_status meepo_import(meepo_table* t, const char* path);
+/* Incremental export (needs MEEPO_FLAG_TRACK_DIRTY). The table remembers which
+ * tuples were inserted (find_or_insert), updated (apply_gradients), imported or
+ * re-admitted since they were last written by a delta export (or since create).
+ * meepo_export_delta_buffers returns exactly those tuples, sorted by key, with
+ * the calling convention of meepo_export_buffers, and marks them clean; a pure
+ * size query (keys == NULL) marks nothing. meepo_export_delta writes them as a
+ * file of the same "MEEPOTB1" format, so meepo_import applies a delta as an
+ * upsert: a full export followed by the deltas taken after it, imported in
+ * order, reproduces the table's tuples (keys evicted in between stay in the
+ * importing table: a delta carries no deletions). Full exports neither read nor
+ * change the marks. Eviction forgets the mark of the evicted tuple. */
+MEEPO_API meepo_status meepo_export_delta_buffers(meepo_table* t, uint64_t* keys, void* rows, void* state,
+                                                  uint64_t* scores, uint32_t* steps, uint64_t max_n,
+                                                  uint64_t* n_out);
+MEEPO_API meepo_status meepo_export_delta(meepo_table* t, const char* path);
 
 /* --- sharding helpers (one process per GPU; the exchange itself is the
  *     caller's collective: torch.distributed / NCCL all-to-all, or the fused

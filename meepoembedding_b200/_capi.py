@@ -24,12 +24,13 @@ SGD, ADAGRAD, ADAM, ADAGRAD_ROWWISE = 0, 1, 2, 3
 LRU, LFU = 0, 1
 KEY_MISS, KEY_FOUND, KEY_INSERTED, KEY_FULL, KEY_INVALID = range(5)
 FLAG_TRACK_SCORES = 1
+FLAG_TRACK_DIRTY = 2
 KEY_EMPTY = 0xFFFFFFFFFFFFFFFF
 KEY_RESERVED = 0xFFFFFFFFFFFFFFFE
 REDUCE_LEAF = 256
 MAX_PEERS = 8
 PEER_BLOB_BYTES = 256
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class Config(C.Structure):
@@ -108,7 +109,9 @@ SIGNATURES = {
     "meepo_spill_readmit": (C.c_int, [_P, _P, _U64, _P]),
     "meepo_export_buffers": (C.c_int, [_P, _P, _P, _P, _P, _P, _U64, C.POINTER(_U64)]),
     "meepo_import_buffers": (C.c_int, [_P, _P, _P, _P, _P, _P, _U64, _P]),
+    "meepo_export_delta_buffers": (C.c_int, [_P, _P, _P, _P, _P, _P, _U64, C.POINTER(_U64)]),
     "meepo_export": (C.c_int, [_P, C.c_char_p]),
+    "meepo_export_delta": (C.c_int, [_P, C.c_char_p]),
     "meepo_import": (C.c_int, [_P, C.c_char_p]),
     "meepo_owner": (C.c_uint32, [_U64, _U32]),
     "meepo_shard_partition": (C.c_int, [_P, _P, _U64, _U32, _P, _P, _P, _P]),

@@ -45,6 +45,7 @@ struct TableView {
   uint4* state;
   uint2* scores;
   uint32_t* steps;
+  uint32_t* dirty;  // one bit per slot, only with MEEPO_FLAG_TRACK_DIRTY: inserted / updated since the last delta export
   unsigned long long* counters;
   uint32_t num_buckets, slots;
   uint32_t cpr, scpr;  // 16-byte chunks per row / per state row
@@ -206,6 +207,13 @@ __device__ __forceinline__ Probe probe_find_or_insert(const TB& t, uint64_t key)
   }
   r.status = MEEPO_KEY_FULL;
   return r;
+}
+
+__device__ __forceinline__ void mark_dirty(const TableView& t, uint32_t slot) {
+  if (t.dirty) atomicOr(t.dirty + (slot >> 5), 1u << (slot & 31u));
+}
+__device__ __forceinline__ void mark_clean(const TableView& t, uint32_t slot) {
+  if (t.dirty) atomicAnd(t.dirty + (slot >> 5), ~(1u << (slot & 31u)));
 }
 
 // --- row init (meepo.h "Init") -----------------------------------------------------------------

@@ -131,6 +131,7 @@ __global__ void release_kernel(TableView t, const uint32_t* __restrict__ vslot, 
     *tag_ptr(t, s) = 0;
     t.scores[s] = make_uint2(0, 0);
     if (t.steps) t.steps[s] = 0;
+    mark_clean(t, s);
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     atomicAdd(t.counters + C_SIZE, (unsigned long long)(-(long long)k));
@@ -180,6 +181,7 @@ __global__ void __launch_bounds__(256) readmit_copy_kernel(TableView t, SpillVie
       const uint4 m = sp.meta[d];
       if (t.scores) t.scores[s] = make_uint2(m.z, m.w);
       if (t.steps) t.steps[s] = sp.steps[d];
+      mark_dirty(t, s);
     }
   }
 }

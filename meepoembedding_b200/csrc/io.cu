@@ -14,10 +14,11 @@
 namespace meepo {
 
 // live (key, slot) pairs in slot order: one ordered compaction pass (compact.cuh)
+// (delta: only the slots whose dirty bit is set — meepo.h "Incremental export")
 __global__ void __launch_bounds__(kCompactThreads) live_compact_kernel(TableView t, uint32_t m,
                                                                        uint64_t* __restrict__ live_key,
                                                                        uint32_t* __restrict__ live_slot,
-                                                                       CompactState cs) {
+                                                                       CompactState cs, int delta) {
   CompactTile ct = compact_begin(cs, m);
   unsigned flags = 0;
   uint64_t key[kCompactItems];
@@ -25,6 +26,7 @@ __global__ void __launch_bounds__(kCompactThreads) live_compact_kernel(TableView
   for (int k = 0; k < kCompactItems; k++) {
     const uint64_t p = ct.pos(k);
     key[k] = p < m ? *key_ptr(t, (uint32_t)p) : MEEPO_KEY_EMPTY;
+    if (delta && p < m && !((t.dirty[p >> 5] >> (p & 31u)) & 1u)) key[k] = MEEPO_KEY_EMPTY;
     if (key[k] != MEEPO_KEY_EMPTY) flags |= 1u << k;
   }
   compact_rank(ct, flags, cs);
@@ -75,6 +77,14 @@ __global__ void export_meta_kernel(TableView t, const uint32_t* __restrict__ slo
     if (steps) steps[j] = t.steps ? t.steps[s] : 0u;
   }
 }
+// number of dirty slots (a released slot never keeps its bit: evict.cu release_kernel)
+__global__ void __launch_bounds__(256) dirty_count_kernel(const uint32_t* __restrict__ dirty, uint32_t words,
+                                                          unsigned long long* __restrict__ out) {
+  uint32_t c = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < words; i += gridDim.x * blockDim.x) c += __popc(dirty[i]);
+  c = __reduce_add_sync(0xFFFFFFFFu, c);
+  if ((threadIdx.x & 31u) == 0 && c) atomicAdd(out, (unsigned long long)c);
+}
 __global__ void import_meta_kernel(TableView t, const uint32_t* __restrict__ slot, uint32_t n,
                                    const uint64_t* __restrict__ scores, const uint32_t* __restrict__ steps) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -85,6 +95,7 @@ __global__ void import_meta_kernel(TableView t, const uint32_t* __restrict__ slo
       t.scores[s] = make_uint2((uint32_t)sc, (uint32_t)(sc >> 32));
     }
     if (t.steps) t.steps[s] = steps ? steps[i] : 0u;
+    mark_dirty(t, s);
   }
 }
 
@@ -123,9 +134,27 @@ meepo_status live_size(meepo_table* t, uint64_t* out) {
   return MEEPO_OK;
 }
 
-// Live (key, slot) pairs sorted by key, left in the workspace. Synchronous.
+static meepo_status dirty_size(meepo_table* t, uint64_t* out) {
+  if (!t->v.dirty) return fail(MEEPO_EINVAL, "incremental export needs MEEPO_FLAG_TRACK_DIRTY");
+  unsigned long long v = 0;
+  unsigned long long* cell = t->dstate->scratch64;
+  const uint32_t words = (t->v.slots + 31) / 32;
+  MEEPO_CUDA_TRY(cudaDeviceSynchronize());
+  MEEPO_CUDA_TRY(cudaMemsetAsync(cell, 0, 8, nullptr));
+  dirty_count_kernel<<<std::min<uint32_t>((words + 255) / 256, (uint32_t)t->num_sms * 8), 256>>>(t->v.dirty, words, cell);
+  MEEPO_CUDA_TRY(cudaGetLastError());
+  MEEPO_CUDA_TRY(cudaMemcpy(&v, cell, 8, cudaMemcpyDeviceToHost));
+  *out = v;
+  return MEEPO_OK;
+}
+static meepo_status dirty_clear(meepo_table* t, cudaStream_t stream) {
+  MEEPO_CUDA_TRY(cudaMemsetAsync(t->v.dirty, 0, (size_t)((t->v.slots + 31) / 32) * 4, stream));
+  return MEEPO_OK;
+}
+
+// Live (key, slot) pairs sorted by key, left in the workspace (delta: the dirty ones only). Synchronous.
 meepo_status sorted_live(meepo_table* t, uint64_t n, uint64_t** keys_sorted, uint32_t** slots_sorted,
-                         cudaStream_t stream) {
+                         cudaStream_t stream, bool delta = false) {
   const uint32_t m = t->v.slots;
   const size_t cbytes = compact_state_bytes(m);
   size_t cub_bytes = 0;
@@ -142,7 +171,8 @@ meepo_status sorted_live(meepo_table* t, uint64_t n, uint64_t** keys_sorted, uin
   char* cstate = t->ws.take<char>(cbytes);
   MEEPO_CUDA_TRY(cudaMemsetAsync(cstate, 0, cbytes, stream));
   live_compact_kernel<<<compact_tiles(m), kCompactThreads, 0, stream>>>(t->v, m, k_in, s_in,
-                                                                        compact_carve(cstate, t->err_word + kErrLookback));
+                                                                        compact_carve(cstate, t->err_word + kErrLookback),
+                                                                        delta ? 1 : 0);
   MEEPO_CUDA_TRY(cudaGetLastError());
   if (n)
     MEEPO_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, cub_bytes, (const uint64_t*)k_in, k_out, (const uint32_t*)s_in,
@@ -197,14 +227,14 @@ static_assert(sizeof(FileHeader) == 56, "header layout");
 
 extern "C" {
 
-MEEPO_API meepo_status meepo_export_buffers(meepo_table* t, uint64_t* keys, void* rows, void* state,
-                                            uint64_t* scores, uint32_t* steps, uint64_t max_n, uint64_t* n_out) {
+static meepo_status export_buffers_impl(meepo_table* t, uint64_t* keys, void* rows, void* state, uint64_t* scores,
+                                        uint32_t* steps, uint64_t max_n, uint64_t* n_out, bool delta) {
   if (!t || !n_out) return fail(MEEPO_EINVAL, "null argument");
   DeviceGuard guard(t->device);
   VerbScope vs(t, nullptr);
   MEEPO_TRY(vs.rc);
   uint64_t n = 0;
-  MEEPO_TRY(live_size(t, &n));
+  MEEPO_TRY(delta ? dirty_size(t, &n) : live_size(t, &n));
   *n_out = n;
   if (!keys) return MEEPO_OK;
   if (max_n < n) return fail(MEEPO_EINVAL, "export buffers too small");
@@ -212,7 +242,7 @@ MEEPO_API meepo_status meepo_export_buffers(meepo_table* t, uint64_t* keys, void
   cudaStream_t stream = nullptr;
   uint64_t* ks;
   uint32_t* ss;
-  MEEPO_TRY(sorted_live(t, n, &ks, &ss, stream));
+  MEEPO_TRY(sorted_live(t, n, &ks, &ss, stream, delta));
   MEEPO_CUDA_TRY(cudaMemcpyAsync(keys, ks, n * 8, cudaMemcpyDeviceToDevice, stream));
   if (rows)
     arena_gather_kernel<<<warp_grid(t, n), 256, 0, stream>>>(t->v.rows, ss, (uint32_t)n, t->v.cpr,
@@ -222,8 +252,19 @@ MEEPO_API meepo_status meepo_export_buffers(meepo_table* t, uint64_t* keys, void
                                                              reinterpret_cast<uint4*>(state));
   if (scores || steps) export_meta_kernel<<<warp_grid(t, n), 256, 0, stream>>>(t->v, ss, (uint32_t)n, scores, steps);
   MEEPO_CUDA_TRY(cudaGetLastError());
+  if (delta) MEEPO_TRY(dirty_clear(t, stream));
   MEEPO_CUDA_TRY(cudaStreamSynchronize(stream));
   return MEEPO_OK;
+}
+
+MEEPO_API meepo_status meepo_export_buffers(meepo_table* t, uint64_t* keys, void* rows, void* state,
+                                            uint64_t* scores, uint32_t* steps, uint64_t max_n, uint64_t* n_out) {
+  return export_buffers_impl(t, keys, rows, state, scores, steps, max_n, n_out, false);
+}
+MEEPO_API meepo_status meepo_export_delta_buffers(meepo_table* t, uint64_t* keys, void* rows, void* state,
+                                                  uint64_t* scores, uint32_t* steps, uint64_t max_n,
+                                                  uint64_t* n_out) {
+  return export_buffers_impl(t, keys, rows, state, scores, steps, max_n, n_out, true);
 }
 
 MEEPO_API meepo_status meepo_import_buffers(meepo_table* t, const uint64_t* keys, const void* rows,
@@ -245,13 +286,13 @@ MEEPO_API meepo_status meepo_import_buffers(meepo_table* t, const uint64_t* keys
   return MEEPO_OK;
 }
 
-MEEPO_API meepo_status meepo_export(meepo_table* t, const char* path) {
+static meepo_status export_file_impl(meepo_table* t, const char* path, bool delta) {
   if (!t || !path) return fail(MEEPO_EINVAL, "null argument");
   DeviceGuard guard(t->device);
   VerbScope vs(t, nullptr);
   MEEPO_TRY(vs.rc);
   uint64_t n = 0;
-  MEEPO_TRY(live_size(t, &n));
+  MEEPO_TRY(delta ? dirty_size(t, &n) : live_size(t, &n));
   FILE* f = fopen(path, "wb");
   if (!f) return fail(MEEPO_EIO, std::string("cannot open ") + path);
   std::unique_ptr<FILE, int (*)(FILE*)> closer(f, fclose);
@@ -270,7 +311,7 @@ MEEPO_API meepo_status meepo_export(meepo_table* t, const char* path) {
   cudaStream_t stream = nullptr;
   uint64_t* ks;
   uint32_t* ss;
-  MEEPO_TRY(sorted_live(t, n, &ks, &ss, stream));  // stays valid: nothing below touches the workspace
+  MEEPO_TRY(sorted_live(t, n, &ks, &ss, stream, delta));  // stays valid: nothing below touches the workspace
   // one device staging buffer + one pinned bounce buffer, sections written in file order
   const uint64_t chunk = 1u << 16;
   const size_t widest = std::max<size_t>({(size_t)t->row_bytes, (size_t)t->state_bytes, 8});
@@ -318,8 +359,15 @@ MEEPO_API meepo_status meepo_export(meepo_table* t, const char* path) {
   cudaFree(d_stage);
   cudaFreeHost(h_stage);
   if (rc == MEEPO_OK && fflush(f) != 0) rc = fail(MEEPO_EIO, "flush failed");
+  if (rc == MEEPO_OK && delta) {  // the tuples are on disk: forget their marks
+    rc = dirty_clear(t, stream);
+    if (rc == MEEPO_OK && cudaStreamSynchronize(stream) != cudaSuccess) rc = fail(MEEPO_ECUDA, "dirty clear failed");
+  }
   return rc;
 }
+
+MEEPO_API meepo_status meepo_export(meepo_table* t, const char* path) { return export_file_impl(t, path, false); }
+MEEPO_API meepo_status meepo_export_delta(meepo_table* t, const char* path) { return export_file_impl(t, path, true); }
 
 MEEPO_API meepo_status meepo_import(meepo_table* t, const char* path) {
   if (!t || !path) return fail(MEEPO_EINVAL, "null argument");

@@ -38,6 +38,7 @@ __global__ void __launch_bounds__(256) publish_kernel(TableView t, const uint32_
     const uint32_t s = __ldg(new_slots + i);
     if (s == kNil) continue;
     *tag_ptr(t, s) = (uint8_t)digest_of(mix64(*key_ptr(t, s)));
+    mark_dirty(t, s);
     mine++;
   }
   mine = __reduce_add_sync(0xFFFFFFFFu, mine);

@@ -177,6 +177,9 @@ MEEPO_API meepo_status meepo_create(const meepo_config* cfg, meepo_table** out) 
     return bail(e, "cudaMalloc(scores)");
   if (cfg->opt == MEEPO_ADAM && (e = cudaMalloc(&v.steps, slots * 4)) != cudaSuccess)
     return bail(e, "cudaMalloc(steps)");
+  if ((cfg->flags & MEEPO_FLAG_TRACK_DIRTY) && ((e = cudaMalloc(&v.dirty, (slots + 31) / 32 * 4)) != cudaSuccess ||
+                                                (e = cudaMemset(v.dirty, 0, (slots + 31) / 32 * 4)) != cudaSuccess))
+    return bail(e, "cudaMalloc(dirty bits)");
   if ((e = cudaMalloc(&t->dstate, sizeof(DeviceState))) != cudaSuccess) return bail(e, "cudaMalloc(dstate)");
   v.counters = t->dstate->counters;
   // keys = EMPTY (all ones), then the 16-byte headers (tags + metadata) = 0
@@ -224,6 +227,7 @@ MEEPO_API meepo_status meepo_destroy(meepo_table* t) {
   cudaFree(t->v.state);
   cudaFree(t->v.scores);
   cudaFree(t->v.steps);
+  cudaFree(t->v.dirty);
   cudaFree(t->dstate);
   cudaFree(t->ws.base);
   cudaFree(t->cache.keys);

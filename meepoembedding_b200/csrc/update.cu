@@ -225,6 +225,7 @@ __global__ void __launch_bounds__(256) apply_kernel(TableView t, ApplyArgs a) {
       continue;
     }
     float alpha = adam_alpha<OPT>(t, slot, gmask, gl == 0);
+    if (OPT != kStoreOnly && gl == 0) mark_dirty(t, slot);
     uint32_t accum = 0;  // row-wise Adagrad: the accumulator as it was before this step
     if constexpr (OPT == MEEPO_ADAGRAD_ROWWISE) {
       // meepo.h: s_r over this lane's chunk classes r = gl + m * GL, the halving tree inside the lane for the
@@ -311,6 +312,10 @@ __global__ void __launch_bounds__(256) apply_pipelined_kernel(TableView t, Apply
         base = __shfl_sync(gmask, base, lane & ~(GL - 1));
         for (uint32_t c = q; c < nleaf; c += GL) a.leaf_desc[base + c] = make_uint2(u + h, c);
       }
+    }
+    if (OPT != kStoreOnly && q == 0) {
+      if (okA) mark_dirty(t, da.y);
+      if (okB) mark_dirty(t, db.y);
     }
     if (okA) {
       float alpha = adam_alpha<OPT>(t, da.y, gmask, q == 0);
@@ -491,6 +496,7 @@ __global__ void __launch_bounds__(256) long_finish_kernel(TableView t, ApplyArgs
     }
     if (threadIdx.x == 0) {
       alpha_s = 0.0f;
+      if (OPT != kStoreOnly) mark_dirty(t, slot);
       if constexpr (OPT == MEEPO_ADAM) {  // per-row step count -> scalar step size (meepo.h "Update")
         const uint32_t tt = t.steps[slot] + 1;
         t.steps[slot] = tt;

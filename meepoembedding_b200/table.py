@@ -66,6 +66,7 @@ class Table:
         init_seed: int = 0,
         device: int = 0,
         track_scores: bool = False,
+        track_dirty: bool = False,
         host_spill_bytes: int = 0,
         lib: capi.Library | None = None,
     ):
@@ -78,7 +79,7 @@ class Table:
         self.device = int(device)
         cfg = capi.Config(
             dim=self.dim,
-            flags=capi.FLAG_TRACK_SCORES if track_scores else 0,
+            flags=(capi.FLAG_TRACK_SCORES if track_scores else 0) | (capi.FLAG_TRACK_DIRTY if track_dirty else 0),
             capacity=int(capacity),
             dtype=self.dtype,
             opt=self.opt,
@@ -248,15 +249,21 @@ class Table:
         self.lib.check(self.lib.export_buffers(self._h, None, None, None, None, None, 0, C.byref(n)))
         return int(n.value)
 
-    def export_buffers(self, keys, rows=None, state=None, scores=None, steps=None, max_n=None) -> int:
+    def export_buffers(self, keys, rows=None, state=None, scores=None, steps=None, max_n=None, delta=False) -> int:
         n = C.c_uint64(0)
         max_n = self._n(keys, max_n)
-        self.lib.check(
-            self.lib.export_buffers(
-                self._h, _ptr(keys), _ptr(rows), _ptr(state), _ptr(scores), _ptr(steps), max_n, C.byref(n)
-            )
-        )
+        fn = self.lib.export_delta_buffers if delta else self.lib.export_buffers
+        self.lib.check(fn(self._h, _ptr(keys), _ptr(rows), _ptr(state), _ptr(scores), _ptr(steps), max_n, C.byref(n)))
         return int(n.value)
+
+    # incremental export (include/meepo.h "Incremental export"; needs track_dirty=True)
+    def export_delta_size(self) -> int:
+        n = C.c_uint64(0)
+        self.lib.check(self.lib.export_delta_buffers(self._h, None, None, None, None, None, 0, C.byref(n)))
+        return int(n.value)
+
+    def export_delta_file(self, path: str):
+        self.lib.check(self.lib.export_delta(self._h, path.encode()))
 
     def import_buffers(self, keys, rows, state=None, scores=None, steps=None, status_out=None, n=None):
         n = self._n(keys, n)

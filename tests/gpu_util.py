@@ -37,16 +37,18 @@ def gpu_apply(t, keys: np.ndarray, grads: np.ndarray, dtype: str):
     torch.cuda.synchronize()
 
 
-def gpu_export(t):
-    """(keys, rows, state, scores, steps) of a CUDA table as host arrays, sorted by key."""
-    n = t.export_size()
+def gpu_export(t, delta=False):
+    """(keys, rows, state, scores, steps) of a CUDA table as host arrays, sorted by key (delta: the
+    incremental export, which marks the returned tuples clean)."""
+    n = t.export_delta_size() if delta else t.export_size()
     keys = torch.empty(n, dtype=torch.int64, device=DEV)
     rows = torch.empty((n, t.row_bytes), dtype=torch.uint8, device=DEV)
     state = torch.empty((n, max(t.state_bytes, 1)), dtype=torch.uint8, device=DEV)
     scores = torch.empty(n, dtype=torch.int64, device=DEV)
     steps = torch.empty(n, dtype=torch.int32, device=DEV)
-    got = t.export_buffers(keys, rows, state if t.state_bytes else None, scores, steps, max_n=n)
-    assert got == n
+    if not (delta and n == 0):
+        got = t.export_buffers(keys, rows, state if t.state_bytes else None, scores, steps, max_n=n, delta=delta)
+        assert got == n
     rdt = np.float32 if t.dtype == capi.F32 else np.uint16
     return (keys.cpu().numpy().view(np.uint64), rows.cpu().numpy().view(rdt).reshape(n, t.dim),
             state.cpu().numpy()[:, :t.state_bytes].copy().view(np.float32).reshape(n, t.state_bytes // 4),

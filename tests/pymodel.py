@@ -54,6 +54,7 @@ class Model:
         self.epoch = 0
         self.spill = {}   # key -> tuple, insertion-ordered (python dicts keep order)
         self.spill_tuples = spill_tuples
+        self.dirty = set()  # include/meepo.h "Incremental export"
 
     # storage rounding
     def _store(self, v):
@@ -112,6 +113,7 @@ class Model:
                 self.step[k] = 0
                 self.freq[k] = 0
                 self.last[k] = 0
+                self.dirty.add(k)
             st[i] = capi.KEY_FOUND if k in present_at_start else capi.KEY_INSERTED
             rows[i] = self.rows[k]
             if self.track:
@@ -168,6 +170,7 @@ class Model:
                 w = w - (alpha * m) / (np.sqrt(v) + self.eps)
                 self.state[k] = np.concatenate([m, v])
             self.rows[k] = self._store(w)
+            self.dirty.add(k)
 
     def evict(self, policy, target_load):
         target = int(math.floor(target_load * self.capacity))
@@ -184,6 +187,7 @@ class Model:
                 self.spill[key] = (self.rows[key], self.state[key], self.step[key], self.freq[key], self.last[key])
             for d in (self.rows, self.state, self.step, self.freq, self.last):
                 del d[key]
+            self.dirty.discard(key)
         return k
 
     def readmit(self, keys):
@@ -200,5 +204,12 @@ class Model:
                 st[i] = capi.KEY_FULL
             else:
                 self.rows[k], self.state[k], self.step[k], self.freq[k], self.last[k] = self.spill.pop(k)
+                self.dirty.add(k)
                 st[i] = capi.KEY_INSERTED
         return st
+
+    def export_delta(self):
+        """Keys touched since the last delta export, ascending; marks them clean."""
+        out = sorted(self.dirty)
+        self.dirty.clear()
+        return out

@@ -152,3 +152,60 @@ def test_host_buffer_verbs(oracle_lib, cuda_lib, dtype, dim):
         np.testing.assert_array_equal(st, ost)
         np.testing.assert_array_equal(rows, orows)
     assert g.stats()["size"] == o.stats()["size"]
+
+
+@pytest.mark.parametrize("dtype,optimizer", [("f32", "adagrad"), ("bf16", "adam"), ("bf16", "adagrad_rowwise")])
+def test_delta_export_parity(oracle_lib, cuda_lib, tmp_path, dtype, optimizer):
+    """Incremental export (include/meepo.h): the same tuples as the oracle's delta, byte-identical delta files,
+    marks dropped by eviction, set again by re-admission and import; base + deltas rebuild the table."""
+    from gpu_util import gpu_apply, gpu_export, gpu_foi
+
+    kw = table_kwargs(dim=32, capacity=4096, dtype=dtype, optimizer=optimizer, track_scores=True, track_dirty=True,
+                      host_spill_bytes=1 << 20)
+    g, o = Table(lib=cuda_lib, **kw), Table(lib=oracle_lib, **kw)
+    replica = Table(lib=cuda_lib, **kw)
+    rng = np.random.default_rng(31)
+    for step in range(6):
+        keys = make_keys(rng, 1500, 6000, dup_frac=0.4)
+        gpu_foi(g, keys, dtype), o.find_or_insert(keys)
+        sub = keys[: 700 + 50 * step]
+        gr = grads_for(dtype, rng.normal(0, 0.1, size=(sub.size, 32)))
+        gpu_apply(g, sub, gr, dtype), o.apply_gradients(sub, gr)
+        lk = make_keys(rng, 500, 6000)
+        gpu_foi(g, lk, dtype, insert=False), o.lookup(lk)
+        if step == 3:
+            assert g.evict("lfu", 0.3) == o.evict("lfu", 0.3)
+            ek = export_sorted(o)[0]
+            back = np.setdiff1d(np.unique(keys[keys < np.uint64(capi.KEY_RESERVED)]), ek)[:40]
+            np.testing.assert_array_equal(g.spill_readmit(back), o.spill_readmit(back))
+        assert g.export_delta_size() == o.export_delta_size()
+        if step % 2 == 0:
+            gd, od = gpu_export(g, delta=True), export_sorted(o, delta=True)
+            for name, a, b in zip(("keys", "rows", "state", "scores", "steps"), gd, od):
+                np.testing.assert_array_equal(a, b, err_msg=f"delta {name} at step {step}")
+            assert g.export_delta_size() == 0
+            from gpu_util import dkeys
+            import torch
+
+            if gd[0].size:
+                replica.import_buffers(dkeys(gd[0]), torch.from_numpy(gd[1].view(np.uint8)).cuda(),
+                                       torch.from_numpy(gd[2].view(np.uint8)).cuda() if g.state_bytes else None,
+                                       dkeys(gd[3]), torch.from_numpy(gd[4].view(np.int32)).cuda())
+                torch.cuda.synchronize()
+        else:
+            pg, po = str(tmp_path / f"g{step}.meepo"), str(tmp_path / f"o{step}.meepo")
+            g.export_delta_file(pg), o.export_delta_file(po)
+            assert filecmp.cmp(pg, po, shallow=False), "GPU and oracle wrote different delta files"
+            assert g.export_delta_size() == 0
+            replica.import_file(pg)
+    keys, rows, state, scores, steps = gpu_export(g)
+    rk, rrows, rstate, _, rsteps = gpu_export(replica)
+    pos = np.searchsorted(rk, keys)
+    assert (rk[pos] == keys).all()
+    np.testing.assert_array_equal(rrows[pos], rows)
+    np.testing.assert_array_equal(rstate[pos], state)
+    np.testing.assert_array_equal(rsteps[pos], steps)
+    # imported tuples are dirty in the importing table
+    assert replica.export_delta_size() == rk.size
+    with pytest.raises(capi.MeepoError):
+        Table(lib=cuda_lib, **table_kwargs()).export_delta_size()

@@ -218,3 +218,55 @@ def test_hypothesis_streams(oracle_lib, ops, dtype, optimizer):
         else:
             assert t.evict("lfu", 0.5) == m.evict(capi.LFU, 0.5)
     check_table_equal(t, m, dtype)
+
+
+def test_delta_export_matches_model_and_replays(oracle_lib, tmp_path):
+    """include/meepo.h "Incremental export": a delta holds exactly the tuples inserted / updated / imported /
+    re-admitted since the previous delta; full export + the deltas, imported in order, rebuild the table."""
+    rng = np.random.default_rng(23)
+    kw = dict(dim=8, capacity=512, dtype="f32", optimizer="adagrad", track_scores=True, track_dirty=True,
+              host_spill_bytes=64 * (24 + 32 + 32))
+    t, m = make_pair(oracle_lib, **kw)
+    replica = Table(lib=oracle_lib, **table_kwargs(**kw))
+    base = str(tmp_path / "base.meepo")
+    t.export_file(base)  # empty base
+    replica.import_file(base)
+    for step in range(6):
+        keys = make_keys(rng, 90, 300)
+        t.find_or_insert(keys), m.find_or_insert(keys)
+        sub = keys[: 40 + 5 * step]  # only part of the batch is trained: the rest is dirty by insertion only
+        g = rng.normal(0, 0.1, size=(sub.size, 8)).astype(np.float32)
+        t.apply_gradients(sub, g), m.apply_gradients(sub, g)
+        lk = make_keys(rng, 50, 300)
+        t.lookup(lk), m.lookup(lk)  # lookups mark nothing
+        if step == 3:
+            assert t.evict("lfu", 0.2) == m.evict(capi.LFU, 0.2)  # evicted tuples lose their mark
+            back = np.array(list(m.spill.keys())[:5], dtype=np.uint64)
+            np.testing.assert_array_equal(t.spill_readmit(back), m.readmit(back))  # ... re-admitted ones gain it
+        assert t.export_delta_size() == len(m.dirty)  # the size query marks nothing
+        assert t.export_delta_size() == len(m.dirty)
+        if step % 2 == 0:
+            dk, drows, dstate, dscores, dsteps = export_sorted(t, delta=True)
+            assert dk.tolist() == m.export_delta()
+            for j, k in enumerate(dk.tolist()):
+                np.testing.assert_array_equal(drows[j], m.rows[k])
+                np.testing.assert_array_equal(dstate[j], m.state[k])
+            assert t.export_delta_size() == 0
+            replica.import_buffers(dk, drows, dstate, dscores, dsteps)
+        else:
+            path = str(tmp_path / f"delta{step}.meepo")
+            t.export_delta_file(path)
+            assert t.export_delta_size() == 0
+            m.export_delta()
+            replica.import_file(path)
+    # the replica holds every live tuple of the table bit for bit (plus the keys evicted since: no deletions)
+    keys, rows, state, scores, steps = export_sorted(t)
+    rk, rrows, rstate, rscores, rsteps = export_sorted(replica)
+    pos = np.searchsorted(rk, keys)
+    assert (rk[pos] == keys).all()
+    np.testing.assert_array_equal(rrows[pos], rows)
+    np.testing.assert_array_equal(rstate[pos], state)
+    # without the flag the verb refuses
+    plain = Table(lib=oracle_lib, **table_kwargs())
+    with pytest.raises(capi.MeepoError):
+        plain.export_delta_size()

@@ -39,14 +39,17 @@ def table_kwargs(dim=16, capacity=4096, dtype="f32", optimizer="adagrad", **kw):
     return d
 
 
-def export_sorted(t: Table):
-    """(keys, rows, state, scores, steps) of a host-library table, sorted by key."""
-    n = t.export_size()
+def export_sorted(t: Table, delta=False):
+    """(keys, rows, state, scores, steps) of a host-library table, sorted by key (delta: the
+    incremental export, which marks the returned tuples clean)."""
+    n = t.export_delta_size() if delta else t.export_size()
     keys = np.empty(n, dtype=np.uint64)
     rows = np.empty((n, t.dim), dtype=np.float32 if t.dtype == capi.F32 else np.uint16)
     state = np.empty((n, t.state_bytes // 4), dtype=np.float32)
     scores = np.empty(n, dtype=np.uint64)
     steps = np.empty(n, dtype=np.uint32)
-    got = t.export_buffers(keys, rows, state, scores, steps, max_n=n)
+    if delta and n == 0:
+        return keys, rows, state, scores, steps
+    got = t.export_buffers(keys, rows, state, scores, steps, max_n=n, delta=delta)
     assert got == n
     return keys, rows, state, scores, steps
