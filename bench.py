@@ -276,8 +276,10 @@ def pin_to_gpu_numa_node(dev_index):
 class GpuRun:
     """One workload on the GPU arm: table, prefill, timed region, roofline, parity check, e2e."""
 
-    def __init__(self, args, name, w, dist, rank, world, local_rank, dist_mod, steps, miss_frac=0.0):
+    def __init__(self, args, name, w, dist, rank, world, local_rank, dist_mod, steps, miss_frac=0.0, warmup=None):
         import torch
+
+        self.warmup = args.warmup if warmup is None else warmup
 
         self.torch = torch
         self.args, self.name, self.w, self.dist = args, name, w, dist
@@ -354,7 +356,7 @@ class GpuRun:
         self.prefill_s = time.perf_counter() - t0
         self.size0 = self.table.stats()["size"]
 
-        self.nb = self.nsteps + self.args.warmup
+        self.nb = self.nsteps + self.warmup
         self.host_batches = gen_batches(w, self.nb + 1, self.dist, self.rank, self.world, self.miss_frac)  # +1: parity
         self.dkeys = [torch.from_numpy(k.view(np.int64)).to(dev) for k in self.host_batches]
         gen = torch.Generator(device=dev)
@@ -403,7 +405,7 @@ class GpuRun:
     # ------------------------------------------------------------------ timed region
     def timed(self):
         torch, args = self.torch, self.args
-        steps, warmup = self.nb - args.warmup, args.warmup
+        steps, warmup = self.nb - self.warmup, self.warmup
         clocks = ClockSampler(self.local_rank) if self.rank == 0 else None
         for i in range(warmup):
             self.step(i)
@@ -619,7 +621,7 @@ class GpuRun:
         apply_gradients(i)) so that rows come down while gradients go up."""
         torch, w, B, R, dev = self.torch, self.w, self.B, self.R, self.dev
         ne = min(self.args.e2e_steps, self.steps)
-        hk = [torch.from_numpy(self.host_batches[self.args.warmup + i].view(np.int64)).pin_memory() for i in range(ne)]
+        hk = [torch.from_numpy(self.host_batches[self.warmup + i].view(np.int64)).pin_memory() for i in range(ne)]
         hg = self.grads.cpu().pin_memory()
         hrows = [torch.empty((B, w["dim"]), dtype=self.tdt).pin_memory() for _ in range(2)]
         hst = [torch.empty(B, dtype=torch.uint8).pin_memory() for _ in range(2)]
@@ -739,12 +741,13 @@ class GpuRun:
                 "overflow_buckets": st1["overflow_buckets"], "probe_hist": st1.get("probe_hist"),
                 "prefill_s": self.prefill_s, "unique_per_batch": self.U_avg,
                 "inserted_during_bench": st1["inserts"] - self.st0["inserts"],
-                "inserted_per_step": (st1["inserts"] - self.st0["inserts"]) / self.steps}
+                "inserted_per_step": (st1["inserts"] - self.st0["inserts"]) / self.steps,
+                "promoted_from_host_tier_per_step": (st1["promotions"] - self.st0["promotions"]) / self.steps}
 
     def evict_info(self):
         if not self.evicting:
             return None
-        wu = self.args.warmup
+        wu = self.warmup
         return {"calls_in_timed_region": len([e for e in self.evict_log if e[0] >= wu]),
                 "keys_evicted": [e[1] for e in self.evict_log if e[0] >= wu],
                 "ms_per_call_host_wall": [round(e[2], 3) for e in self.evict_log if e[0] >= wu],
@@ -887,14 +890,16 @@ def main():
             key = name + ("+miss5%" if miss else "")
             try:
                 wa = w if name == main_name else workload(name)
-                r = GpuRun(args, name, wa, d or wa["dist"], rank, world, local_rank, dist_, args.also_steps,
-                           miss_frac=miss)
+                # capacity pressure: one eviction in the warm-up (first-call allocations), three in the timed region
+                ev = wa.get("evict_every")
+                r = GpuRun(args, name, wa, d or wa["dist"], rank, world, local_rank, dist_,
+                           3 * ev if ev else args.also_steps, miss_frac=miss, warmup=ev if ev else None)
                 r.setup()
                 r.timed()
                 roof, kern, launches = r.roofline()
                 par = None if args.no_parity else r.parity_check()
                 if rank == 0:
-                    also[key] = {"value": r.value, "unit": UNIT, "ms_per_step": r.ms_step, "steps": r.steps,
+                    also[key] = {"value": r.value, "unit": UNIT, "ms_per_step": r.ms_step, "steps": r.steps, "warmup": r.warmup,
                                  "config": r.config["workload"], "roofline": {k: roof[k] for k in roof if k != "kernels"},
                                  "step_frac_of_hbm_peak": (roof.get("hbm", roof))["step_frac"], "gpu_launches": launches,
                                  "parity_check": par, "evict": r.evict_info(), "table": r.table_info(),

@@ -85,15 +85,31 @@
  *           epoch at the last such occurrence (the epoch increments once per
  *           find_or_insert / lookup call, first call = 1). LFU orders by freq,
  *           LRU by last_epoch; ties are broken by key, smaller key evicted
- *           first. apply_gradients does not touch the scores. Evicted
- *           (key,row,state,scores,step) tuples go to the pinned host spill tier
- *           when host_spill_bytes > 0: it holds floor(host_spill_bytes /
- *           (24 + row_bytes + state_bytes)) tuples, victims are appended in
- *           eviction order (ascending (score,key)), the oldest tuple is dropped
- *           when it is full, and a newer copy of a key replaces an older one.
- *           meepo_spill_readmit restores tuples; find_or_insert of a key that
- *           sits in the spill tier re-initialises it unless the caller re-admits
- *           first.
+ *           first. apply_gradients does not touch the scores.
+ * Host tier When host_spill_bytes > 0 the table has a SECOND LEVEL in pinned host
+ *           memory: a ring of T = floor(host_spill_bytes / (24 + row_bytes +
+ *           state_bytes)) tuple slabs. meepo_evict appends its victims (key, row,
+ *           state, scores, step) at the head of the ring in eviction order
+ *           (ascending (score, key)): the a-th tuple ever appended goes to slab
+ *           a mod T, so once the ring has wrapped every append overwrites (drops)
+ *           the oldest slab. A key has at most one tuple in the tier: a newer copy
+ *           replaces the older one, whose slab then stays empty until the head
+ *           passes it. The first level (HBM) always wins: a key that sits in both
+ *           (possible after meepo_import*) is served from HBM.
+ *           find_or_insert of a key that is not in HBM but in the tier PROMOTES
+ *           it instead of re-initialising it: the key gets a slot, its row,
+ *           optimizer state and step count are restored, its scores are restored
+ *           and then this batch's occurrences are counted (freq = tier freq +
+ *           occurrences, last_epoch = epoch), and its tier slab becomes empty.
+ *           Every occurrence reports MEEPO_KEY_FOUND and receives the restored
+ *           row: "was in the table when the call started" covers both levels.
+ *           When no slot is free its occurrences report MEEPO_KEY_FULL (row =
+ *           zeros) and the tuple stays in the tier. lookup serves such a key from
+ *           the tier without promoting it (MEEPO_KEY_FOUND, the row; the tuple's
+ *           scores do not change). apply_gradients does not look into the tier
+ *           (a training step calls find_or_insert on its keys first): gradients
+ *           of keys that are only there are dropped and counted in grad_dropped.
+ *           meepo_spill_readmit promotes keys ahead of their next use.
  * Sharding  owner(key, G) = umulhi64(mix64(key ^ 0xD6E8FEB86659FD93), G).
  */
 #ifndef MEEPO_H_
@@ -164,20 +180,22 @@ typedef struct {
 typedef struct {
   uint64_t capacity;     /* slots */
   uint64_t size;         /* live keys */
-  uint64_t inserts;      /* keys inserted since create */
+  uint64_t inserts;      /* keys given a slot since create (new keys and imports; not promotions) */
   uint64_t hits;         /* key occurrences that were found (foi + lookup) */
   uint64_t misses;       /* lookup occurrences not found */
   uint64_t full;         /* occurrences rejected because the table was full */
   uint64_t evictions;    /* keys removed by meepo_evict */
   uint64_t updates;      /* unique-key optimizer steps applied */
   uint64_t grad_dropped; /* gradient occurrences whose key was absent/invalid */
-  uint64_t spill_keys;   /* tuples currently held in the host spill tier */
-  uint64_t spill_bytes;  /* bytes currently held in the host spill tier */
+  uint64_t spill_keys;   /* tuples currently held in the host tier */
+  uint64_t spill_bytes;  /* bytes they occupy (spill_keys * (24 + row_bytes + state_bytes)) */
   uint64_t epoch;        /* batch epoch */
   uint64_t overflow_buckets; /* buckets whose overflow flag is set */
   uint64_t row_bytes, state_bytes; /* per slot */
   uint64_t peer_keys_received;  /* sharded forward verbs: (sender, key) entries this owner served */
   uint64_t peer_grads_received; /* sharded apply_gradients: (sender, key) gradient rows received */
+  uint64_t promotions;          /* keys find_or_insert / spill_readmit brought back from the host tier */
+  uint64_t tier_hits;           /* lookup occurrences served from the host tier */
   uint64_t probe_hist[4];       /* live keys sitting 0, 1, 2, >= 3 buckets past their home bucket (probe length - 1);
                                    the oracle, which has no buckets, reports {size, 0, 0, 0} */
 } meepo_stats_t;
@@ -251,12 +269,20 @@ MEEPO_API meepo_status meepo_apply_gradients_host_async(meepo_table* t, const ui
 MEEPO_API meepo_status meepo_wait(meepo_table* t, uint64_t ticket);
 
 /* --- capacity management -------------------------------------------------- */
+/* Stream-ordered. The call reads the table size (one host synchronisation with
+ * `stream`), then enqueues the selection, the hand-over to the host tier and
+ * the slot release and returns; *n_evicted (may be NULL) is exact on return.
+ * The victims' tuples are first gathered into a device staging buffer and
+ * drained to the pinned ring by plain DMA copies on a private stream underneath
+ * whatever the caller enqueues next; until the next meepo_evict the staged
+ * tuples are served (promoted, looked up) straight from HBM. */
 MEEPO_API meepo_status meepo_evict(meepo_table* t, int32_t policy, double target_load,
                                    uint64_t* n_evicted, void* stream);
-/* Re-admit keys from the host spill tier (row, state and score restored).
- * keys: HOST pointer. status_out (host, may be NULL): FOUND = already in table
- * (spill copy dropped), INSERTED = restored, MISS = not in the spill tier,
- * FULL / INVALID as above. */
+/* Promote keys from the host tier ahead of their next use (row, state, step and
+ * scores restored as they were; the call counts no occurrence). keys: HOST
+ * pointer. status_out (host, may be NULL): FOUND = already in HBM (a tier copy,
+ * if there is one, is dropped), INSERTED = restored (every duplicate of such a
+ * key reports INSERTED), MISS = in neither level, FULL / INVALID as above. */
 MEEPO_API meepo_status meepo_spill_readmit(meepo_table* t, const uint64_t* keys, uint64_t n,
                                            uint8_t* status_out);
 

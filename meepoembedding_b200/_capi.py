@@ -74,6 +74,8 @@ class Stats(C.Structure):
             "state_bytes",
             "peer_keys_received",
             "peer_grads_received",
+            "promotions",
+            "tier_hits",
         )
     ] + [("probe_hist", C.c_uint64 * 4)]
 

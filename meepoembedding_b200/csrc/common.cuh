@@ -29,7 +29,8 @@ constexpr uint32_t kBucket = MEEPO_BUCKET_SLOTS;  // 14
 constexpr uint32_t kNil = 0xFFFFFFFFu;
 
 enum Counter : int {
-  C_SIZE = 0, C_INSERTS, C_HITS, C_MISSES, C_FULL, C_EVICTIONS, C_UPDATES, C_DROPPED, C_OVERFLOW, C_PEER_KEYS, C_PEER_GRADS, C_COUNT
+  C_SIZE = 0, C_INSERTS, C_HITS, C_MISSES, C_FULL, C_EVICTIONS, C_UPDATES, C_DROPPED, C_OVERFLOW, C_PEER_KEYS, C_PEER_GRADS,
+  C_PROMOTIONS, C_TIER_HITS, C_TIER_LIVE, C_COUNT
 };
 
 struct __align__(128) BucketLine {
@@ -38,6 +39,23 @@ struct __align__(128) BucketLine {
   uint64_t key[kBucket];
 };
 static_assert(sizeof(BucketLine) == 128, "a bucket is one 128-byte line");
+
+// Host tier (meepo.h "Host tier"): a ring of `slabs` tuple slabs in mapped pinned host memory, managed entirely
+// from the device. The device keeps which key each slab holds (ring_key) and an open-addressing index key -> slab
+// (linear probing; erased cells become tombstones, the index is rebuilt from ring_key when they pile up). The
+// slabs [stage_d0, stage_d0 + stage_m) mod slabs — the tuples of the latest meepo_evict — also sit in a staging
+// buffer in HBM, from which they are served while (and after) they drain to the host ring by DMA.
+struct TierView {
+  uint64_t* idx_key;   // [idx_mask + 1] MEEPO_KEY_EMPTY = never used, MEEPO_KEY_RESERVED = tombstone
+  uint32_t* idx_val;   // slab of idx_key[c]
+  uint64_t* ring_key;  // [slabs] MEEPO_KEY_EMPTY = the slab holds nothing
+  uint32_t idx_mask, slabs;  // slabs == 0: the table has no host tier
+  uint4 *h_rows, *h_state, *h_meta;  // the ring: [slabs][cpr], [slabs][scpr], [slabs] {key lo, key hi, freq, epoch}
+  uint32_t* h_steps;                 // [slabs]
+  uint4 *s_rows, *s_state, *s_meta;  // staging copy of stage_m slabs, same layout
+  uint32_t* s_steps;
+  uint32_t stage_d0, stage_m;
+};
 
 struct TableView {
   BucketLine* buckets;
@@ -54,6 +72,7 @@ struct TableView {
   float lr, eps, beta1, beta2, init_accum, init_scale;
   uint64_t init_seed;
   uint32_t epoch;
+  TierView tier;
 };
 
 __host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
@@ -214,6 +233,64 @@ __device__ __forceinline__ void mark_dirty(const TableView& t, uint32_t slot) {
 }
 __device__ __forceinline__ void mark_clean(const TableView& t, uint32_t slot) {
   if (t.dirty) atomicAnd(t.dirty + (slot >> 5), ~(1u << (slot & 31u)));
+}
+
+// --- host tier -----------------------------------------------------------------------------------
+constexpr uint64_t kTierSalt = 0x7A3C91E5B4D2F680ull;  // the index hashes differently from the buckets
+constexpr uint64_t kTomb = MEEPO_KEY_RESERVED;
+__device__ __forceinline__ uint32_t tier_home(const TierView& tv, uint64_t key) {
+  return (uint32_t)mix64(key ^ kTierSalt) & tv.idx_mask;
+}
+// Index cell holding `key`, or kNil. The index only changes in publish / evict / readmit kernels, never while
+// probe kernels run.
+__device__ __forceinline__ uint32_t tier_cell(const TierView& tv, uint64_t key) {
+  if (!tv.slabs) return kNil;
+  uint32_t c = tier_home(tv, key);
+  for (uint32_t p = 0; p <= tv.idx_mask; p++, c = (c + 1) & tv.idx_mask) {
+    const uint64_t k = tv.idx_key[c];
+    if (k == key) return c;
+    if (k == MEEPO_KEY_EMPTY) return kNil;
+  }
+  return kNil;
+}
+__device__ __forceinline__ uint32_t tier_slab(const TierView& tv, uint64_t key) {
+  const uint32_t c = tier_cell(tv, key);
+  return c == kNil ? kNil : tv.idx_val[c];
+}
+// Remove `key` from the tier (its slab becomes empty). Safe when several threads erase the same key: one wins.
+__device__ __forceinline__ bool tier_erase(const TableView& t, uint64_t key) {
+  const TierView& tv = t.tier;
+  const uint32_t c = tier_cell(tv, key);
+  if (c == kNil) return false;
+  const uint32_t d = tv.idx_val[c];
+  if (atomicCAS(reinterpret_cast<unsigned long long*>(tv.ring_key + d), (unsigned long long)key,
+                (unsigned long long)MEEPO_KEY_EMPTY) != key)
+    return false;
+  tv.idx_key[c] = kTomb;
+  atomicAdd(t.counters + C_TIER_LIVE, ~0ull);
+  return true;
+}
+struct TierTuple {  // where the tuple of a slab can be read
+  const uint4 *rows, *state, *meta;
+  const uint32_t* steps;
+};
+__device__ __forceinline__ TierTuple tier_tuple(const TableView& t, uint32_t slab) {
+  const TierView& tv = t.tier;
+  uint32_t j = slab - tv.stage_d0;
+  if (slab < tv.stage_d0) j += tv.slabs;
+  TierTuple r;
+  if (j < tv.stage_m) {
+    r.rows = tv.s_rows + (size_t)j * t.cpr;
+    r.state = tv.s_state + (size_t)j * t.scpr;
+    r.meta = tv.s_meta + j;
+    r.steps = tv.s_steps + j;
+  } else {
+    r.rows = tv.h_rows + (size_t)slab * t.cpr;
+    r.state = tv.h_state + (size_t)slab * t.scpr;
+    r.meta = tv.h_meta + slab;
+    r.steps = tv.h_steps + slab;
+  }
+  return r;
 }
 
 // --- row init (meepo.h "Init") -----------------------------------------------------------------

@@ -1,18 +1,25 @@
-// evict.cu — capacity management (include/meepo.h "Evict"): exact selection of the
-// lowest-(score,key) victims, zero-copy spill of their tuples into the pinned host tier, slot
-// release without tombstones (the per-bucket overflow bits keep lookups correct), and re-admission.
+// evict.cu — capacity management (include/meepo.h "Evict" / "Host tier"): exact selection of
+// the lowest-(score,key) victims, hand-over of their tuples to the host tier, slot release without tombstones
+// (the per-bucket overflow bits keep lookups correct), and explicit re-admission.
 //
-// Selection is a 4-pass MSB-first radix select on the 32-bit score (one 256-bin histogram pass
-// over the score array each, 8 B/slot), then only the candidates (score <= threshold) are
-// compacted and ordered by (score, key) with two stable radix sorts. The spill copy is a kernel
-// that writes 16-byte chunks straight into mapped pinned host memory over PCIe; the host only
-// keeps the key -> slab index. Runs between batches, never concurrently with the probe kernels.
-#include <cub/device/device_radix_sort.cuh>
-
-#include <chrono>
-#include <thread>
+// Everything data-dependent stays on the device. The host reads ONE number (the table size, which fixes the
+// victim count k and with it every grid and scratch size), then enqueues:
+//   select   4 histogram passes over the table on the score bytes (most significant first); a 1-CTA step kernel
+//            turns each histogram into the next byte of the threshold T — no copy to the host per pass
+//   split    one more pass: slots with score < T are victims (list A), slots with score == T are candidates
+//            (list B: the ties — under LFU millions of keys share freq = 1)
+//   tie      8 histogram passes over the KEYS OF LIST B select the key threshold, so that exactly k victims
+//            remain (smaller key goes first) without sorting the ties
+//   order    the k victims sorted by (score, key) with the library's own radix sort (3 x 32-bit keys)
+//   tier     the last min(k, slabs) victims go to the ring: retire the slabs they overwrite from the device
+//            index, file the new keys, gather the tuples into a staging buffer in HBM; a private stream then
+//            drains the staging buffer into the pinned ring with plain DMA copies (the slabs of one eviction
+//            are consecutive) underneath whatever the caller enqueues next
+//   release  keys -> EMPTY, tags -> 0, scores / steps -> 0; overflow bits rebuilt
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "table.h"
 
@@ -23,107 +30,356 @@ __device__ __forceinline__ uint32_t score_of(const TableView& t, uint32_t s, int
   return policy == MEEPO_LFU ? sc.x : sc.y;
 }
 
-// Radix select over the composite (score, key), most significant byte first. Score passes
-// (key_pass == 0): histogram of byte `shift/8` of the score over live slots whose higher score bytes
-// equal `prefix`. Key passes: among the slots whose score IS the threshold `prefix`, histogram of
-// byte `shift/8` of the key over those whose higher key bytes equal `kprefix` — the tie-break
-// (smaller key first) is selected exactly instead of sorting tens of millions of tied candidates.
-__global__ void __launch_bounds__(256) score_hist_kernel(TableView t, int policy, uint32_t prefix, uint32_t mask,
-                                                         int shift, int key_pass, uint64_t kprefix, uint64_t kmask,
-                                                         unsigned long long* __restrict__ hist) {
+struct SelState {  // device-side state of the selection
+  uint32_t prefix, mask;           // decided bytes of the score threshold T
+  uint32_t nA, nB, nV, bad;        // list lengths; victims taken from B; a histogram that did not add up
+  uint32_t ormask, pad;            // OR of every live score (first pass): a byte that is 0 everywhere needs no pass
+  unsigned long long remaining;    // victims still to be found among the undecided slots
+  unsigned long long ties;         // slots in the bin the threshold fell into
+  unsigned long long kprefix, kmask;  // decided bytes of the key threshold
+};
+
+__global__ void sel_init_kernel(SelState* sel, unsigned long long k) {
+  SelState s{};
+  s.remaining = k;
+  *sel = s;
+}
+
+// Histogram of byte `shift/8` of the score over the live slots whose higher score bytes equal the prefix. The
+// first pass (shift 24) also ORs all live scores together; a later pass whose byte is zero in every score has
+// nothing to count (LFU frequencies and LRU epochs are small numbers: two or three of the four passes end here).
+__global__ void __launch_bounds__(256) score_hist_kernel(TableView t, int policy, SelState* __restrict__ sel,
+                                                         int shift, unsigned long long* __restrict__ hist) {
+  __shared__ uint32_t sh[256];
+  const uint32_t prefix = sel->prefix, mask = sel->mask;
+  if (shift != 24 && ((sel->ormask >> shift) & 0xFFu) == 0) return;
+  sh[threadIdx.x] = 0;
+  __syncthreads();
+  uint32_t acc_or = 0;
+  const uint32_t lane = threadIdx.x & 31u;
+  for (uint32_t s0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; s0 < t.slots; s0 += gridDim.x * blockDim.x) {
+    const uint32_t s = s0 + lane;
+    bool in = false;
+    uint32_t bin = 0;
+    if (s < t.slots && *key_ptr(t, s) != MEEPO_KEY_EMPTY) {
+      const uint32_t sc = score_of(t, s, policy);
+      acc_or |= sc;
+      in = (sc & mask) == prefix;
+      bin = (sc >> shift) & 0xFFu;
+    }
+    // scores cluster: most warps hold one bin only, and 32 shared-memory atomics on one address serialise
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, in);
+    if (!m) continue;
+    const uint32_t b0 = __shfl_sync(0xFFFFFFFFu, bin, __ffs(m) - 1);
+    if (__all_sync(0xFFFFFFFFu, !in || bin == b0)) {
+      if (lane == 0) atomicAdd(&sh[b0], (uint32_t)__popc(m));
+    } else if (in) {
+      atomicAdd(&sh[bin], 1u);
+    }
+  }
+  __syncthreads();
+  if (sh[threadIdx.x]) atomicAdd(hist + threadIdx.x, (unsigned long long)sh[threadIdx.x]);
+  if (shift == 24) {
+    acc_or = __reduce_or_sync(0xFFFFFFFFu, acc_or);
+    if (lane == 0 && acc_or) atomicOr(&sel->ormask, acc_or);
+  }
+}
+// The same over the keys of list B (all of them have score == T) on byte `shift/8` of the key.
+__global__ void __launch_bounds__(256) key_hist_kernel(const uint64_t* __restrict__ bkey, const SelState* __restrict__ sel,
+                                                       int shift, unsigned long long* __restrict__ hist) {
   __shared__ uint32_t sh[256];
   sh[threadIdx.x] = 0;
   __syncthreads();
-  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < t.slots; s += gridDim.x * blockDim.x) {
-    const uint64_t key = *key_ptr(t, s);
-    if (key == MEEPO_KEY_EMPTY) continue;
-    const uint32_t sc = score_of(t, s, policy);
-    if ((sc & mask) != prefix) continue;
-    if (!key_pass)
-      atomicAdd(&sh[(sc >> shift) & 0xFFu], 1u);
-    else if ((key & kmask) == kprefix)
-      atomicAdd(&sh[(uint32_t)(key >> shift) & 0xFFu], 1u);
+  const uint32_t n = sel->nB;
+  const unsigned long long kprefix = sel->kprefix, kmask = sel->kmask;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint64_t key = bkey[i];
+    if ((key & kmask) == kprefix) atomicAdd(&sh[(uint32_t)(key >> shift) & 0xFFu], 1u);
   }
   __syncthreads();
   if (sh[threadIdx.x]) atomicAdd(hist + threadIdx.x, (unsigned long long)sh[threadIdx.x]);
 }
-
-// candidates = live slots with (score, key) <= (threshold, key_threshold) — exactly the victims
-// (order arbitrary; sorted afterwards)
-__global__ void __launch_bounds__(256) candidates_kernel(TableView t, int policy, uint32_t threshold,
-                                                         uint64_t key_threshold, uint64_t* __restrict__ ckey,
-                                                         uint32_t* __restrict__ cslot, uint32_t* __restrict__ count) {
-  const uint32_t lane = threadIdx.x & 31;
-  for (uint32_t s0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; s0 < t.slots; s0 += gridDim.x * blockDim.x) {
-    const uint32_t s = s0 + lane;
-    uint64_t key = MEEPO_KEY_EMPTY;
-    bool take = false;
-    if (s < t.slots) {
-      key = *key_ptr(t, s);
-      if (key != MEEPO_KEY_EMPTY) {
-        const uint32_t sc = score_of(t, s, policy);
-        take = sc < threshold || (sc == threshold && key <= key_threshold);
-      }
+// One radix-select step: the bin holding the `remaining`-th smallest undecided item becomes the next byte.
+__global__ void __launch_bounds__(256) sel_step_kernel(SelState* sel, unsigned long long* __restrict__ hist, int shift,
+                                                       int key_pass) {
+  if (!key_pass && shift != 24 && ((sel->ormask >> shift) & 0xFFu) == 0) {  // the pass was skipped: byte = 0
+    if (threadIdx.x == 0) sel->mask |= 0xFFu << shift;
+    return;
+  }
+  if (threadIdx.x == 0) {
+    unsigned long long cum = 0, rem = sel->remaining;
+    int b = 0;
+    for (; b < 256; b++) {
+      if (cum + hist[b] >= rem) break;
+      cum += hist[b];
     }
-    const unsigned m = __ballot_sync(0xFFFFFFFFu, take);
-    if (!m) continue;
-    const int leader = __ffs(m) - 1;
-    uint32_t base = 0;
-    if ((int)lane == leader) base = atomicAdd(count, (uint32_t)__popc(m));
-    base = __shfl_sync(0xFFFFFFFFu, base, leader);
-    if (take) {
-      const uint32_t p = base + __popc(m & ((1u << lane) - 1u));
-      ckey[p] = key;
-      cslot[p] = s;
+    if (b == 256) {  // cannot happen while the table is not mutated underneath
+      b = 255;
+      cum -= hist[255];
+      sel->bad = 1;
+    }
+    sel->remaining = rem - cum;
+    sel->ties = hist[b];
+    if (key_pass) {
+      sel->kprefix |= (unsigned long long)b << shift;
+      sel->kmask |= 0xFFull << shift;
+    } else {
+      sel->prefix |= (uint32_t)b << shift;
+      sel->mask |= 0xFFu << shift;
+    }
+  }
+  __syncthreads();
+  hist[threadIdx.x] = 0;
+}
+
+// CTA-wide reservation of list space. Every thread calls it with the warp ballots of its ITEMS items in up to two
+// classes; one thread adds the CTA totals to the global counters — ONE atomic per class and per 2048 items: the list
+// counters are single addresses, and atomics on one address serialise in L2 (a warp-level atomicAdd per 32 slots
+// cost 2.8 ms on a 60M-slot pass). Returns the list index of the first item of this warp in each class.
+constexpr int kSelItems = 8;
+constexpr uint32_t kSelTile = 256 * kSelItems;
+struct Reserve2 {
+  uint32_t a, b;
+};
+__device__ __forceinline__ Reserve2 block_reserve2(const unsigned (&ma)[kSelItems], const unsigned (&mb)[kSelItems],
+                                                   uint32_t* counter_a, uint32_t* counter_b) {
+  __shared__ uint32_t s_a[8], s_b[8], s_base[2];
+  const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+  uint32_t wa = 0, wb = 0;
+#pragma unroll
+  for (int k = 0; k < kSelItems; k++) {
+    wa += __popc(ma[k]);
+    wb += __popc(mb[k]);
+  }
+  __syncthreads();  // the previous round's readers are done with the shared cells
+  if (lane == 0) {
+    s_a[w] = wa;
+    s_b[w] = wb;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t ta = 0, tb = 0;
+    for (int i = 0; i < 8; i++) {
+      const uint32_t xa = s_a[i], xb = s_b[i];
+      s_a[i] = ta;
+      s_b[i] = tb;
+      ta += xa;
+      tb += xb;
+    }
+    s_base[0] = ta ? atomicAdd(counter_a, ta) : 0u;
+    s_base[1] = (tb && counter_b) ? atomicAdd(counter_b, tb) : 0u;
+  }
+  __syncthreads();
+  return Reserve2{s_base[0] + s_a[w], s_base[1] + s_b[w]};
+}
+
+// Slots below the threshold -> list A (victims), slots at the threshold -> list B (candidates).
+__global__ void __launch_bounds__(256) split_kernel(TableView t, int policy, SelState* sel, uint64_t* __restrict__ akey,
+                                                    uint32_t* __restrict__ aslot, uint32_t* __restrict__ ascore,
+                                                    uint64_t* __restrict__ bkey, uint32_t* __restrict__ bslot) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t T = sel->prefix;
+  const unsigned below = (1u << lane) - 1u;
+  for (uint64_t base = (uint64_t)blockIdx.x * kSelTile; base < t.slots; base += (uint64_t)gridDim.x * kSelTile) {
+    uint64_t key[kSelItems];
+    uint32_t sc[kSelItems];
+    unsigned ma[kSelItems], mb[kSelItems];
+    int cls[kSelItems];  // 1: below, 2: at the threshold
+#pragma unroll
+    for (int k = 0; k < kSelItems; k++) {
+      const uint64_t s = base + (uint32_t)k * 256u + threadIdx.x;
+      key[k] = s < t.slots ? *key_ptr(t, (uint32_t)s) : MEEPO_KEY_EMPTY;
+      sc[k] = 0;
+      cls[k] = 0;
+      if (key[k] != MEEPO_KEY_EMPTY) {
+        sc[k] = score_of(t, (uint32_t)s, policy);
+        cls[k] = sc[k] < T ? 1 : (sc[k] == T ? 2 : 0);
+      }
+      ma[k] = __ballot_sync(0xFFFFFFFFu, cls[k] == 1);
+      mb[k] = __ballot_sync(0xFFFFFFFFu, cls[k] == 2);
+    }
+    Reserve2 r = block_reserve2(ma, mb, &sel->nA, &sel->nB);
+#pragma unroll
+    for (int k = 0; k < kSelItems; k++) {
+      const uint32_t s = (uint32_t)(base + (uint32_t)k * 256u + threadIdx.x);
+      if (cls[k] == 1) {
+        const uint32_t p = r.a + __popc(ma[k] & below);
+        akey[p] = key[k];
+        aslot[p] = s;
+        ascore[p] = sc[k];
+      } else if (cls[k] == 2) {
+        const uint32_t p = r.b + __popc(mb[k] & below);
+        bkey[p] = key[k];
+        bslot[p] = s;
+      }
+      r.a += __popc(ma[k]);
+      r.b += __popc(mb[k]);
+    }
+  }
+}
+// The candidates with key <= the key threshold join the victims (appended after list A).
+__global__ void __launch_bounds__(256) take_ties_kernel(SelState* sel, const uint64_t* __restrict__ bkey,
+                                                        const uint32_t* __restrict__ bslot, uint64_t* __restrict__ akey,
+                                                        uint32_t* __restrict__ aslot, uint32_t* __restrict__ ascore,
+                                                        uint32_t k_total) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t n = sel->nB, nA = sel->nA, T = sel->prefix;
+  const unsigned long long Tkey = sel->kprefix;
+  const unsigned below = (1u << lane) - 1u;
+  for (uint64_t base = (uint64_t)blockIdx.x * kSelTile; base < n; base += (uint64_t)gridDim.x * kSelTile) {
+    uint64_t key[kSelItems];
+    unsigned m[kSelItems], none[kSelItems];
+    bool take[kSelItems];
+#pragma unroll
+    for (int k = 0; k < kSelItems; k++) {
+      const uint64_t i = base + (uint32_t)k * 256u + threadIdx.x;
+      key[k] = i < n ? bkey[i] : MEEPO_KEY_EMPTY;
+      take[k] = i < n && key[k] <= Tkey;
+      m[k] = __ballot_sync(0xFFFFFFFFu, take[k]);
+      none[k] = 0;
+    }
+    Reserve2 r = block_reserve2(m, none, &sel->nV, nullptr);
+#pragma unroll
+    for (int k = 0; k < kSelItems; k++) {
+      if (take[k]) {
+        const uint32_t p = nA + r.a + __popc(m[k] & below);
+        if (p < k_total) {
+          akey[p] = key[k];
+          aslot[p] = bslot[base + (uint32_t)k * 256u + threadIdx.x];
+          ascore[p] = T;
+        }
+      }
+      r.a += __popc(m[k]);
     }
   }
 }
 
-__global__ void iota_kernel(uint32_t* __restrict__ v, uint32_t n) {
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) v[i] = i;
+// sort keys of the three passes that order the victims by (score, key): key low word, key high word, score
+__global__ void sort_key_kernel(int what, const uint64_t* __restrict__ vkey, const uint32_t* __restrict__ vscore,
+                                const uint32_t* __restrict__ ord, uint32_t n, uint32_t* __restrict__ out,
+                                uint32_t* __restrict__ iota) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t j = ord ? ord[i] : i;
+    out[i] = what == 0 ? (uint32_t)vkey[j] : what == 1 ? (uint32_t)(vkey[j] >> 32) : vscore[j];
+    if (iota) iota[i] = i;
+  }
 }
-__global__ void gather_scores_kernel(TableView t, int policy, const uint32_t* __restrict__ order,
-                                     const uint32_t* __restrict__ cslot, uint32_t n, uint32_t* __restrict__ out) {
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    out[i] = score_of(t, cslot[order[i]], policy);
-}
-// victims in eviction order: vslot[j], vkey[j] for j < k
-__global__ void victims_kernel(const uint32_t* __restrict__ order, const uint32_t* __restrict__ cslot,
-                               const uint64_t* __restrict__ ckey, uint32_t k, uint32_t* __restrict__ vslot,
+// victims in eviction order
+__global__ void victims_kernel(const uint32_t* __restrict__ ord, const uint32_t* __restrict__ aslot,
+                               const uint64_t* __restrict__ akey, uint32_t k, uint32_t* __restrict__ vslot,
                                uint64_t* __restrict__ vkey) {
   for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < k; j += gridDim.x * blockDim.x) {
-    vslot[j] = cslot[order[j]];
-    vkey[j] = ckey[order[j]];
+    vslot[j] = aslot[ord[j]];
+    vkey[j] = akey[ord[j]];
   }
 }
 
-struct SpillView {  // structure-of-arrays slab in mapped pinned host memory
-  uint4* rows;      // [cap][cpr]
-  uint4* state;     // [cap][scpr]
-  uint4* meta;      // [cap] {key lo, key hi, freq, epoch} ; step lives in steps[]
-  uint32_t* steps;  // [cap]
-};
+// --- host tier: device-side index maintenance -----------------------------------------------------------
+__device__ __forceinline__ uint64_t ld_key_volatile(const uint64_t* p) {
+  return *reinterpret_cast<const volatile uint64_t*>(p);
+}
+// File `key` (known not to be in the index) -> slab: the first tombstone / unused cell of its probe path.
+__device__ __forceinline__ void tier_index_put(const TierView& tv, uint64_t key, uint32_t slab) {
+  uint32_t c = tier_home(tv, key);
+  for (uint32_t p = 0; p <= tv.idx_mask; p++, c = (c + 1) & tv.idx_mask) {
+    const uint64_t k = ld_key_volatile(tv.idx_key + c);
+    if (k != MEEPO_KEY_EMPTY && k != kTomb) continue;
+    if (atomicCAS(reinterpret_cast<unsigned long long*>(tv.idx_key + c), (unsigned long long)k,
+                  (unsigned long long)key) == k) {
+      tv.idx_val[c] = slab;
+      return;
+    }
+    // another key took the cell: move on
+  }
+}
+// The slabs [d0, d0 + m) mod slabs are about to be overwritten: whatever they hold leaves the index.
+__global__ void __launch_bounds__(256) tier_retire_kernel(TableView t, uint32_t d0, uint32_t m) {
+  const TierView& tv = t.tier;
+  uint32_t gone = 0;
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += gridDim.x * blockDim.x) {
+    uint32_t d = d0 + j;
+    if (d >= tv.slabs) d -= tv.slabs;
+    const uint64_t old = tv.ring_key[d];
+    if (old == MEEPO_KEY_EMPTY) continue;
+    const uint32_t c = tier_cell(tv, old);
+    if (c != kNil) tv.idx_key[c] = kTomb;
+    tv.ring_key[d] = MEEPO_KEY_EMPTY;
+    gone++;
+  }
+  gone = __reduce_add_sync(0xFFFFFFFFu, gone);
+  if ((threadIdx.x & 31u) == 0 && gone) atomicAdd(t.counters + C_TIER_LIVE, (unsigned long long)(-(long long)gone));
+}
+// File the m new tuples: keys[j] -> slab (d0 + j) mod slabs. An older copy of a key gives way (its slab empties).
+__global__ void __launch_bounds__(256) tier_insert_kernel(TableView t, const uint64_t* __restrict__ keys, uint32_t d0,
+                                                          uint32_t m) {
+  const TierView& tv = t.tier;
+  uint32_t fresh = 0;
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += gridDim.x * blockDim.x) {
+    uint32_t d = d0 + j;
+    if (d >= tv.slabs) d -= tv.slabs;
+    const uint64_t key = keys[j];
+    // an older copy? (cells may be claimed by other threads of this kernel meanwhile, never released)
+    uint32_t c = tier_home(tv, key), hit = kNil;
+    for (uint32_t p = 0; p <= tv.idx_mask; p++, c = (c + 1) & tv.idx_mask) {
+      const uint64_t k = ld_key_volatile(tv.idx_key + c);
+      if (k == key) {
+        hit = c;
+        break;
+      }
+      if (k == MEEPO_KEY_EMPTY) break;
+    }
+    if (hit != kNil) {
+      tv.ring_key[tv.idx_val[hit]] = MEEPO_KEY_EMPTY;
+      tv.idx_val[hit] = d;
+    } else {
+      tier_index_put(tv, key, d);
+      fresh++;
+    }
+    tv.ring_key[d] = key;
+  }
+  fresh = __reduce_add_sync(0xFFFFFFFFu, fresh);
+  if ((threadIdx.x & 31u) == 0 && fresh) atomicAdd(t.counters + C_TIER_LIVE, (unsigned long long)fresh);
+}
+// Index from scratch out of ring_key (tombstones gone). idx_key must be all EMPTY.
+__global__ void __launch_bounds__(256) tier_rebuild_kernel(TableView t) {
+  const TierView& tv = t.tier;
+  for (uint32_t d = blockIdx.x * blockDim.x + threadIdx.x; d < tv.slabs; d += gridDim.x * blockDim.x) {
+    const uint64_t key = tv.ring_key[d];
+    if (key != MEEPO_KEY_EMPTY) tier_index_put(tv, key, d);
+  }
+}
 
-// one warp per spilled victim: tuple -> host slab (zero-copy stores over PCIe)
-__global__ void __launch_bounds__(256) spill_copy_kernel(TableView t, SpillView sp, const uint32_t* __restrict__ vslot,
-                                                         const uint32_t* __restrict__ slab, uint32_t n) {
+struct TierDst {  // where the tuples of an eviction are written: staging (j) or the ring itself (slab)
+  uint4 *rows, *state, *meta;
+  uint32_t* steps;
+  uint32_t d0, slabs;  // slabs != 0: destination index = (d0 + j) mod slabs, else j
+};
+// one warp per victim: tuple -> destination
+__global__ void __launch_bounds__(256) tier_gather_kernel(TableView t, TierDst dst, const uint32_t* __restrict__ vslot,
+                                                          uint32_t n) {
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
   for (uint32_t j = warp; j < n; j += nwarps) {
-    const uint32_t s = vslot[j], d = slab[j];
-    for (uint32_t q = lane; q < t.cpr; q += 32) sp.rows[(size_t)d * t.cpr + q] = t.rows[(size_t)s * t.cpr + q];
-    for (uint32_t q = lane; q < t.scpr; q += 32) sp.state[(size_t)d * t.scpr + q] = t.state[(size_t)s * t.scpr + q];
+    const uint32_t s = vslot[j];
+    uint32_t d = j;
+    if (dst.slabs) {
+      d = dst.d0 + j;
+      if (d >= dst.slabs) d -= dst.slabs;
+    }
+    for (uint32_t q = lane; q < t.cpr; q += 32) dst.rows[(size_t)d * t.cpr + q] = ld_stream(t.rows + (size_t)s * t.cpr + q);
+    for (uint32_t q = lane; q < t.scpr; q += 32)
+      dst.state[(size_t)d * t.scpr + q] = ld_stream(t.state + (size_t)s * t.scpr + q);
     if (lane == 0) {
       const uint64_t key = *key_ptr(t, s);
       const uint2 sc = t.scores[s];
-      sp.meta[d] = make_uint4((uint32_t)key, (uint32_t)(key >> 32), sc.x, sc.y);
-      sp.steps[d] = t.steps ? t.steps[s] : 0u;
+      dst.meta[d] = make_uint4((uint32_t)key, (uint32_t)(key >> 32), sc.x, sc.y);
+      dst.steps[d] = t.steps ? t.steps[s] : 0u;
     }
   }
 }
 
-// release the victims' slots: key -> EMPTY, tag -> 0, scores/steps -> 0 (overflow bits stay)
+// release the victims' slots: key -> EMPTY, tag -> 0, scores/steps -> 0 (overflow bits are rebuilt below)
 __global__ void release_kernel(TableView t, const uint32_t* __restrict__ vslot, uint32_t k) {
   for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < k; j += gridDim.x * blockDim.x) {
     const uint32_t s = vslot[j];
@@ -166,76 +422,199 @@ __global__ void __launch_bounds__(256) overflow_mark_kernel(TableView t) {
   if ((threadIdx.x & 31u) == 0 && fresh) atomicAdd(t.counters + C_OVERFLOW, (unsigned long long)fresh);
 }
 
-// one warp per re-admitted tuple: host slab -> arena slot (zero-copy loads over PCIe)
-__global__ void __launch_bounds__(256) readmit_copy_kernel(TableView t, SpillView sp, const uint32_t* __restrict__ slot,
+// --- meepo_spill_readmit ----------------------------------------------------------------------------------
+// Thread per key: FOUND (in HBM), MISS (in neither level), or claim a slot for a key of the tier (INSERTED for
+// every duplicate, FULL). slot_out[i] != kNil only for the thread that has to copy the tuple.
+__global__ void __launch_bounds__(256) readmit_probe_kernel(TableView t, const uint64_t* __restrict__ keys, uint32_t n,
+                                                            uint8_t* __restrict__ status, uint32_t* __restrict__ slot_out,
+                                                            uint32_t* __restrict__ slab_out) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint64_t k = keys[i];
+    uint8_t st = MEEPO_KEY_INVALID;
+    uint32_t slot = kNil, slab = kNil;
+    if (key_valid(k)) {
+      if (probe_find<kCoherent>(t, k) != kNil) {
+        st = MEEPO_KEY_FOUND;
+      } else if ((slab = tier_slab(t.tier, k)) == kNil) {
+        st = MEEPO_KEY_MISS;
+      } else {
+        const Probe pr = probe_find_or_insert(t, k);
+        if (pr.status == MEEPO_KEY_FULL) {
+          st = MEEPO_KEY_FULL;
+          atomicAdd(t.counters + C_FULL, 1ull);
+        } else {
+          st = MEEPO_KEY_INSERTED;
+          if (pr.winner) slot = pr.slot;
+        }
+      }
+    }
+    status[i] = st;
+    slot_out[i] = slot;
+    slab_out[i] = slab;
+  }
+}
+// one warp per restored tuple: tier (staging or ring, zero-copy over PCIe) -> arena slot, scores as they were
+__global__ void __launch_bounds__(256) readmit_copy_kernel(TableView t, const uint32_t* __restrict__ slot,
                                                            const uint32_t* __restrict__ slab, uint32_t n) {
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
   for (uint32_t j = warp; j < n; j += nwarps) {
-    const uint32_t s = slot[j], d = slab[j];
+    const uint32_t s = slot[j];
     if (s == kNil) continue;
-    for (uint32_t q = lane; q < t.cpr; q += 32) t.rows[(size_t)s * t.cpr + q] = sp.rows[(size_t)d * t.cpr + q];
-    for (uint32_t q = lane; q < t.scpr; q += 32) t.state[(size_t)s * t.scpr + q] = sp.state[(size_t)d * t.scpr + q];
+    const TierTuple tt = tier_tuple(t, slab[j]);
+    for (uint32_t q = lane; q < t.cpr; q += 32) t.rows[(size_t)s * t.cpr + q] = tt.rows[q];
+    for (uint32_t q = lane; q < t.scpr; q += 32) t.state[(size_t)s * t.scpr + q] = tt.state[q];
     if (lane == 0) {
-      const uint4 m = sp.meta[d];
+      const uint4 m = *tt.meta;
       if (t.scores) t.scores[s] = make_uint2(m.z, m.w);
-      if (t.steps) t.steps[s] = sp.steps[d];
-      mark_dirty(t, s);
+      if (t.steps) t.steps[s] = *tt.steps;
     }
   }
 }
-
-__global__ void found_flags_kernel(TableView t, const uint64_t* __restrict__ keys, uint32_t n,
-                                   uint8_t* __restrict__ found) {
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const uint64_t k = keys[i];
-    found[i] = key_valid(k) && probe_find<kReadOnly>(t, k) != kNil;
-  }
-}
-
-static SpillView spill_view(const meepo_table* t) {
-  SpillView sp;
-  char* p = t->spill_ring;
-  const uint64_t cap = t->spill_cap_tuples;
-  sp.rows = reinterpret_cast<uint4*>(p);
-  p += cap * t->row_bytes;
-  sp.state = reinterpret_cast<uint4*>(p);
-  p += cap * t->state_bytes;
-  sp.meta = reinterpret_cast<uint4*>(p);
-  p += cap * 16;
-  sp.steps = reinterpret_cast<uint32_t*>(p);
-  return sp;
-}
-
-// host bookkeeping of the spill tier; mirrors the FIFO + newest-copy-wins rule of meepo.h "Evict"
-static void spill_drop(meepo_table* t, uint64_t key) {
-  SpillTuple* it = t->spill_index.find(key);
-  if (!it) return;
-  t->spill_free.push_back((uint32_t)it->ring_index);
-  t->spill_index.erase(key);
-}
-static uint32_t spill_push(meepo_table* t, uint64_t key) {
-  spill_drop(t, key);
-  while (t->spill_index.size() >= t->spill_cap_tuples) {
-    auto f = t->spill_fifo.front();
-    t->spill_fifo.pop_front();
-    SpillTuple* it = t->spill_index.find(f.second);
-    if (it && it->seq == f.first) {
-      t->spill_free.push_back((uint32_t)it->ring_index);
-      t->spill_index.erase(f.second);
-    }
-  }
-  const uint32_t slab = t->spill_free.back();
-  t->spill_free.pop_back();
-  const uint64_t seq = t->spill_seq++;
-  t->spill_index.put(key, SpillTuple{seq, slab});
-  t->spill_fifo.emplace_back(seq, key);
-  return slab;
+// keys that were already in HBM: a tier copy, if there is one, is dropped
+__global__ void __launch_bounds__(256) readmit_drop_kernel(TableView t, const uint64_t* __restrict__ keys,
+                                                           const uint8_t* __restrict__ status, uint32_t n) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    if (status[i] == MEEPO_KEY_FOUND) tier_erase(t, keys[i]);
 }
 
 static int grid1d(const meepo_table* t, uint64_t n) {
   return (int)std::max<uint64_t>(1, std::min<uint64_t>((n + 255) / 256, (uint64_t)t->num_sms * 8));
+}
+static int gridwarp(const meepo_table* t, uint64_t rows) {
+  return (int)std::max<uint64_t>(1, std::min<uint64_t>((rows + 7) / 8, (uint64_t)t->num_sms * 8));
+}
+static int gridsel(const meepo_table* t, uint64_t n) {
+  return (int)std::max<uint64_t>(1, std::min<uint64_t>((n + kSelTile - 1) / kSelTile, (uint64_t)t->num_sms * 4));
+}
+
+// ring layout: rows[slabs], state[slabs], meta[slabs], steps[slabs] (structure of arrays, so that the slabs of
+// one eviction are four contiguous runs)
+static void tier_carve(const meepo_table* t, char* p, uint64_t cap, uint4** rows, uint4** state, uint4** meta,
+                       uint32_t** steps) {
+  *rows = reinterpret_cast<uint4*>(p);
+  p += cap * t->row_bytes;
+  *state = reinterpret_cast<uint4*>(p);
+  p += cap * t->state_bytes;
+  *meta = reinterpret_cast<uint4*>(p);
+  p += cap * 16;
+  *steps = reinterpret_cast<uint32_t*>(p);
+}
+
+meepo_status tier_create(meepo_table* t) {
+  const uint64_t slabs = t->cfg.host_spill_bytes / t->tuple_bytes();
+  if (slabs == 0) return MEEPO_OK;
+  if (slabs > (1ull << 30)) return fail(MEEPO_EINVAL, "host tier: more than 2^30 slabs");
+  TierView& tv = t->v.tier;
+  MEEPO_CUDA_TRY(cudaHostAlloc(&t->spill_ring, slabs * t->tuple_bytes(), cudaHostAllocMapped | cudaHostAllocPortable));
+  t->spill_cap_tuples = slabs;
+  tier_carve(t, t->spill_ring, slabs, &tv.h_rows, &tv.h_state, &tv.h_meta, &tv.h_steps);
+  uint64_t cells = 1024;
+  while (cells < 2 * slabs) cells <<= 1;
+  MEEPO_CUDA_TRY(cudaMalloc(&tv.idx_key, cells * 8));
+  MEEPO_CUDA_TRY(cudaMalloc(&tv.idx_val, cells * 4));
+  MEEPO_CUDA_TRY(cudaMalloc(&tv.ring_key, slabs * 8));
+  MEEPO_CUDA_TRY(cudaMemset(tv.idx_key, 0xFF, cells * 8));
+  MEEPO_CUDA_TRY(cudaMemset(tv.ring_key, 0xFF, slabs * 8));
+  tv.idx_mask = (uint32_t)(cells - 1);
+  tv.slabs = (uint32_t)slabs;
+  tv.stage_d0 = tv.stage_m = 0;
+  MEEPO_CUDA_TRY(cudaStreamCreateWithFlags(&t->tier_stream, cudaStreamNonBlocking));
+  MEEPO_CUDA_TRY(cudaEventCreateWithFlags(&t->tier_staged, cudaEventDisableTiming));
+  MEEPO_CUDA_TRY(cudaEventCreateWithFlags(&t->tier_drained, cudaEventDisableTiming));
+  return MEEPO_OK;
+}
+
+void tier_destroy(meepo_table* t) {
+  if (t->tier_stream) {
+    cudaStreamSynchronize(t->tier_stream);
+    cudaStreamDestroy(t->tier_stream);
+  }
+  if (t->tier_staged) cudaEventDestroy(t->tier_staged);
+  if (t->tier_drained) cudaEventDestroy(t->tier_drained);
+  cudaFree(t->v.tier.idx_key);
+  cudaFree(t->v.tier.idx_val);
+  cudaFree(t->v.tier.ring_key);
+  cudaFree(t->tier_stage);
+  if (t->spill_ring) cudaFreeHost(t->spill_ring);
+  t->spill_ring = nullptr;
+}
+
+// Hands the victims vslot[j0 .. j0 + m) / vkey[..] (eviction order) to the ring. head = tuples appended before
+// this eviction, k = victims of this eviction (the first k - m would be overwritten by the later ones anyway).
+static meepo_status tier_append(meepo_table* t, const uint32_t* vslot, const uint64_t* vkey, uint64_t k,
+                                cudaStream_t stream) {
+  TierView& tv = t->v.tier;
+  const uint64_t slabs = tv.slabs;
+  const uint64_t m = std::min<uint64_t>(k, slabs), j0 = k - m;
+  const uint32_t d0 = (uint32_t)((t->tier_head + j0) % slabs);
+  // tombstones pile up in the index: rebuild it from ring_key before it could run out of unused cells
+  const uint64_t cells = (uint64_t)tv.idx_mask + 1;
+  if (t->tier_nonempty_ub + m > cells / 4 * 3) {
+    ProfScope ps(t, "evict.tier_index_rebuild", stream);
+    MEEPO_CUDA_TRY(cudaMemsetAsync(tv.idx_key, 0xFF, cells * 8, stream));
+    tier_rebuild_kernel<<<grid1d(t, slabs), 256, 0, stream>>>(t->v);
+    t->tier_nonempty_ub = std::min<uint64_t>(slabs, t->tier_head);
+  }
+  {
+    ProfScope ps(t, "evict.tier_index(2 kernels)", stream);
+    tier_retire_kernel<<<grid1d(t, m), 256, 0, stream>>>(t->v, d0, (uint32_t)m);
+    tier_insert_kernel<<<grid1d(t, m), 256, 0, stream>>>(t->v, vkey + j0, d0, (uint32_t)m);
+    MEEPO_CUDA_TRY(cudaGetLastError());
+  }
+  t->tier_nonempty_ub += m;
+  // the previous eviction's drain must be over before its staging buffer is reused
+  if (t->tier_draining) MEEPO_CUDA_TRY(cudaStreamWaitEvent(stream, t->tier_drained, 0));
+  static const uint64_t stage_limit = [] {
+    const char* e = getenv("MEEPO_TIER_STAGE_MAX_BYTES");
+    return e ? strtoull(e, nullptr, 10) : (8ull << 30);
+  }();
+  const bool staged = m * t->tuple_bytes() <= stage_limit;
+  if (staged && m > t->tier_stage_cap) {
+    if (t->tier_draining) MEEPO_CUDA_TRY(cudaEventSynchronize(t->tier_drained));
+    MEEPO_CUDA_TRY(cudaStreamSynchronize(stream));
+    cudaFree(t->tier_stage);
+    t->tier_stage = nullptr;
+    t->tier_stage_cap = 0;
+    const uint64_t cap = m + m / 4;
+    MEEPO_CUDA_TRY(cudaMalloc(&t->tier_stage, cap * t->tuple_bytes()));
+    t->tier_stage_cap = cap;
+    tier_carve(t, t->tier_stage, cap, &tv.s_rows, &tv.s_state, &tv.s_meta, &tv.s_steps);
+  }
+  TierDst dst;
+  if (staged) {
+    dst = TierDst{tv.s_rows, tv.s_state, tv.s_meta, tv.s_steps, 0, 0};
+  } else {
+    dst = TierDst{tv.h_rows, tv.h_state, tv.h_meta, tv.h_steps, d0, (uint32_t)slabs};
+  }
+  {
+    ProfScope ps(t, staged ? "evict.gather_to_staging" : "evict.spill_copy(pcie, zero-copy)", stream);
+    tier_gather_kernel<<<gridwarp(t, m), 256, 0, stream>>>(t->v, dst, vslot + j0, (uint32_t)m);
+    MEEPO_CUDA_TRY(cudaGetLastError());
+  }
+  tv.stage_d0 = staged ? d0 : 0;
+  tv.stage_m = staged ? (uint32_t)m : 0;
+  if (staged) {  // drain: the slabs are consecutive (mod slabs), so each array is one or two plain copies
+    MEEPO_CUDA_TRY(cudaEventRecord(t->tier_staged, stream));
+    MEEPO_CUDA_TRY(cudaStreamWaitEvent(t->tier_stream, t->tier_staged, 0));
+    const uint64_t first = std::min<uint64_t>(m, slabs - d0);
+    auto copy = [&](char* ring, const char* stage, uint64_t width) -> cudaError_t {
+      if (!width) return cudaSuccess;
+      cudaError_t e = cudaMemcpyAsync(ring + (uint64_t)d0 * width, stage, first * width, cudaMemcpyDeviceToHost, t->tier_stream);
+      if (e == cudaSuccess && first < m)
+        e = cudaMemcpyAsync(ring, stage + first * width, (m - first) * width, cudaMemcpyDeviceToHost, t->tier_stream);
+      return e;
+    };
+    MEEPO_CUDA_TRY(copy((char*)tv.h_rows, (const char*)tv.s_rows, t->row_bytes));
+    MEEPO_CUDA_TRY(copy((char*)tv.h_state, (const char*)tv.s_state, t->state_bytes));
+    MEEPO_CUDA_TRY(copy((char*)tv.h_meta, (const char*)tv.s_meta, 16));
+    MEEPO_CUDA_TRY(copy((char*)tv.h_steps, (const char*)tv.s_steps, 4));
+    MEEPO_CUDA_TRY(cudaEventRecord(t->tier_drained, t->tier_stream));
+    t->tier_draining = true;
+  }
+  t->tier_head += k;
+  return MEEPO_OK;
 }
 
 }  // namespace meepo
@@ -256,152 +635,75 @@ MEEPO_API meepo_status meepo_evict(meepo_table* t, int32_t policy, double target
   MEEPO_TRY(vs.rc);
   if (n_evicted) *n_evicted = 0;
   uint64_t size = 0;
-  MEEPO_TRY(live_size(t, &size));
+  {  // the one host synchronisation of the call: with `stream` only (a drain of the previous eviction goes on)
+    unsigned long long v = 0;
+    MEEPO_CUDA_TRY(cudaMemcpyAsync(&v, t->dstate->counters + C_SIZE, 8, cudaMemcpyDeviceToHost, stream));
+    MEEPO_CUDA_TRY(cudaStreamSynchronize(stream));
+    size = v;
+  }
   const uint64_t target = (uint64_t)std::floor(target_load * (double)t->v.slots);
   if (size <= target) return MEEPO_OK;
   const uint64_t k = size - target;
   t->cache_valid = false;
   t->slot_gen++;  // slots are about to change owners
 
-  // --- radix select: threshold T = score of the k-th smallest, need `remaining` of the ties
-  unsigned long long* d_hist = t->dstate->hist;
-  unsigned long long h_hist[256];
-  uint32_t prefix = 0, mask = 0;
-  uint64_t remaining = k, ties = 0;
-  const int sgrid = grid1d(t, t->v.slots);
-  for (int shift = 24; shift >= 0; shift -= 8) {
-    ProfScope ps(t, "evict.select(radix pass)", stream);
-    MEEPO_CUDA_TRY(cudaMemsetAsync(d_hist, 0, sizeof h_hist, stream));
-    score_hist_kernel<<<sgrid, 256, 0, stream>>>(t->v, policy, prefix, mask, shift, 0, 0ull, 0ull, d_hist);
-    MEEPO_CUDA_TRY(cudaMemcpyAsync(h_hist, d_hist, sizeof h_hist, cudaMemcpyDeviceToHost, stream));
-    MEEPO_CUDA_TRY(cudaStreamSynchronize(stream));
-    uint64_t cum = 0;
-    int b = 0;
-    for (; b < 256; b++) {
-      if (cum + h_hist[b] >= remaining) break;
-      cum += h_hist[b];
-    }
-    if (b == 256) return fail(MEEPO_ECUDA, "evict: inconsistent score histogram");
-    remaining -= cum;
-    ties = h_hist[b];
-    prefix |= (uint32_t)b << shift;
-    mask |= 0xFFu << shift;
-  }
-  const uint32_t T = prefix;
-  // `remaining` of the `ties` slots with score == T go too: the ones with the smallest keys
-  uint64_t Tkey = MEEPO_KEY_EMPTY;
-  if (remaining < ties) {
-    uint64_t kprefix = 0, kmask = 0;
-    for (int shift = 56; shift >= 0; shift -= 8) {
-      ProfScope ps(t, "evict.select(radix pass)", stream);
-      MEEPO_CUDA_TRY(cudaMemsetAsync(d_hist, 0, sizeof h_hist, stream));
-      score_hist_kernel<<<sgrid, 256, 0, stream>>>(t->v, policy, T, 0xFFFFFFFFu, shift, 1, kprefix, kmask, d_hist);
-      MEEPO_CUDA_TRY(cudaMemcpyAsync(h_hist, d_hist, sizeof h_hist, cudaMemcpyDeviceToHost, stream));
-      MEEPO_CUDA_TRY(cudaStreamSynchronize(stream));
-      uint64_t cum = 0;
-      int b = 0;
-      for (; b < 256; b++) {
-        if (cum + h_hist[b] >= remaining) break;
-        cum += h_hist[b];
-      }
-      if (b == 256) return fail(MEEPO_ECUDA, "evict: inconsistent key histogram");
-      remaining -= cum;
-      kprefix |= (uint64_t)b << shift;
-      kmask |= 0xFFull << shift;
-    }
-    Tkey = kprefix;
-  }
-  const uint64_t ncand = k;  // exactly the victims
-
-  // --- candidates ordered by (score, key): sort by key, then stable sort by score
-  size_t cub1 = 0, cub2 = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, cub1, (const uint64_t*)nullptr, (uint64_t*)nullptr, (const uint32_t*)nullptr,
-                                  (uint32_t*)nullptr, (int)ncand, 0, 64);
-  cub::DeviceRadixSort::SortPairs(nullptr, cub2, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
-                                  (uint32_t*)nullptr, (int)ncand, 0, 32);
-  const size_t need = 2 * Workspace::pad(ncand * 8) + 6 * Workspace::pad(ncand * 4) + Workspace::pad(std::max(cub1, cub2)) +
-                      Workspace::pad(k * 8) + 2 * Workspace::pad(k * 4) + 4096;
+  const size_t sort_tmp = radix_sort_temp_bytes(k, 32);
+  const size_t need = Workspace::pad(sizeof(SelState)) + Workspace::pad(k * 8) + 2 * Workspace::pad(k * 4) +  // list A
+                      Workspace::pad(size * 8) + Workspace::pad(size * 4) +                                  // list B
+                      4 * Workspace::pad(k * 4) + Workspace::pad(sort_tmp) +                                 // sort
+                      Workspace::pad(k * 8) + Workspace::pad(k * 4) + 8192;
   MEEPO_TRY(t->ws.reserve(need, stream));
-  uint64_t* ckey = t->ws.take<uint64_t>(ncand);
-  uint64_t* ckey_sorted = t->ws.take<uint64_t>(ncand);
-  uint32_t* cslot = t->ws.take<uint32_t>(ncand);
-  uint32_t* ord_a = t->ws.take<uint32_t>(ncand);
-  uint32_t* ord_b = t->ws.take<uint32_t>(ncand);
-  uint32_t* ord_c = t->ws.take<uint32_t>(ncand);
-  uint32_t* sc_a = t->ws.take<uint32_t>(ncand);
-  uint32_t* sc_b = t->ws.take<uint32_t>(ncand);
-  char* tmp = t->ws.take<char>(std::max(cub1, cub2));
+  SelState* sel = t->ws.take<SelState>(1);
+  uint64_t* akey = t->ws.take<uint64_t>(k);
+  uint32_t* aslot = t->ws.take<uint32_t>(k);
+  uint32_t* ascore = t->ws.take<uint32_t>(k);
+  uint64_t* bkey = t->ws.take<uint64_t>(size);
+  uint32_t* bslot = t->ws.take<uint32_t>(size);
+  uint32_t* sk_a = t->ws.take<uint32_t>(k);
+  uint32_t* sk_b = t->ws.take<uint32_t>(k);
+  uint32_t* ord_a = t->ws.take<uint32_t>(k);
+  uint32_t* ord_b = t->ws.take<uint32_t>(k);
+  char* tmp = t->ws.take<char>(sort_tmp);
   uint64_t* vkey = t->ws.take<uint64_t>(k);
   uint32_t* vslot = t->ws.take<uint32_t>(k);
-  uint32_t* vslab = t->ws.take<uint32_t>(k);
-  uint32_t* d_count = &t->dstate->evict_count;
-  {
-  ProfScope ps(t, "evict.order_candidates(4 kernels + 2 cub sorts)", stream);
-  MEEPO_CUDA_TRY(cudaMemsetAsync(d_count, 0, 4, stream));
-  candidates_kernel<<<sgrid, 256, 0, stream>>>(t->v, policy, T, Tkey, ckey, cslot, d_count);
-  const int cgrid = grid1d(t, ncand);
-  iota_kernel<<<cgrid, 256, 0, stream>>>(ord_a, (uint32_t)ncand);
-  MEEPO_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, cub1, (const uint64_t*)ckey, ckey_sorted, (const uint32_t*)ord_a,
-                                                 ord_b, (int)ncand, 0, 64, stream));
-  gather_scores_kernel<<<cgrid, 256, 0, stream>>>(t->v, policy, ord_b, cslot, (uint32_t)ncand, sc_a);
-  MEEPO_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, cub2, (const uint32_t*)sc_a, sc_b, (const uint32_t*)ord_b, ord_c,
-                                                 (int)ncand, 0, 32, stream));
-  victims_kernel<<<grid1d(t, k), 256, 0, stream>>>(ord_c, cslot, ckey, (uint32_t)k, vslot, vkey);
-  MEEPO_CUDA_TRY(cudaGetLastError());
-  }
+  unsigned long long* d_hist = t->dstate->hist;
+  const int sgrid = grid1d(t, t->v.slots);
 
-  // --- spill the last min(k, cap) victims (earlier ones would be pushed out by the FIFO anyway)
-  if (t->spill_cap_tuples) {
-    const uint64_t m = std::min<uint64_t>(k, t->spill_cap_tuples);
-    std::vector<uint64_t> hk(m);
-    std::vector<uint32_t> hs(m);
-    MEEPO_CUDA_TRY(cudaMemcpyAsync(hk.data(), vkey + (k - m), m * 8, cudaMemcpyDeviceToHost, stream));
-    MEEPO_CUDA_TRY(cudaStreamSynchronize(stream));
-    if (k > m) {  // everything older is pushed out by m == cap fresh tuples
-      t->spill_index.clear();
-      t->spill_fifo.clear();
-      t->spill_free.clear();
-      for (uint64_t i = t->spill_cap_tuples; i-- > 0;) t->spill_free.push_back((uint32_t)i);
+  {  // --- threshold T = score of the k-th smallest (score, key)
+    ProfScope ps(t, "evict.select(4 table passes)", stream);
+    sel_init_kernel<<<1, 1, 0, stream>>>(sel, k);
+    MEEPO_CUDA_TRY(cudaMemsetAsync(d_hist, 0, 256 * 8, stream));
+    for (int shift = 24; shift >= 0; shift -= 8) {
+      score_hist_kernel<<<sgrid, 256, 0, stream>>>(t->v, policy, sel, shift, d_hist);
+      sel_step_kernel<<<1, 256, 0, stream>>>(sel, d_hist, shift, 0);
     }
-    const int wgrid = (int)std::max<uint64_t>(1, std::min<uint64_t>((m + 7) / 8, (uint64_t)t->num_sms * 4));
-    t->spill_index.reserve(std::min<uint64_t>(t->spill_index.size() + m, t->spill_cap_tuples));
-    const bool roomy = t->spill_free.size() >= m;  // no tuple has to be pushed out to make room
-    auto h0 = std::chrono::steady_clock::now();
-    if (roomy) {
-      // Slabs first (pops only), so that the PCIe copy can start; the index is filed underneath it. A key that
-      // already has an older copy gets a fresh slab and the old one goes back to the free list afterwards —
-      // which slab a tuple sits in is not observable, what the tier holds is the same as in the loop below.
-      for (uint64_t j = 0; j < m; j++) {
-        hs[j] = t->spill_free.back();
-        t->spill_free.pop_back();
-      }
-    } else {
-      for (uint64_t j = 0; j < m; j++) {  // the index is far larger than the host caches: fetch ahead
-        if (j + 16 < m) t->spill_index.prefetch(hk[j + 16]);
-        hs[j] = spill_push(t, hk[j]);
-      }
-    }
-    MEEPO_CUDA_TRY(cudaMemcpyAsync(vslab, hs.data(), m * 4, cudaMemcpyHostToDevice, stream));
-    {
-      ProfScope ps(t, "evict.spill_copy(pcie)", stream);
-      spill_copy_kernel<<<wgrid, 256, 0, stream>>>(t->v, spill_view(t), vslot + (k - m), vslab, (uint32_t)m);
-    }
-    if (roomy) {  // several host threads file the index while this one appends the FIFO entries
-      const uint64_t seq0 = t->spill_seq;
-      t->spill_seq += m;
-      std::vector<uint32_t> freed;
-      std::thread filer([&] {
-        t->spill_index.replace_all(hk.data(), hs.data(), seq0, m, freed,
-                                   (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2)));
-      });
-      for (uint64_t j = 0; j < m; j++) t->spill_fifo.emplace_back(seq0 + j, hk[j]);
-      filer.join();
-      t->spill_free.insert(t->spill_free.end(), freed.begin(), freed.end());
-    }
-    prof_add_host(t, roomy ? "evict.host_index(wall, under the spill copy)" : "evict.host_index(wall)",
-                  std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count());
-    MEEPO_CUDA_TRY(cudaStreamSynchronize(stream));  // hs must outlive the copy
+    MEEPO_CUDA_TRY(cudaGetLastError());
   }
+  {  // --- victims below T, candidates at T; the key threshold among the candidates
+    ProfScope ps(t, "evict.split+ties(1 table pass + 8 list passes)", stream);
+    split_kernel<<<gridsel(t, t->v.slots), 256, 0, stream>>>(t->v, policy, sel, akey, aslot, ascore, bkey, bslot);
+    const int bgrid = grid1d(t, size);
+    for (int shift = 56; shift >= 0; shift -= 8) {
+      key_hist_kernel<<<bgrid, 256, 0, stream>>>(bkey, sel, shift, d_hist);
+      sel_step_kernel<<<1, 256, 0, stream>>>(sel, d_hist, shift, 1);
+    }
+    take_ties_kernel<<<gridsel(t, size), 256, 0, stream>>>(sel, bkey, bslot, akey, aslot, ascore, (uint32_t)k);
+    MEEPO_CUDA_TRY(cudaGetLastError());
+  }
+  {  // --- eviction order: ascending (score, key)
+    ProfScope ps(t, "evict.order(3 radix sorts)", stream);
+    const int kgrid = grid1d(t, k);
+    if (!radix_sort_supported(k, 32)) return fail(MEEPO_EINVAL, "evict: too many victims for one call");
+    sort_key_kernel<<<kgrid, 256, 0, stream>>>(0, akey, ascore, nullptr, (uint32_t)k, sk_a, ord_a);
+    MEEPO_TRY(radix_sort_pairs(t, tmp, sk_a, sk_b, ord_a, ord_b, (uint32_t)k, 32, stream));
+    sort_key_kernel<<<kgrid, 256, 0, stream>>>(1, akey, ascore, ord_b, (uint32_t)k, sk_a, nullptr);
+    MEEPO_TRY(radix_sort_pairs(t, tmp, sk_a, sk_b, ord_b, ord_a, (uint32_t)k, 32, stream));
+    sort_key_kernel<<<kgrid, 256, 0, stream>>>(2, akey, ascore, ord_a, (uint32_t)k, sk_a, nullptr);
+    MEEPO_TRY(radix_sort_pairs(t, tmp, sk_a, sk_b, ord_a, ord_b, (uint32_t)k, 32, stream));
+    victims_kernel<<<kgrid, 256, 0, stream>>>(ord_b, aslot, akey, (uint32_t)k, vslot, vkey);
+    MEEPO_CUDA_TRY(cudaGetLastError());
+  }
+  if (t->v.tier.slabs) MEEPO_TRY(tier_append(t, vslot, vkey, k, stream));
   {
     ProfScope ps(t, "evict.release", stream);
     release_kernel<<<grid1d(t, k), 256, 0, stream>>>(t->v, vslot, (uint32_t)k);
@@ -412,7 +714,6 @@ MEEPO_API meepo_status meepo_evict(meepo_table* t, int32_t policy, double target
     overflow_mark_kernel<<<grid1d(t, t->v.slots), 256, 0, stream>>>(t->v);
   }
   MEEPO_CUDA_TRY(cudaGetLastError());
-  MEEPO_CUDA_TRY(cudaStreamSynchronize(stream));
   if (n_evicted) *n_evicted = k;
   return MEEPO_OK;
 }
@@ -426,60 +727,24 @@ MEEPO_API meepo_status meepo_spill_readmit(meepo_table* t, const uint64_t* keys,
   cudaStream_t stream = nullptr;
   VerbScope vs(t, stream);
   MEEPO_TRY(vs.rc);
-  MEEPO_TRY(t->ws.reserve(Workspace::pad(n * 8) + Workspace::pad(n) + 4 * Workspace::pad(n * 4) + 4096, stream));
+  MEEPO_TRY(t->ws.reserve(Workspace::pad(n * 8) + Workspace::pad(n) + 2 * Workspace::pad(n * 4) + 4096, stream));
   uint64_t* d_keys = t->ws.take<uint64_t>(n);
-  uint8_t* d_found = t->ws.take<uint8_t>(n);
+  uint8_t* d_status = t->ws.take<uint8_t>(n);
   uint32_t* d_slot = t->ws.take<uint32_t>(n);
   uint32_t* d_slab = t->ws.take<uint32_t>(n);
-  uint32_t* d_new = t->ws.take<uint32_t>(n);
   MEEPO_CUDA_TRY(cudaMemcpyAsync(d_keys, keys, n * 8, cudaMemcpyHostToDevice, stream));
-  found_flags_kernel<<<grid1d(t, n), 256, 0, stream>>>(t->v, d_keys, (uint32_t)n, d_found);
-  std::vector<uint8_t> found(n);
-  MEEPO_CUDA_TRY(cudaMemcpyAsync(found.data(), d_found, n, cudaMemcpyDeviceToHost, stream));
-  uint64_t size = 0;
-  MEEPO_TRY(live_size(t, &size));  // synchronises
-  std::vector<uint64_t> ins_keys;
-  std::vector<uint32_t> ins_slab;
-  std::unordered_map<uint64_t, int> admitted;  // keys restored earlier in this call count as present
-  for (uint64_t i = 0; i < n; i++) {
-    const uint64_t k = keys[i];
-    uint8_t st;
-    if (!key_valid(k))
-      st = MEEPO_KEY_INVALID;
-    else if (found[i] || admitted.count(k)) {
-      st = MEEPO_KEY_FOUND;
-      if (!admitted.count(k)) spill_drop(t, k);
-    } else {
-      SpillTuple* it = t->spill_index.find(k);
-      if (!it)
-        st = MEEPO_KEY_MISS;
-      else if (size + ins_keys.size() >= t->v.slots)
-        st = MEEPO_KEY_FULL;
-      else {
-        ins_keys.push_back(k);
-        ins_slab.push_back((uint32_t)it->ring_index);
-        t->spill_index.erase(k);  // the slab is recycled after the copy below
-        admitted[k] = 1;
-        st = MEEPO_KEY_INSERTED;
-      }
-    }
-    if (status_out) status_out[i] = st;
-  }
-  const uint64_t m = ins_keys.size();
-  if (m) {
-    t->cache_valid = false;
-    t->slot_gen++;
-    MEEPO_CUDA_TRY(cudaMemcpyAsync(d_keys, ins_keys.data(), m * 8, cudaMemcpyHostToDevice, stream));
-    MEEPO_CUDA_TRY(cudaMemcpyAsync(d_slab, ins_slab.data(), m * 4, cudaMemcpyHostToDevice, stream));
-    NewList nl{d_new};
-    MEEPO_TRY(import_probe_launch(t, d_keys, m, d_slot, nullptr, nl, stream));
-    MEEPO_TRY(publish_slots(t, nl.slots, m, stream));
-    const int wgrid = (int)std::max<uint64_t>(1, std::min<uint64_t>((m + 7) / 8, (uint64_t)t->num_sms * 4));
-    readmit_copy_kernel<<<wgrid, 256, 0, stream>>>(t->v, spill_view(t), d_slot, d_slab, (uint32_t)m);
+  t->cache_valid = false;
+  t->slot_gen++;
+  readmit_probe_kernel<<<grid1d(t, n), 256, 0, stream>>>(t->v, d_keys, (uint32_t)n, d_status, d_slot, d_slab);
+  if (t->v.tier.slabs) {  // without a tier every key is FOUND, MISS or INVALID and nothing moves
+    readmit_copy_kernel<<<gridwarp(t, n), 256, 0, stream>>>(t->v, d_slot, d_slab, (uint32_t)n);
+    readmit_drop_kernel<<<grid1d(t, n), 256, 0, stream>>>(t->v, d_keys, d_status, (uint32_t)n);
     MEEPO_CUDA_TRY(cudaGetLastError());
-    MEEPO_CUDA_TRY(cudaStreamSynchronize(stream));
-    for (uint32_t s : ins_slab) t->spill_free.push_back(s);
+    MEEPO_TRY(publish_slots(t, d_slot, n, stream));  // tags, size, and the restored keys leave the tier
   }
+  MEEPO_CUDA_TRY(cudaGetLastError());
+  if (status_out) MEEPO_CUDA_TRY(cudaMemcpyAsync(status_out, d_status, n, cudaMemcpyDeviceToHost, stream));
+  MEEPO_CUDA_TRY(cudaStreamSynchronize(stream));
   return MEEPO_OK;
 }
 

@@ -4,7 +4,7 @@
 
 namespace meepo {
 
-template <int CPR, bool INSERT>
+template <int CPR, bool INSERT, bool TIER>
 __global__ void __launch_bounds__(256, 4) probe_gather_kernel(TableView t, const uint64_t* __restrict__ keys,
                                                            uint32_t n, uint4* __restrict__ out,
                                                            uint8_t* __restrict__ status, NewList nl, SlotCache sc) {
@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(256, 4) probe_gather_kernel(TableView t, const
     const uint32_t i = tile * 32u + lane;
     const uint32_t tile_keys = min(32u, n - tile * 32u);
     const uint64_t key = i < n ? __ldg(keys + i) : MEEPO_KEY_EMPTY;
-    probe_gather_tile<CPR, INSERT>(t, key, i < n, tile_keys, out + (size_t)tile * 32u * cpr,
+    probe_gather_tile<CPR, INSERT, false, TIER>(t, key, i < n, tile_keys, out + (size_t)tile * 32u * cpr,
                                    status ? status + i : nullptr, sc.slots ? sc.slots + i : nullptr,
                                    sc.keys ? sc.keys + i : nullptr, 1u, nl.slots ? nl.slots + i : nullptr, cnt,
                                    scache, lane);
@@ -33,33 +33,42 @@ __global__ void __launch_bounds__(256, 4) probe_gather_kernel(TableView t, const
 // Writes the tags of the slots claimed by the preceding probe_gather_kernel<.., true> (new_slots[i]
 // != kNil) and folds their number into the table size.
 __global__ void __launch_bounds__(256) publish_kernel(TableView t, const uint32_t* __restrict__ new_slots, uint32_t n) {
-  uint32_t mine = 0;
+  uint32_t mine = 0, promoted = 0;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint32_t s = __ldg(new_slots + i);
     if (s == kNil) continue;
-    *tag_ptr(t, s) = (uint8_t)digest_of(mix64(*key_ptr(t, s)));
+    const uint64_t key = *key_ptr(t, s);
+    *tag_ptr(t, s) = (uint8_t)digest_of(mix64(key));
     mark_dirty(t, s);
     mine++;
+    // a key that came back from the host tier leaves it now: the probe kernels of this call had to see it there
+    if (t.tier.slabs && tier_erase(t, key)) promoted++;
   }
   mine = __reduce_add_sync(0xFFFFFFFFu, mine);
+  promoted = __reduce_add_sync(0xFFFFFFFFu, promoted);
   if ((threadIdx.x & 31u) == 0 && mine) {
     atomicAdd(t.counters + C_SIZE, (unsigned long long)mine);
-    atomicAdd(t.counters + C_INSERTS, (unsigned long long)mine);
+    if (mine > promoted) atomicAdd(t.counters + C_INSERTS, (unsigned long long)(mine - promoted));
+    if (promoted) atomicAdd(t.counters + C_PROMOTIONS, (unsigned long long)promoted);
   }
 }
 
-template <bool INSERT>
+template <bool INSERT, bool TIER>
 static const void* pick_kernel(uint32_t cpr) {
   switch (cpr) {
-    case 1: return (const void*)probe_gather_kernel<1, INSERT>;
-    case 2: return (const void*)probe_gather_kernel<2, INSERT>;
-    case 4: return (const void*)probe_gather_kernel<4, INSERT>;
-    case 8: return (const void*)probe_gather_kernel<8, INSERT>;
-    case 16: return (const void*)probe_gather_kernel<16, INSERT>;
-    case 32: return (const void*)probe_gather_kernel<32, INSERT>;
-    case 64: return (const void*)probe_gather_kernel<64, INSERT>;
-    default: return (const void*)probe_gather_kernel<0, INSERT>;
+    case 1: return (const void*)probe_gather_kernel<1, INSERT, TIER>;
+    case 2: return (const void*)probe_gather_kernel<2, INSERT, TIER>;
+    case 4: return (const void*)probe_gather_kernel<4, INSERT, TIER>;
+    case 8: return (const void*)probe_gather_kernel<8, INSERT, TIER>;
+    case 16: return (const void*)probe_gather_kernel<16, INSERT, TIER>;
+    case 32: return (const void*)probe_gather_kernel<32, INSERT, TIER>;
+    case 64: return (const void*)probe_gather_kernel<64, INSERT, TIER>;
+    default: return (const void*)probe_gather_kernel<0, INSERT, TIER>;
   }
+}
+static const void* pick_kernel(bool insert, bool tier, uint32_t cpr) {
+  if (tier) return insert ? pick_kernel<true, true>(cpr) : pick_kernel<false, true>(cpr);
+  return insert ? pick_kernel<true, false>(cpr) : pick_kernel<false, false>(cpr);
 }
 
 // A find_or_insert / lookup call = begin, one or more chunks, end. Chunks of one call share the
@@ -98,7 +107,7 @@ meepo_status probe_gather_begin(meepo_table* t, uint64_t n_total, bool insert, c
 meepo_status probe_gather_chunk(meepo_table* t, const uint64_t* keys, uint64_t n, void* rows_out,
                                 uint8_t* status_out, bool insert, cudaStream_t stream) {
   if (n == 0) return MEEPO_OK;
-  const void* kern = insert ? pick_kernel<true>(t->v.cpr) : pick_kernel<false>(t->v.cpr);
+  const void* kern = pick_kernel(insert, t->v.tier.slabs != 0, t->v.cpr);
   const uint64_t tiles = (n + 31) / 32;
   const int grid = grid_for(t, kern, 256, 0, (tiles + 7) / 8);
   uint32_t n32 = (uint32_t)n;

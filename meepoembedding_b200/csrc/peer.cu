@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(256) grad_prep_kernel(const __grid_constant__ 
 // --- owner: probe + gather + peer store ------------------------------------------------------------
 // Tile = 32 consecutive positions of ONE source's lane. Every row goes to its own destination (SCATTER tile
 // body): the requester's output tensor at the key's canonical batch index, or the requester's return region.
-template <int CPR, bool INSERT>
+template <int CPR, bool INSERT, bool TIER = false>
 __global__ void __launch_bounds__(256, 3) owner_probe_gather_kernel(TableView t, const __grid_constant__ PeerSet ps,
                                                                  const PeerWork* __restrict__ work, NewList nl,
                                                                  uint32_t* __restrict__ entry_slot) {
@@ -441,7 +441,7 @@ __global__ void __launch_bounds__(256, 3) owner_probe_gather_kernel(TableView t,
         else
           dst = (unsigned long long)(ps.w[s].ret_rows + r * cpr);
       }
-      probe_gather_tile<CPR, INSERT, true>(t, key, valid, tile_keys, nullptr, valid ? ps.w[s].ret_status + r : nullptr,
+      probe_gather_tile<CPR, INSERT, true, TIER>(t, key, valid, tile_keys, nullptr, valid ? ps.w[s].ret_status + r : nullptr,
                                            entry_slot + e, nullptr, occ, nl.slots + e, cnt, scache, lane, dst);
     }
   }
@@ -449,8 +449,10 @@ __global__ void __launch_bounds__(256, 3) owner_probe_gather_kernel(TableView t,
   flush_tile_counts(t, cnt, lane);
 }
 
+// A shard with a host tier runs the generic-width kernel (the tier variants are not specialised per row width).
 template <bool INSERT>
-static const void* pick_owner_kernel(uint32_t cpr) {
+static const void* pick_owner_kernel(uint32_t cpr, bool tier = false) {
+  if (tier) return (const void*)owner_probe_gather_kernel<0, INSERT, true>;
   switch (cpr) {
     case 1: return (const void*)owner_probe_gather_kernel<1, INSERT>;
     case 2: return (const void*)owner_probe_gather_kernel<2, INSERT>;
@@ -649,7 +651,8 @@ static meepo_status sharded_forward(meepo_table* t, const uint64_t* keys, uint64
   MEEPO_TRY(barrier(t, p->chunk_cnt + (p->chunks - 1) * kMaxPeers, fwork, nullptr, false, nullptr, true, out_off, stream));
   {
     ProfScope ps(t, insert ? "sharded.owner_find_or_insert" : "sharded.owner_lookup", stream);
-    const void* kern = insert ? pick_owner_kernel<true>(t->v.cpr) : pick_owner_kernel<false>(t->v.cpr);
+    const void* kern = insert ? pick_owner_kernel<true>(t->v.cpr, t->v.tier.slabs != 0)
+                              : pick_owner_kernel<false>(t->v.cpr, t->v.tier.slabs != 0);
     const uint64_t tiles = ((uint64_t)p->world * p->region + 31) / 32 + p->world;
     const int grid = grid_for(t, kern, 256, 0, (tiles + 7) / 8);
     const PeerWork* work = fwork;

@@ -85,13 +85,48 @@ __device__ __forceinline__ void fixup_fresh(const TableView& t, uint64_t key, co
   }
 }
 
+// Keys served from the host tier (meepo.h "Host tier"): promoted by find_or_insert (the CAS winner restores row,
+// state, step and the tier's freq into its slot) or read through by lookup. One key at a time, the lanes cover
+// its chunks; the tuple is read from the staging buffer (HBM) or the pinned ring (zero-copy over PCIe).
+template <bool SCATTER = false>
+__device__ __forceinline__ void fixup_tier(const TableView& t, const Probe& pr, uint32_t tslab, uint32_t tile_keys,
+                                           uint4* __restrict__ out_tile, uint32_t lane, unsigned long long dst = 0) {
+  unsigned m = __ballot_sync(0xFFFFFFFFu, tslab != kNil);
+  const uint32_t cpr = t.cpr;
+  while (m) {
+    const int j = __ffs(m) - 1;
+    m &= m - 1;
+    const uint32_t s = __shfl_sync(0xFFFFFFFFu, pr.slot, j);
+    const bool win = __shfl_sync(0xFFFFFFFFu, (int)pr.winner, j);
+    const uint32_t slab = __shfl_sync(0xFFFFFFFFu, tslab, j);
+    uint4* orow = out_tile + (size_t)j * cpr;
+    if constexpr (SCATTER) orow = reinterpret_cast<uint4*>(__shfl_sync(0xFFFFFFFFu, dst, j));
+    if ((uint32_t)j >= tile_keys) continue;
+    const TierTuple tt = tier_tuple(t, slab);
+    for (uint32_t off = lane; off < cpr; off += 32) {
+      const uint4 v = tt.rows[off];
+      if (win) t.rows[(size_t)s * cpr + off] = v;
+      st_stream(orow + off, v);
+    }
+    if (win) {
+      for (uint32_t off = lane; off < t.scpr; off += 32) t.state[(size_t)s * t.scpr + off] = tt.state[off];
+      if (lane == 0) {
+        // the slot's scores were zero: the occurrences of this batch are added by the score path, here the past
+        if (t.scores) atomicAdd(&t.scores[s].x, tt.meta->z);
+        if (t.steps) t.steps[s] = *tt.steps;
+      }
+    }
+  }
+}
+
 // Generic-width version (any cpr): the fallback for row widths without a specialised kernel.
 template <bool SCATTER = false>
-__device__ __forceinline__ void gather_tile_slow(const TableView& t, uint64_t key, const Probe& pr,
+__device__ __forceinline__ void gather_tile_slow(const TableView& t, uint64_t key, const Probe& pr, uint32_t tslab,
                                                  uint32_t tile_keys, uint4* __restrict__ out_tile,
                                                  uint32_t lane, unsigned long long dst = 0) {
   const uint32_t cpr = t.cpr;
   for (uint32_t j = 0; j < tile_keys; j++) {
+    if (__shfl_sync(0xFFFFFFFFu, tslab, j) != kNil) continue;  // fixup_tier moves it
     const uint32_t s = __shfl_sync(0xFFFFFFFFu, pr.slot, j);
     const uint32_t st = __shfl_sync(0xFFFFFFFFu, pr.status, j);
     const bool win = __shfl_sync(0xFFFFFFFFu, (int)pr.winner, j);
@@ -116,7 +151,7 @@ __device__ __forceinline__ void gather_tile_slow(const TableView& t, uint64_t ke
 }
 
 struct TileCounts {
-  uint32_t hit = 0, miss = 0, full = 0;
+  uint32_t hit = 0, miss = 0, full = 0, tier = 0;
 };
 
 // LFU / LRU score updates (meepo.h "Evict": freq += occurrences, last_epoch = epoch) go through a
@@ -166,7 +201,8 @@ static_assert(kScoreCells == 1u << 9, "score_cache_add hashes to 9 bits");
 // the sender's duplicate count on the sharded path): added to the hit/miss counters and to the key's
 // LFU score.
 // SCATTER: out_tile is ignored, this lane's row goes to (uint4*)dst (see tile_dst).
-template <int CPR, bool INSERT, bool SCATTER = false>
+// TIER: the table has a host tier (compiled out otherwise: the tier code costs registers in the hot kernels).
+template <int CPR, bool INSERT, bool SCATTER = false, bool TIER = false>
 __device__ __forceinline__ void probe_gather_tile(const TableView& t, uint64_t key, bool valid, uint32_t tile_keys,
                                                   uint4* __restrict__ out_tile, uint8_t* status_out,
                                                   uint32_t* slot_out, uint64_t* key_out, uint32_t occurrences,
@@ -178,6 +214,16 @@ __device__ __forceinline__ void probe_gather_tile(const TableView& t, uint64_t k
   } else if (key_valid(key)) {
     pr.slot = probe_find<kReadOnly>(t, key);
     pr.status = pr.slot != kNil ? MEEPO_KEY_FOUND : MEEPO_KEY_MISS;
+  }
+  // second level (meepo.h "Host tier"): a key that is not in HBM but in the tier is FOUND — promoted by
+  // find_or_insert (unless the table is full), read through by lookup
+  uint32_t tslab = kNil;
+  if constexpr (TIER) {
+    if (valid && (pr.status == MEEPO_KEY_INSERTED || pr.status == MEEPO_KEY_MISS)) tslab = tier_slab(t.tier, key);
+    if (tslab != kNil) {
+      pr.status = MEEPO_KEY_FOUND;
+      if (!INSERT) cnt.tier += occurrences;
+    }
   }
   if (valid) {
     if (status_out) *status_out = (uint8_t)pr.status;
@@ -200,12 +246,14 @@ __device__ __forceinline__ void probe_gather_tile(const TableView& t, uint64_t k
     fresh = __any_sync(0xFFFFFFFFu, pr.status == MEEPO_KEY_INSERTED);
   }
   if (CPR > 0) {
-    gather_tile_fast<(CPR > 0 ? CPR : 1), SCATTER>(t, pr.status == MEEPO_KEY_INSERTED ? kNil : pr.slot, tile_keys,
-                                                   out_tile, lane, dst);
+    gather_tile_fast<(CPR > 0 ? CPR : 1), SCATTER>(t, (pr.status == MEEPO_KEY_INSERTED || tslab != kNil) ? kNil : pr.slot,
+                                                   tile_keys, out_tile, lane, dst);
     if (fresh) fixup_fresh<(CPR > 0 ? CPR : 1), SCATTER>(t, key, pr, tile_keys, out_tile, lane, dst);
   } else {
-    gather_tile_slow<SCATTER>(t, key, pr, tile_keys, out_tile, lane, dst);
+    gather_tile_slow<SCATTER>(t, key, pr, tslab, tile_keys, out_tile, lane, dst);
   }
+  if constexpr (TIER)
+    if (__any_sync(0xFFFFFFFFu, tslab != kNil)) fixup_tier<SCATTER>(t, pr, tslab, tile_keys, out_tile, lane, dst);
 }
 
 // stats: one atomic per warp per counter for the whole launch
@@ -213,7 +261,9 @@ __device__ __forceinline__ void flush_tile_counts(const TableView& t, TileCounts
   c.hit = __reduce_add_sync(0xFFFFFFFFu, c.hit);
   c.miss = __reduce_add_sync(0xFFFFFFFFu, c.miss);
   c.full = __reduce_add_sync(0xFFFFFFFFu, c.full);
+  c.tier = __reduce_add_sync(0xFFFFFFFFu, c.tier);
   if (lane == 0) {
+    if (c.tier) atomicAdd(t.counters + C_TIER_HITS, (unsigned long long)c.tier);
     if (c.hit) atomicAdd(t.counters + C_HITS, (unsigned long long)c.hit);
     if (c.miss) atomicAdd(t.counters + C_MISSES, (unsigned long long)c.miss);
     if (c.full) atomicAdd(t.counters + C_FULL, (unsigned long long)c.full);

@@ -201,13 +201,11 @@ MEEPO_API meepo_status meepo_create(const meepo_config* cfg, meepo_table** out) 
       return bail(e, "cudaEventCreate");
   }
   if (cfg->host_spill_bytes) {
-    t->spill_cap_tuples = cfg->host_spill_bytes / t->tuple_bytes();
-    if (t->spill_cap_tuples) {
-      if ((e = cudaHostAlloc(&t->spill_ring, t->spill_cap_tuples * t->tuple_bytes(), cudaHostAllocMapped | cudaHostAllocPortable)) !=
-          cudaSuccess)
-        return bail(e, "cudaHostAlloc(spill)");
-      for (uint64_t i = t->spill_cap_tuples; i-- > 0;) t->spill_free.push_back((uint32_t)i);
-      t->spill_index.reserve(t->spill_cap_tuples);  // no rehash while evicting
+    const meepo_status rc = tier_create(t);
+    if (rc != MEEPO_OK) {
+      const std::string m = meepo_last_error();
+      meepo_destroy(t);
+      return fail(rc, m);
     }
   }
   if ((e = cudaDeviceSynchronize()) != cudaSuccess) return bail(e, "cudaDeviceSynchronize");
@@ -232,7 +230,7 @@ MEEPO_API meepo_status meepo_destroy(meepo_table* t) {
   cudaFree(t->ws.base);
   cudaFree(t->cache.keys);
   cudaFree(t->cache.slots);
-  if (t->spill_ring) cudaFreeHost(t->spill_ring);
+  tier_destroy(t);
   if (t->err_host) cudaFreeHost(const_cast<uint32_t*>(t->err_host));
   if (t->order_ev) cudaEventDestroy(t->order_ev);
   delete t;
@@ -258,8 +256,10 @@ MEEPO_API meepo_status meepo_stats(meepo_table* t, meepo_stats_t* out) {
   out->overflow_buckets = c[C_OVERFLOW];
   out->peer_keys_received = c[C_PEER_KEYS];
   out->peer_grads_received = c[C_PEER_GRADS];
-  out->spill_keys = t->spill_index.size();
-  out->spill_bytes = t->spill_index.size() * t->tuple_bytes();
+  out->spill_keys = c[C_TIER_LIVE];
+  out->spill_bytes = c[C_TIER_LIVE] * t->tuple_bytes();
+  out->promotions = c[C_PROMOTIONS];
+  out->tier_hits = c[C_TIER_HITS];
   out->epoch = t->epoch;
   out->row_bytes = t->row_bytes;
   out->state_bytes = t->state_bytes;

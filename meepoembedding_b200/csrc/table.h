@@ -3,10 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
-#include <deque>
 #include <string>
-#include <thread>
-#include <unordered_map>
 #include <vector>
 
 #include "common.cuh"
@@ -75,146 +72,6 @@ struct NewList {
   uint32_t* slots;
 };
 
-struct SpillTuple {  // host spill tier bookkeeping (payload lives in the pinned ring)
-  uint64_t seq;
-  uint64_t ring_index;
-};
-
-// key -> SpillTuple on the host: open addressing, linear probing, backward-shift deletion. An evict
-// call files hundreds of thousands of keys here; a node-based map spends longer on that than the
-// GPU does on selecting and copying the victims. One shard of the index below.
-class SpillShard {
- public:
-  SpillTuple* find(uint64_t key) {
-    if (cells_.empty()) return nullptr;
-    for (size_t i = home(key);; i = (i + 1) & mask_) {
-      if (cells_[i].key == key) return &cells_[i].val;
-      if (cells_[i].key == kFree) return nullptr;
-    }
-  }
-  void put(uint64_t key, SpillTuple v) {
-    if ((size_ + 1) * 10 > cells_.size() * 7) grow();
-    for (size_t i = home(key);; i = (i + 1) & mask_) {
-      if (cells_[i].key == key) {
-        cells_[i].val = v;
-        return;
-      }
-      if (cells_[i].key == kFree) {
-        cells_[i].key = key;
-        cells_[i].val = v;
-        size_++;
-        return;
-      }
-    }
-  }
-  bool erase(uint64_t key) {
-    if (cells_.empty()) return false;
-    size_t i = home(key);
-    for (;; i = (i + 1) & mask_) {
-      if (cells_[i].key == key) break;
-      if (cells_[i].key == kFree) return false;
-    }
-    for (size_t j = (i + 1) & mask_;; j = (j + 1) & mask_) {  // close the gap
-      if (cells_[j].key == kFree) break;
-      const size_t hj = home(cells_[j].key);
-      if (((j - hj) & mask_) >= ((j - i) & mask_)) {
-        cells_[i] = cells_[j];
-        i = j;
-      }
-    }
-    cells_[i].key = kFree;
-    size_--;
-    return true;
-  }
-  void clear() {
-    for (auto& c : cells_) c.key = kFree;
-    size_ = 0;
-  }
-  void reserve(size_t n) {
-    while (cells_.size() * 7 < n * 10) grow();
-  }
-  void prefetch(uint64_t key) const {
-    if (!cells_.empty()) __builtin_prefetch(&cells_[home(key)], 1, 1);
-  }
-  size_t size() const { return size_; }
-
- private:
-  static constexpr uint64_t kFree = MEEPO_KEY_EMPTY;  // never a storable key
-  struct Cell {
-    uint64_t key;
-    SpillTuple val;
-  };
-  size_t home(uint64_t key) const { return (size_t)mix64(key) & mask_; }
-  void grow() {
-    std::vector<Cell> old;
-    old.swap(cells_);
-    cells_.assign(old.empty() ? 1024 : old.size() * 2, Cell{kFree, {0, 0}});
-    mask_ = cells_.size() - 1;
-    size_ = 0;
-    for (auto& c : old)
-      if (c.key != kFree) put(c.key, c.val);
-  }
-  std::vector<Cell> cells_;
-  size_t mask_ = 0, size_ = 0;
-};
-
-// The index proper: 16 independent shards selected by the top bits of the key's hash (the cell inside a
-// shard comes from the low bits), so that one evict call can file its victims from several host threads —
-// the table is far larger than the host caches and every access is a DRAM round trip.
-class SpillIndex {
- public:
-  static constexpr int kShards = 16;
-  SpillTuple* find(uint64_t key) { return sh_[shard_of(key)].find(key); }
-  void put(uint64_t key, SpillTuple v) { sh_[shard_of(key)].put(key, v); }
-  bool erase(uint64_t key) { return sh_[shard_of(key)].erase(key); }
-  void prefetch(uint64_t key) const { sh_[shard_of(key)].prefetch(key); }
-  void clear() {
-    for (auto& s : sh_) s.clear();
-  }
-  void reserve(size_t n) {
-    for (auto& s : sh_) s.reserve(n / kShards + n / (4 * kShards) + 64);
-  }
-  size_t size() const {
-    size_t n = 0;
-    for (auto& s : sh_) n += s.size();
-    return n;
-  }
-  // keys[j] -> {seq0 + j, slabs[j]} for j in [0, m): the keys are distinct; the slab of the older copy of a key,
-  // if there was one, is appended to `freed`. Runs on up to `threads` host threads, each owning whole shards.
-  void replace_all(const uint64_t* keys, const uint32_t* slabs, uint64_t seq0, size_t m, std::vector<uint32_t>& freed,
-                   int threads);
-
- private:
-  static int shard_of(uint64_t key) { return (int)(mix64(key) >> 60); }
-  SpillShard sh_[kShards];
-};
-static_assert(SpillIndex::kShards == 16, "shard_of takes the top 4 hash bits");
-
-inline void SpillIndex::replace_all(const uint64_t* keys, const uint32_t* slabs, uint64_t seq0, size_t m,
-                                    std::vector<uint32_t>& freed, int threads) {
-  threads = std::max(1, std::min(threads, (int)kShards));
-  std::vector<std::vector<uint32_t>> old(threads);
-  auto work = [&](int tid) {
-    for (size_t j = 0; j < m; j++) {
-      const int sh = shard_of(keys[j]);
-      if (sh % threads != tid) continue;
-      if (j + 64 < m) sh_[shard_of(keys[j + 64])].prefetch(keys[j + 64]);  // harmless when it is another thread's
-      SpillShard& s = sh_[sh];
-      if (SpillTuple* o = s.find(keys[j])) old[tid].push_back((uint32_t)o->ring_index);
-      s.put(keys[j], SpillTuple{seq0 + j, slabs[j]});
-    }
-  };
-  if (threads == 1 || m < 4096) {
-    for (int tid = 0; tid < threads; tid++) work(tid);
-  } else {
-    std::vector<std::thread> pool;
-    for (int tid = 1; tid < threads; tid++) pool.emplace_back(work, tid);
-    work(0);
-    for (auto& th : pool) th.join();
-  }
-  for (auto& v : old) freed.insert(freed.end(), v.begin(), v.end());
-}
-
 }  // namespace meepo
 
 struct meepo_table {
@@ -247,13 +104,16 @@ struct meepo_table {
   // host-buffer front end (pinned staging + private streams), created lazily
   struct HostPipe* pipe = nullptr;
   struct meepo::PeerState* peer = nullptr;
-  // host spill tier
-  char* spill_ring = nullptr;       // pinned
-  uint64_t spill_cap_tuples = 0;
-  uint64_t spill_seq = 0;
-  meepo::SpillIndex spill_index;                                // key -> newest tuple
-  std::deque<std::pair<uint64_t, uint64_t>> spill_fifo;         // (seq, key), oldest first; stale entries skipped
-  std::vector<uint32_t> spill_free;                             // free slab indices
+  // host tier (meepo.h "Host tier"; evict.cu): the device-side view is v.tier
+  char* spill_ring = nullptr;    // mapped pinned host memory: the ring of slabs
+  uint64_t spill_cap_tuples = 0; // slabs
+  uint64_t tier_head = 0;        // tuples appended so far: the next one goes to slab tier_head % slabs
+  uint64_t tier_nonempty_ub = 0; // upper bound of the index cells that are not EMPTY (live + tombstones)
+  char* tier_stage = nullptr;    // device staging buffer of the latest eviction's tuples
+  uint64_t tier_stage_cap = 0;   // ... in tuples
+  cudaStream_t tier_stream = nullptr;  // drains the staging buffer to the ring
+  cudaEvent_t tier_staged = nullptr, tier_drained = nullptr;
+  bool tier_draining = false;
 
   uint64_t tuple_bytes() const { return 24 + (uint64_t)row_bytes + state_bytes; }
 };
@@ -374,6 +234,9 @@ void destroy_peer(meepo_table* t);
 // lookup.cu: write the tags of the slots listed in slots[0..n) (kNil cells skipped) and fold their
 // number into the size
 meepo_status publish_slots(meepo_table* t, const uint32_t* slots, uint64_t n, cudaStream_t stream);
+// evict.cu: the host tier
+meepo_status tier_create(meepo_table* t);
+void tier_destroy(meepo_table* t);
 // io.cu
 meepo_status live_size(meepo_table* t, uint64_t* out);
 meepo_status import_probe_launch(meepo_table* t, const uint64_t* keys, uint64_t n, uint32_t* slot_out,

@@ -52,8 +52,13 @@ class Model:
         self.freq = {}
         self.last = {}
         self.epoch = 0
-        self.spill = {}   # key -> tuple, insertion-ordered (python dicts keep order)
+        # host tier (include/meepo.h "Host tier"): a ring of T slabs, the a-th append goes to slab a mod T
         self.spill_tuples = spill_tuples
+        self.ring = [None] * spill_tuples  # slab -> (key, tuple) or None
+        self.spill = {}                    # key -> slab
+        self.head = 0
+        self.promotions = 0
+        self.tier_hits = 0
         self.dirty = set()  # include/meepo.h "Incremental export"
 
     # storage rounding
@@ -91,28 +96,53 @@ class Model:
     def valid(k):
         return k < capi.KEY_RESERVED
 
+    def _tier_append(self, key, tup):
+        d = self.head % self.spill_tuples
+        if self.ring[d] is not None:        # the oldest slab is overwritten: its tuple is gone
+            del self.spill[self.ring[d][0]]
+        if key in self.spill:               # a newer copy replaces the older one, whose slab stays empty
+            self.ring[self.spill[key]] = None
+        self.ring[d] = (key, tup)
+        self.spill[key] = d
+        self.head += 1
+
+    def _tier_take(self, key):
+        d = self.spill.pop(key)
+        tup = self.ring[d][1]
+        self.ring[d] = None
+        return tup
+
     def _probe(self, keys, insert):
         self.epoch += 1
         n = len(keys)
         rows = np.zeros((n, self.dim), dtype=F)
         st = np.zeros(n, dtype=np.uint8)
-        present_at_start = set(self.rows.keys())
+        present_at_start = set(self.rows.keys()) | set(self.spill.keys())
         for i, k in enumerate(int(x) for x in keys):
             if not self.valid(k):
                 st[i] = capi.KEY_INVALID
                 continue
             if k not in self.rows:
                 if not insert:
-                    st[i] = capi.KEY_MISS
+                    if k in self.spill:  # served from the tier, not promoted, scores untouched
+                        st[i] = capi.KEY_FOUND
+                        rows[i] = self.ring[self.spill[k]][1][0]
+                        self.tier_hits += 1
+                    else:
+                        st[i] = capi.KEY_MISS
                     continue
                 if len(self.rows) >= self.capacity:
                     st[i] = capi.KEY_FULL
                     continue
-                self.rows[k] = self._store(init_row(k, self.seed, self.dim, self.init_scale))
-                self.state[k] = self._new_state()
-                self.step[k] = 0
-                self.freq[k] = 0
-                self.last[k] = 0
+                if k in self.spill:      # promotion
+                    self.rows[k], self.state[k], self.step[k], self.freq[k], self.last[k] = self._tier_take(k)
+                    self.promotions += 1
+                else:
+                    self.rows[k] = self._store(init_row(k, self.seed, self.dim, self.init_scale))
+                    self.state[k] = self._new_state()
+                    self.step[k] = 0
+                    self.freq[k] = 0
+                    self.last[k] = 0
                 self.dirty.add(k)
             st[i] = capi.KEY_FOUND if k in present_at_start else capi.KEY_INSERTED
             rows[i] = self.rows[k]
@@ -181,10 +211,7 @@ class Model:
         victims = sorted(self.rows.keys(), key=lambda key: (score[key], key))[:k]
         for key in victims:
             if self.spill_tuples:
-                self.spill.pop(key, None)
-                while len(self.spill) >= self.spill_tuples:
-                    self.spill.pop(next(iter(self.spill)))
-                self.spill[key] = (self.rows[key], self.state[key], self.step[key], self.freq[key], self.last[key])
+                self._tier_append(key, (self.rows[key], self.state[key], self.step[key], self.freq[key], self.last[key]))
             for d in (self.rows, self.state, self.step, self.freq, self.last):
                 del d[key]
             self.dirty.discard(key)
@@ -192,19 +219,25 @@ class Model:
 
     def readmit(self, keys):
         st = np.zeros(len(keys), dtype=np.uint8)
+        restored = set()
         for i, k in enumerate(int(x) for x in keys):
             if not self.valid(k):
                 st[i] = capi.KEY_INVALID
+            elif k in restored:
+                st[i] = capi.KEY_INSERTED  # every duplicate of a restored key
             elif k in self.rows:
                 st[i] = capi.KEY_FOUND
-                self.spill.pop(k, None)
+                if k in self.spill:
+                    self._tier_take(k)
             elif k not in self.spill:
                 st[i] = capi.KEY_MISS
             elif len(self.rows) >= self.capacity:
                 st[i] = capi.KEY_FULL
             else:
-                self.rows[k], self.state[k], self.step[k], self.freq[k], self.last[k] = self.spill.pop(k)
+                self.rows[k], self.state[k], self.step[k], self.freq[k], self.last[k] = self._tier_take(k)
                 self.dirty.add(k)
+                self.promotions += 1
+                restored.add(k)
                 st[i] = capi.KEY_INSERTED
         return st
 

@@ -178,6 +178,6 @@ def test_c_example_runs_on_the_gpu(tmp_path):
                            f"-Wl,-rpath,{lib_dir}", "-o", str(exe)])
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "backend cuda-sm_100a, ABI 2" in r.stdout
+    assert f"backend cuda-sm_100a, ABI {capi.ABI_VERSION}" in r.stdout
     # 50000 distinct keys inserted, evicted down to 2% of 2^20 slots (rounded to buckets), 1000 probed for re-admission
     assert "size " in r.stdout and "in the spill tier" in r.stdout

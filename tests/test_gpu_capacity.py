@@ -98,7 +98,7 @@ def test_evict_spill_readmit_parity(oracle_lib, cuda_lib, policy, dtype, optimiz
         assert ng == no and ng > 0
         assert_tables_equal(g, o)
         gs, os_ = g.stats(), o.stats()
-        for k in ("size", "evictions", "spill_keys", "spill_bytes"):
+        for k in ("size", "evictions", "spill_keys", "spill_bytes", "promotions", "tier_hits", "hits", "inserts"):
             assert gs[k] == os_[k], k
         rng = np.random.default_rng(int(target * 100))
         probe_keys = make_keys(rng, 1500, 6000, dup_frac=0.2)
@@ -109,6 +109,94 @@ def test_evict_spill_readmit_parity(oracle_lib, cuda_lib, policy, dtype, optimiz
         run_stream((g, o), dtype, dim, 6, steps=2, n=2500, universe=6000)
         assert_tables_equal(g, o)
     assert g.evict(policy, 1.0) == 0
+
+
+@pytest.mark.parametrize("dtype,dim,optimizer", [("f32", 128, "adagrad"), ("bf16", 128, "adam"), ("bf16", 24 * 8, "sgd"),
+                                                 ("f32", 8, "adagrad_rowwise")])
+def test_host_tier_is_a_second_level(oracle_lib, cuda_lib, dtype, dim, optimizer):
+    """include/meepo.h "Host tier" (SURVEY 8f-1): universe 4x the HBM capacity, a ring that holds the rest. No
+    trained row is ever lost: find_or_insert promotes (device and chunked host verb), lookup reads through, and
+    statuses / rows equal those of a table that is large enough never to evict. Bit-exact against the oracle."""
+    from gpu_util import gpu_apply, gpu_foi
+
+    cap, universe = 4096, 16000
+    probe = Table(lib=oracle_lib, **table_kwargs(dim=dim, capacity=64, dtype=dtype, optimizer=optimizer))
+    tuple_bytes = 24 + probe.row_bytes + probe.state_bytes
+    kw = table_kwargs(dim=dim, capacity=cap, dtype=dtype, optimizer=optimizer, track_scores=True)
+    g = Table(lib=cuda_lib, host_spill_bytes=20000 * tuple_bytes, **kw)
+    o = Table(lib=oracle_lib, host_spill_bytes=20000 * tuple_bytes, **kw)
+    big = Table(lib=cuda_lib, **dict(kw, capacity=4 * universe))  # never evicts: ground truth of the values
+    rng = np.random.default_rng(41)
+    for step in range(24):
+        keys = make_keys(rng, 1200, universe, dup_frac=0.3)
+        if step % 3 == 2:
+            r, s = g.find_or_insert(keys)  # numpy in: the chunked host verb
+        else:
+            r, s = gpu_foi(g, keys, dtype)
+        orr, os_ = o.find_or_insert(keys)
+        br, bs = gpu_foi(big, keys, dtype)
+        np.testing.assert_array_equal(s, os_, err_msg=f"step {step}")
+        np.testing.assert_array_equal(r, orr, err_msg=f"step {step}")
+        np.testing.assert_array_equal(s, bs, err_msg=f"step {step}: a key came back re-initialised")
+        np.testing.assert_array_equal(r, br, err_msg=f"step {step}: a trained row was lost")
+        gr = grads_for(dtype, rng.normal(0, 0.1, size=(keys.size, dim)))
+        gpu_apply(g, keys, gr, dtype), o.apply_gradients(keys, gr), gpu_apply(big, keys, gr, dtype)
+        lk = make_keys(rng, 700, universe)
+        r, s = gpu_foi(g, lk, dtype, insert=False)
+        orr, os_ = o.lookup(lk)
+        br, bs = gpu_foi(big, lk, dtype, insert=False)
+        np.testing.assert_array_equal(s, os_)
+        np.testing.assert_array_equal(r, orr)
+        np.testing.assert_array_equal(s, bs)
+        np.testing.assert_array_equal(r, br)
+        if o.stats()["size"] > 0.7 * cap:
+            policy = "lru" if step % 2 else "lfu"
+            assert g.evict(policy, 0.35) == o.evict(policy, 0.35)
+        if step % 6 == 5:
+            assert_tables_equal(g, o)
+            gs, os_ = g.stats(), o.stats()
+            for k in ("size", "inserts", "hits", "misses", "evictions", "spill_keys", "promotions", "tier_hits"):
+                assert gs[k] == os_[k], (step, k)
+    assert o.stats()["promotions"] > 1000 and o.stats()["tier_hits"] > 500
+
+
+def test_host_tier_ring_wraps_and_index_rebuilds(oracle_lib, cuda_lib):
+    """A ring far smaller than what is evicted: it wraps many times (slabs overwritten, tombstones in the device
+    index, index rebuilds), and a promotion into a full table reports FULL and leaves the tuple where it is."""
+    from gpu_util import gpu_apply, gpu_foi
+
+    dtype, dim = "f32", 8
+    kw = table_kwargs(dim=dim, capacity=2048, dtype=dtype, optimizer="sgd", track_scores=True,
+                      host_spill_bytes=300 * (24 + 32))
+    g, o = Table(lib=cuda_lib, **kw), Table(lib=oracle_lib, **kw)
+    rng = np.random.default_rng(43)
+    for step in range(60):
+        keys = make_keys(rng, 500, 5000, dup_frac=0.2)
+        r, s = gpu_foi(g, keys, dtype)
+        orr, os_ = o.find_or_insert(keys)
+        np.testing.assert_array_equal(s, os_, err_msg=f"step {step}")
+        np.testing.assert_array_equal(r, orr, err_msg=f"step {step}")
+        gr = grads_for(dtype, rng.normal(0, 0.1, size=(keys.size, dim)))
+        gpu_apply(g, keys, gr, dtype), o.apply_gradients(keys, gr)
+        if o.stats()["size"] > 0.6 * 2048:
+            assert g.evict("lfu", 0.5) == o.evict("lfu", 0.5)
+            assert g.stats()["spill_keys"] == o.stats()["spill_keys"]
+    assert_tables_equal(g, o)
+    # to the brim, then ask for tier keys
+    while o.stats()["size"] < o.capacity:
+        fill = make_keys(rng, 600, 10**7, dup_frac=0.0, invalid=False)
+        gpu_foi(g, fill, dtype), o.find_or_insert(fill)
+    assert g.stats()["size"] == g.capacity == o.stats()["size"]
+    probe_keys = make_keys(rng, 3000, 5000, dup_frac=0.0, invalid=False)
+    r, s = gpu_foi(g, probe_keys, dtype)
+    orr, os_ = o.find_or_insert(probe_keys)
+    np.testing.assert_array_equal(s, os_)
+    np.testing.assert_array_equal(r, orr)
+    assert (s == capi.KEY_FULL).any() and g.stats()["spill_keys"] == o.stats()["spill_keys"] > 0
+    r, s = gpu_foi(g, probe_keys, dtype, insert=False)
+    orr, os_ = o.lookup(probe_keys)
+    np.testing.assert_array_equal(s, os_)
+    np.testing.assert_array_equal(r, orr)
 
 
 def test_evict_high_load_chains(oracle_lib, cuda_lib):

@@ -95,7 +95,8 @@ def test_random_verb_sequences(oracle_lib, cuda_lib, tmp_path, seed, dtype, dim,
         if step % 10 == 9:
             assert_tables_equal(g, o)
             gs, os_ = g.stats(), o.stats()
-            for k in ("size", "inserts", "hits", "misses", "evictions", "updates", "grad_dropped", "spill_keys"):
+            for k in ("size", "inserts", "hits", "misses", "evictions", "updates", "grad_dropped", "spill_keys",
+                      "promotions", "tier_hits"):
                 assert gs[k] == os_[k], (step, k)
     assert_tables_equal(g, o)
     g.close(), o.close()

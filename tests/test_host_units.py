@@ -5,15 +5,6 @@ import subprocess
 from conftest import ROOT
 
 
-def test_spill_index_against_unordered_map(tmp_path):
-    exe = tmp_path / "spill_index_test"
-    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
-    subprocess.check_call(["/usr/bin/g++", "-O1", "-std=c++17", "-pthread", "-I", cuda_inc, "-o", str(exe),
-                           os.path.join(ROOT, "tests", "cpp", "spill_index_test.cc")])
-    out = subprocess.check_output([str(exe)], text=True)
-    assert "spill index ok" in out
-
-
 def test_header_is_valid_c_and_cxx(tmp_path):
     """include/meepo.h is the drop-in boundary: it must compile as plain C99 and as C++ on its own."""
     src_c = tmp_path / "use.c"

@@ -107,6 +107,12 @@ def test_full_table_and_sentinels(oracle_lib):
     assert t.stats()["epoch"] == m.epoch
 
 
+def check_tier_equal(t, m):
+    s = t.stats()
+    assert s["spill_keys"] == len(m.spill)
+    assert s["promotions"] == m.promotions and s["tier_hits"] == m.tier_hits
+
+
 @pytest.mark.parametrize("policy", ["lfu", "lru"])
 def test_evict_spill_readmit(oracle_lib, policy):
     rng = np.random.default_rng(11)
@@ -119,13 +125,87 @@ def test_evict_spill_readmit(oracle_lib, policy):
         t.apply_gradients(keys, g), m.apply_gradients(keys, rows_as_f32(g, "bf16"))
     pol = capi.LFU if policy == "lfu" else capi.LRU
     n = t.evict(policy, 0.5)
-    assert n == m.evict(pol, 0.5) and n > 40  # more victims than spill room: FIFO drop exercised
+    assert n == m.evict(pol, 0.5) and n > 40  # more victims than ring slabs: the ring wraps inside one call
     check_table_equal(t, m, "bf16")
-    assert t.stats()["spill_keys"] == len(m.spill)
-    probe = np.array(list(m.spill.keys())[:10] + [1, 2, capi.KEY_EMPTY] + list(m.rows.keys())[:3], dtype=np.uint64)
+    check_tier_equal(t, m)
+    tk = list(m.spill.keys())
+    probe = np.array(tk[:10] + [1, 2, capi.KEY_EMPTY] + list(m.rows.keys())[:3] + tk[:2], dtype=np.uint64)
     np.testing.assert_array_equal(t.spill_readmit(probe), m.readmit(probe))
     check_table_equal(t, m, "bf16")
+    check_tier_equal(t, m)
     assert t.evict(policy, 1.0) == 0
+
+
+@pytest.mark.parametrize("dtype,optimizer", [("f32", "adagrad"), ("bf16", "adam"), ("f32", "adagrad_rowwise")])
+def test_host_tier_is_a_second_level(oracle_lib, dtype, optimizer):
+    """include/meepo.h "Host tier": with a universe 4x the capacity and a ring large enough to hold what HBM
+    cannot, no trained row is ever lost: find_or_insert promotes, lookup reads through, and every key's row /
+    state equals that of a model table that never evicts."""
+    rng = np.random.default_rng(29)
+    cap, universe, dim = 252, 1000, 8
+    kw = dict(dim=dim, capacity=cap, dtype=dtype, optimizer=optimizer, track_scores=True)
+    t, m = make_pair(oracle_lib, host_spill_bytes=2000 * (24 + 32 + 64), **kw)
+    _, big = make_pair(oracle_lib, **dict(kw, capacity=4 * universe))  # never evicts: the ground truth of the VALUES
+    for step in range(30):
+        keys = make_keys(rng, 60, universe, dup_frac=0.3)
+        r, s = t.find_or_insert(keys)
+        mr, ms = m.find_or_insert(keys)
+        br, bs = big.find_or_insert(keys)
+        np.testing.assert_array_equal(s, ms)
+        np.testing.assert_array_equal(rows_as_f32(r, dtype), mr)
+        np.testing.assert_array_equal(s, bs)   # FOUND / INSERTED as if nothing had ever been evicted
+        np.testing.assert_array_equal(mr, br)  # ... and the rows too: promotion restores the trained row
+        g = grads_for(dtype, rng.normal(0, 0.1, size=(keys.size, dim)))
+        t.apply_gradients(keys, g), m.apply_gradients(keys, rows_as_f32(g, dtype)), big.apply_gradients(keys, rows_as_f32(g, dtype))
+        lk = make_keys(rng, 40, universe)
+        r, s = t.lookup(lk)
+        mr, ms = m.lookup(lk)
+        br, bs = big.lookup(lk)
+        np.testing.assert_array_equal(s, ms)
+        np.testing.assert_array_equal(rows_as_f32(r, dtype), mr)
+        np.testing.assert_array_equal(s, bs)
+        np.testing.assert_array_equal(mr, br)
+        if t.stats()["size"] > 0.8 * cap:
+            assert t.evict("lru", 0.4) == m.evict(capi.LRU, 0.4)
+        check_table_equal(t, m, dtype)
+        check_tier_equal(t, m)
+    assert m.promotions > 50 and m.tier_hits > 50
+
+
+def test_host_tier_ring_wraps_and_full_table(oracle_lib):
+    """A ring smaller than what is evicted drops the oldest slabs; promotion into a full table reports FULL and
+    leaves the tuple in the tier."""
+    rng = np.random.default_rng(37)
+    t, m = make_pair(oracle_lib, dim=4, capacity=70, dtype="f32", optimizer="sgd", track_scores=True,
+                     host_spill_bytes=25 * (24 + 16))
+    for step in range(12):
+        keys = make_keys(rng, 50, 160, dup_frac=0.2)
+        r, s = t.find_or_insert(keys)
+        mr, ms = m.find_or_insert(keys)
+        np.testing.assert_array_equal(s, ms)
+        np.testing.assert_array_equal(r, mr)
+        g = rng.normal(0, 0.1, size=(keys.size, 4)).astype(np.float32)
+        t.apply_gradients(keys, g), m.apply_gradients(keys, g)
+        if step % 3 == 2:
+            assert t.evict("lfu", 0.5) == m.evict(capi.LFU, 0.5)
+        check_table_equal(t, m, "f32")
+        check_tier_equal(t, m)
+    # fill the table to the brim, then ask for tier keys: FULL, tuples stay
+    fill = make_keys(rng, 400, 100000, dup_frac=0.0, invalid=False)
+    t.find_or_insert(fill), m.find_or_insert(fill)
+    assert t.stats()["size"] == 70
+    tk = np.array(list(m.spill.keys())[:8], dtype=np.uint64)
+    assert tk.size
+    r, s = t.find_or_insert(tk)
+    mr, ms = m.find_or_insert(tk)
+    np.testing.assert_array_equal(s, ms)
+    assert (s == capi.KEY_FULL).all() and (r == 0).all()
+    check_tier_equal(t, m)
+    r, s = t.lookup(tk)  # still readable through the tier
+    mr, ms = m.lookup(tk)
+    np.testing.assert_array_equal(s, ms)
+    np.testing.assert_array_equal(r, mr)
+    assert (s == capi.KEY_FOUND).all()
 
 
 def test_export_import_roundtrip(oracle_lib, tmp_path):
@@ -192,12 +272,13 @@ def test_bad_arguments(oracle_lib):
 
 
 @settings(max_examples=40, deadline=None)
-@given(st.lists(st.tuples(st.sampled_from(["foi", "lookup", "grad", "evict"]),
+@given(st.lists(st.tuples(st.sampled_from(["foi", "lookup", "grad", "evict", "readmit"]),
                           st.lists(st.integers(0, 40), min_size=0, max_size=60)), min_size=1, max_size=8),
        st.sampled_from(["f32", "bf16"]), st.sampled_from(["sgd", "adagrad", "adam", "adagrad_rowwise"]))
 def test_hypothesis_streams(oracle_lib, ops, dtype, optimizer):
     special = {38: capi.KEY_EMPTY, 39: capi.KEY_RESERVED, 40: capi.KEY_RESERVED - 1, 0: 0}
-    t, m = make_pair(oracle_lib, dim=8, capacity=32, dtype=dtype, optimizer=optimizer, track_scores=True)
+    t, m = make_pair(oracle_lib, dim=8, capacity=32, dtype=dtype, optimizer=optimizer, track_scores=True,
+                     host_spill_bytes=1000)  # a ring of 7..17 slabs: wraps, promotes, reads through
     rng = np.random.default_rng(0)
     for op, ids in ops:
         keys = np.array([special.get(i, i * 0x9E3779B97F4A7C15 & 0xFFFFFFFFFFFFFFFF) for i in ids], dtype=np.uint64)
@@ -215,8 +296,11 @@ def test_hypothesis_streams(oracle_lib, ops, dtype, optimizer):
             g = grads_for(dtype, rng.normal(0, 0.5, size=(keys.size, 8)))
             t.apply_gradients(keys, g)
             m.apply_gradients(keys, rows_as_f32(g, dtype))
+        elif op == "readmit":
+            np.testing.assert_array_equal(t.spill_readmit(keys), m.readmit(keys))
         else:
             assert t.evict("lfu", 0.5) == m.evict(capi.LFU, 0.5)
+        check_tier_equal(t, m)
     check_table_equal(t, m, dtype)
 
 
