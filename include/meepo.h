@@ -110,6 +110,21 @@
  *           (a training step calls find_or_insert on its keys first): gradients
  *           of keys that are only there are dropped and counted in grad_dropped.
  *           meepo_spill_readmit promotes keys ahead of their next use.
+ * Pooling   The *_pooled verbs take the batch as n_bags BAGS: bag b is keys[offsets[b]
+ *           .. offsets[b+1]) with offsets[0] = 0 <= ... <= offsets[n_bags] = n
+ *           (uint32). Towards the table they are exactly find_or_insert / lookup /
+ *           apply_gradients on `keys` (insertion, per-key status, scores, host
+ *           tier); what changes is the row traffic: the forward verbs return one
+ *           pooled row per bag instead of one row per key,
+ *             acc = +0.0f; for the keys of the bag in order: acc = acc + w(key)
+ *           per column in fp32 (w = the key's row widened to fp32; a key without a
+ *           row — MISS, FULL, INVALID — contributes nothing), MEEPO_POOL_MEAN then
+ *           divides by the fp32 bag length offsets[b+1] - offsets[b] (an empty bag
+ *           yields zeros), and the result is stored in the table dtype (bf16: RNE).
+ *           The backward verb takes one gradient row per bag: the gradient of
+ *           every key occurrence of bag b is bag_grads[b] (SUM) or bag_grads[b]
+ *           widened, divided by the fp32 bag length and rounded to the table dtype
+ *           (MEAN); "Update" then applies with occurrences in batch order.
  * Sharding  owner(key, G) = umulhi64(mix64(key ^ 0xD6E8FEB86659FD93), G).
  */
 #ifndef MEEPO_H_
@@ -151,6 +166,7 @@ typedef enum {
 typedef enum { MEEPO_F32 = 0, MEEPO_BF16 = 1 } meepo_dtype;
 typedef enum { MEEPO_SGD = 0, MEEPO_ADAGRAD = 1, MEEPO_ADAM = 2, MEEPO_ADAGRAD_ROWWISE = 3 } meepo_opt;
 typedef enum { MEEPO_LRU = 0, MEEPO_LFU = 1 } meepo_policy;
+typedef enum { MEEPO_POOL_SUM = 0, MEEPO_POOL_MEAN = 1 } meepo_pool;
 
 /* per-key status bytes */
 enum {
@@ -190,7 +206,7 @@ typedef struct {
   uint64_t spill_keys;   /* tuples currently held in the host tier */
   uint64_t spill_bytes;  /* bytes they occupy (spill_keys * (24 + row_bytes + state_bytes)) */
   uint64_t epoch;        /* batch epoch */
-  uint64_t overflow_buckets; /* buckets whose overflow flag is set */
+  uint64_t overflow_buckets; /* home buckets with at least one key displaced into a later bucket */
   uint64_t row_bytes, state_bytes; /* per slot */
   uint64_t peer_keys_received;  /* sharded forward verbs: (sender, key) entries this owner served */
   uint64_t peer_grads_received; /* sharded apply_gradients: (sender, key) gradient rows received */
@@ -235,6 +251,23 @@ MEEPO_API meepo_status meepo_lookup(meepo_table* t, const uint64_t* keys, uint64
 /* grads: n*dim elements of the table dtype. */
 MEEPO_API meepo_status meepo_apply_gradients(meepo_table* t, const uint64_t* keys,
                                              const void* grads, uint64_t n, void* stream);
+
+/* --- pooled (bag) forms: lookup fused with the sum / mean pooling that follows it
+ *     in CTR models; see "Pooling" above. Stream-ordered, device pointers.
+ *     keys: n; offsets: n_bags + 1 uint32; pooled_out / bag_grads: n_bags * dim
+ *     elements of the table dtype; status_out: n bytes (may be NULL). The per-key
+ *     row ([n][dim], written and read back once each by the unfused sequence) never
+ *     exists; the backward verb reads bag_grads through the bag index of every
+ *     occurrence instead of an expanded [n][dim] gradient. */
+MEEPO_API meepo_status meepo_find_or_insert_pooled(meepo_table* t, const uint64_t* keys, uint64_t n,
+                                                   const uint32_t* offsets, uint64_t n_bags, int32_t pool,
+                                                   void* pooled_out, uint8_t* status_out, void* stream);
+MEEPO_API meepo_status meepo_lookup_pooled(meepo_table* t, const uint64_t* keys, uint64_t n,
+                                           const uint32_t* offsets, uint64_t n_bags, int32_t pool,
+                                           void* pooled_out, uint8_t* found_out, void* stream);
+MEEPO_API meepo_status meepo_apply_gradients_pooled(meepo_table* t, const uint64_t* keys, uint64_t n,
+                                                    const uint32_t* offsets, uint64_t n_bags, int32_t pool,
+                                                    const void* bag_grads, void* stream);
 
 /* --- host-buffer front ends (pageable or pinned host pointers) ----------- *
  * Same semantics; the library stages through its own device buffers and

@@ -22,6 +22,7 @@ OK, EINVAL, ENOMEM, ECUDA, ENCCL, EIO = range(6)
 F32, BF16 = 0, 1
 SGD, ADAGRAD, ADAM, ADAGRAD_ROWWISE = 0, 1, 2, 3
 LRU, LFU = 0, 1
+POOL_SUM, POOL_MEAN = 0, 1
 KEY_MISS, KEY_FOUND, KEY_INSERTED, KEY_FULL, KEY_INVALID = range(5)
 FLAG_TRACK_SCORES = 1
 FLAG_TRACK_DIRTY = 2
@@ -100,6 +101,9 @@ SIGNATURES = {
     "meepo_find_or_insert": (C.c_int, [_P, _P, _U64, _P, _P, _P]),
     "meepo_lookup": (C.c_int, [_P, _P, _U64, _P, _P, _P]),
     "meepo_apply_gradients": (C.c_int, [_P, _P, _P, _U64, _P]),
+    "meepo_find_or_insert_pooled": (C.c_int, [_P, _P, _U64, _P, _U64, C.c_int32, _P, _P, _P]),
+    "meepo_lookup_pooled": (C.c_int, [_P, _P, _U64, _P, _U64, C.c_int32, _P, _P, _P]),
+    "meepo_apply_gradients_pooled": (C.c_int, [_P, _P, _U64, _P, _U64, C.c_int32, _P, _P]),
     "meepo_find_or_insert_host": (C.c_int, [_P, _P, _U64, _P, _P]),
     "meepo_lookup_host": (C.c_int, [_P, _P, _U64, _P, _P]),
     "meepo_apply_gradients_host": (C.c_int, [_P, _P, _P, _U64]),

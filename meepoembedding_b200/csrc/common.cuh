@@ -7,9 +7,11 @@
 //                   the key's hash (1..255). The probe loads these 16 bytes, SIMD-compares all tags
 //                   in registers and then touches only the 8-byte key(s) whose tag matched — which
 //                   sit in the SAME line, i.e. an L2 hit, not a second HBM access.
-//   bytes  14..15   per-bucket metadata: bit 0 = overflow (set once any insertion has skipped past
-//                   this bucket because it was full; lookups follow the chain only while it is set,
-//                   so eviction can free slots without tombstones)
+//   bytes  14..15   per-bucket metadata: the largest DISPLACEMENT (in buckets) of any key whose home
+//                   bucket this is (0xFFFF: unknown, walk everything). A probe for a key with home h
+//                   visits buckets h .. h + disp(h) and stops: a miss costs 1 + disp(h) lines — at 90%
+//                   load 90% of the homes have disp 0 — instead of a walk to the end of the run of
+//                   full buckets, and eviction frees slots with no tombstones (disp is recomputed)
 //   bytes 16..127   14 keys (u64, EMPTY = ~0), claimed with one 64-bit CAS
 // Slot s = 14*bucket + index addresses the other arrays:
 //   rows     16-byte chunks [slots * cpr]     value arena
@@ -35,7 +37,7 @@ enum Counter : int {
 
 struct __align__(128) BucketLine {
   uint8_t tag[kBucket];
-  uint16_t meta;  // bit 0: overflow
+  uint16_t meta;  // largest displacement of a key whose home this bucket is
   uint64_t key[kBucket];
 };
 static_assert(sizeof(BucketLine) == 128, "a bucket is one 128-byte line");
@@ -155,23 +157,26 @@ __device__ __forceinline__ uint32_t match_mask(const uint4& h, uint32_t tag) {
   return bytes_eq4(h.x, pat) | (bytes_eq4(h.y, pat) << 4) | (bytes_eq4(h.z, pat) << 8) |
          ((bytes_eq4(h.w, pat) & 3u) << 12);
 }
-__device__ __forceinline__ bool overflowed(const uint4& h) { return (h.w >> 16) & 1u; }
+constexpr uint32_t kDispUnknown = 0xFFFFu;
+__device__ __forceinline__ uint32_t home_disp(const uint4& h) { return h.w >> 16; }
 
-// Slot of `key` or kNil, starting at bucket b with the header already in registers.
+// Slot of `key` or kNil, starting at its home bucket b with the header already in registers: the buckets
+// b .. b + disp(b).
 template <int LD, typename TB>
 __device__ __forceinline__ uint32_t probe_from(const TB& t, uint64_t key, uint32_t tag, uint32_t b, uint4 hdr) {
-  for (uint32_t p = 0; p < t.num_buckets; ++p) {
+  const uint32_t disp = home_disp(hdr);
+  const uint32_t last = disp == kDispUnknown ? t.num_buckets - 1 : min(disp, t.num_buckets - 1);
+  for (uint32_t d = 0;; ++d) {
     uint32_t m = match_mask(hdr, tag);
     while (m) {
       const uint32_t i = __ffs(m) - 1;
       if (load_key<LD>(t, b, i) == key) return b * kBucket + i;
       m &= m - 1;
     }
-    if (!overflowed(hdr)) return kNil;
+    if (d >= last) return kNil;
     b = (b + 1 == t.num_buckets) ? 0 : b + 1;
     hdr = load_header<LD>(t, b);
   }
-  return kNil;
 }
 // Probe without insertion. One HBM line per bucket visited.
 template <int LD = kCoherent, typename TB>
@@ -179,6 +184,20 @@ __device__ __forceinline__ uint32_t probe_find(const TB& t, uint64_t key) {
   const uint64_t h = mix64(key);
   const uint32_t b = bucket_of(h, t.num_buckets);
   return probe_from<LD>(t, key, digest_of(h), b, load_header<LD>(t, b));
+}
+
+// disp(home) = max(disp(home), d); returns true if disp(home) was 0 before (the caller counts such homes). The
+// metadata is the high half of a 32-bit word whose low half holds tags 12 and 13, which no kernel that raises
+// displacements writes (tags are published by their own kernel): with the low half copied from the current
+// value, atomicMax orders the words by displacement alone.
+template <typename TB>
+__device__ __forceinline__ bool raise_disp(const TB& t, uint32_t home, uint32_t d) {
+  uint32_t* w = reinterpret_cast<uint32_t*>(&t.buckets[home]) + 3;
+  d = min(d, kDispUnknown);
+  const uint32_t cur = *reinterpret_cast<volatile uint32_t*>(w);
+  if ((cur >> 16) >= d) return false;
+  const uint32_t old = atomicMax(w, (cur & 0xFFFFu) | (d << 16));
+  return (old >> 16) == 0;
 }
 
 struct Probe {
@@ -202,8 +221,9 @@ __device__ __forceinline__ Probe probe_find_or_insert(const TB& t, uint64_t key)
     return r;
   }
   const uint64_t h = mix64(key);
-  uint32_t b = bucket_of(h, t.num_buckets);
-  for (uint32_t p = 0; p < t.num_buckets; ++p) {
+  const uint32_t home = bucket_of(h, t.num_buckets);
+  uint32_t b = home;
+  for (uint32_t d = 0; d < t.num_buckets; ++d) {
     const uint4 hdr = load_header<kCoherent>(t, b);
     uint32_t free_m = match_mask(hdr, 0);
     while (free_m) {
@@ -214,13 +234,10 @@ __device__ __forceinline__ Probe probe_find_or_insert(const TB& t, uint64_t key)
         r.slot = b * kBucket + i;
         r.status = MEEPO_KEY_INSERTED;
         r.winner = (old == MEEPO_KEY_EMPTY);
+        if (d && r.winner && raise_disp(t, home, d)) atomicAdd(t.counters + C_OVERFLOW, 1ull);
         return r;
       }
       free_m &= free_m - 1;
-    }
-    if (!overflowed(hdr)) {  // tags 12,13 and the metadata share one 32-bit word of the header
-      uint32_t* w = reinterpret_cast<uint32_t*>(&t.buckets[b]) + 3;
-      if (!(atomicOr(w, 1u << 16) & (1u << 16))) atomicAdd(t.counters + C_OVERFLOW, 1ull);
     }
     b = (b + 1 == t.num_buckets) ? 0 : b + 1;
   }

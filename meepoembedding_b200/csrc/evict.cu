@@ -33,7 +33,9 @@ __device__ __forceinline__ uint32_t score_of(const TableView& t, uint32_t s, int
 struct SelState {  // device-side state of the selection
   uint32_t prefix, mask;           // decided bytes of the score threshold T
   uint32_t nA, nB, nV, bad;        // list lengths; victims taken from B; a histogram that did not add up
-  uint32_t ormask, pad;            // OR of every live score (first pass): a byte that is 0 everywhere needs no pass
+  uint32_t nC, c_over;             // list C = the candidates whose top key byte is the threshold's; it overflowed
+  uint32_t ormask, done;           // OR of every live score (first pass): a byte that is 0 everywhere needs no pass;
+                                   // done: the first pass already found T (it lies below 255)
   unsigned long long remaining;    // victims still to be found among the undecided slots
   unsigned long long ties;         // slots in the bin the threshold fell into
   unsigned long long kprefix, kmask;  // decided bytes of the key threshold
@@ -46,90 +48,131 @@ __global__ void sel_init_kernel(SelState* sel, unsigned long long k) {
 }
 
 // Histogram of byte `shift/8` of the score over the live slots whose higher score bytes equal the prefix. The
-// first pass (shift 24) also ORs all live scores together; a later pass whose byte is zero in every score has
-// nothing to count (LFU frequencies and LRU epochs are small numbers: two or three of the four passes end here).
+// first pass (shift 24) also counts min(score, 255) into a second histogram and ORs all live scores together:
+// when the threshold lies below 255 — the usual LFU case, the victims are the keys seen once or twice — that one
+// pass decides it and the other three return at once; otherwise a pass whose byte is zero in every score has
+// nothing to count either (LRU epochs are small numbers).
 __global__ void __launch_bounds__(256) score_hist_kernel(TableView t, int policy, SelState* __restrict__ sel,
-                                                         int shift, unsigned long long* __restrict__ hist) {
-  __shared__ uint32_t sh[256];
+                                                         int shift, unsigned long long* __restrict__ hist,
+                                                         unsigned long long* __restrict__ hist_low) {
+  __shared__ uint32_t sh[256], sl[256];
   const uint32_t prefix = sel->prefix, mask = sel->mask;
-  if (shift != 24 && ((sel->ormask >> shift) & 0xFFu) == 0) return;
+  const bool first = shift == 24;
+  if (!first && (sel->done || ((sel->ormask >> shift) & 0xFFu) == 0)) return;
   sh[threadIdx.x] = 0;
+  sl[threadIdx.x] = 0;
   __syncthreads();
   uint32_t acc_or = 0;
   const uint32_t lane = threadIdx.x & 31u;
   for (uint32_t s0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; s0 < t.slots; s0 += gridDim.x * blockDim.x) {
     const uint32_t s = s0 + lane;
     bool in = false;
-    uint32_t bin = 0;
+    uint32_t bin = 0, low = 0;
     if (s < t.slots && *key_ptr(t, s) != MEEPO_KEY_EMPTY) {
       const uint32_t sc = score_of(t, s, policy);
       acc_or |= sc;
       in = (sc & mask) == prefix;
       bin = (sc >> shift) & 0xFFu;
+      low = min(sc, 255u);
     }
     // scores cluster: most warps hold one bin only, and 32 shared-memory atomics on one address serialise
     const unsigned m = __ballot_sync(0xFFFFFFFFu, in);
     if (!m) continue;
-    const uint32_t b0 = __shfl_sync(0xFFFFFFFFu, bin, __ffs(m) - 1);
+    const int l0 = __ffs(m) - 1;
+    const uint32_t b0 = __shfl_sync(0xFFFFFFFFu, bin, l0);
     if (__all_sync(0xFFFFFFFFu, !in || bin == b0)) {
       if (lane == 0) atomicAdd(&sh[b0], (uint32_t)__popc(m));
     } else if (in) {
       atomicAdd(&sh[bin], 1u);
     }
+    if (first) {
+      const uint32_t w0 = __shfl_sync(0xFFFFFFFFu, low, l0);
+      if (__all_sync(0xFFFFFFFFu, !in || low == w0)) {
+        if (lane == 0) atomicAdd(&sl[w0], (uint32_t)__popc(m));
+      } else if (in) {
+        atomicAdd(&sl[low], 1u);
+      }
+    }
   }
   __syncthreads();
   if (sh[threadIdx.x]) atomicAdd(hist + threadIdx.x, (unsigned long long)sh[threadIdx.x]);
-  if (shift == 24) {
+  if (first) {
+    if (sl[threadIdx.x]) atomicAdd(hist_low + threadIdx.x, (unsigned long long)sl[threadIdx.x]);
     acc_or = __reduce_or_sync(0xFFFFFFFFu, acc_or);
     if (lane == 0 && acc_or) atomicOr(&sel->ormask, acc_or);
   }
 }
-// The same over the keys of list B (all of them have score == T) on byte `shift/8` of the key.
-__global__ void __launch_bounds__(256) key_hist_kernel(const uint64_t* __restrict__ bkey, const SelState* __restrict__ sel,
-                                                       int shift, unsigned long long* __restrict__ hist) {
+// The same over candidate keys (all of them have score == T) on byte `shift/8` of the key: list C (the candidates
+// that share the threshold's top byte, ~1/256 of list B), or list B itself if C overflowed its allotment.
+__global__ void __launch_bounds__(256) key_hist_kernel(const uint64_t* __restrict__ bkey, const uint64_t* __restrict__ ckey,
+                                                       const SelState* __restrict__ sel, int shift,
+                                                       unsigned long long* __restrict__ hist) {
   __shared__ uint32_t sh[256];
   sh[threadIdx.x] = 0;
   __syncthreads();
-  const uint32_t n = sel->nB;
+  const bool over = sel->c_over != 0;
+  const uint64_t* __restrict__ src = over ? bkey : ckey;
+  const uint32_t n = over ? sel->nB : sel->nC;
   const unsigned long long kprefix = sel->kprefix, kmask = sel->kmask;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const uint64_t key = bkey[i];
+    const uint64_t key = src[i];
     if ((key & kmask) == kprefix) atomicAdd(&sh[(uint32_t)(key >> shift) & 0xFFu], 1u);
   }
   __syncthreads();
   if (sh[threadIdx.x]) atomicAdd(hist + threadIdx.x, (unsigned long long)sh[threadIdx.x]);
 }
 // One radix-select step: the bin holding the `remaining`-th smallest undecided item becomes the next byte.
+// hist_low (first score step only): counts of min(score, 255); if the k-th smallest score is below 255 the
+// threshold is final.
 __global__ void __launch_bounds__(256) sel_step_kernel(SelState* sel, unsigned long long* __restrict__ hist, int shift,
-                                                       int key_pass) {
-  if (!key_pass && shift != 24 && ((sel->ormask >> shift) & 0xFFu) == 0) {  // the pass was skipped: byte = 0
-    if (threadIdx.x == 0) sel->mask |= 0xFFu << shift;
+                                                       int key_pass, unsigned long long* __restrict__ hist_low) {
+  if (!key_pass && shift != 24 && (sel->done || ((sel->ormask >> shift) & 0xFFu) == 0)) {  // the pass was skipped
+    if (threadIdx.x == 0 && !sel->done) sel->mask |= 0xFFu << shift;                       // ... its byte is 0
     return;
   }
   if (threadIdx.x == 0) {
     unsigned long long cum = 0, rem = sel->remaining;
     int b = 0;
-    for (; b < 256; b++) {
-      if (cum + hist[b] >= rem) break;
-      cum += hist[b];
+    bool decided = false;
+    if (hist_low) {
+      for (; b < 255; b++) {
+        if (cum + hist_low[b] >= rem) break;
+        cum += hist_low[b];
+      }
+      if (b < 255) {  // T = b exactly
+        sel->prefix = (uint32_t)b;
+        sel->mask = 0xFFFFFFFFu;
+        sel->remaining = rem - cum;
+        sel->ties = hist_low[b];
+        sel->done = 1;
+        decided = true;
+      }
     }
-    if (b == 256) {  // cannot happen while the table is not mutated underneath
-      b = 255;
-      cum -= hist[255];
-      sel->bad = 1;
-    }
-    sel->remaining = rem - cum;
-    sel->ties = hist[b];
-    if (key_pass) {
-      sel->kprefix |= (unsigned long long)b << shift;
-      sel->kmask |= 0xFFull << shift;
-    } else {
-      sel->prefix |= (uint32_t)b << shift;
-      sel->mask |= 0xFFu << shift;
+    if (!decided) {
+      cum = 0;
+      for (b = 0; b < 256; b++) {
+        if (cum + hist[b] >= rem) break;
+        cum += hist[b];
+      }
+      if (b == 256) {  // cannot happen while the table is not mutated underneath
+        b = 255;
+        cum -= hist[255];
+        sel->bad = 1;
+      }
+      sel->remaining = rem - cum;
+      sel->ties = hist[b];
+      if (key_pass) {
+        sel->kprefix |= (unsigned long long)b << shift;
+        sel->kmask |= 0xFFull << shift;
+      } else {
+        sel->prefix |= (uint32_t)b << shift;
+        sel->mask |= 0xFFu << shift;
+      }
     }
   }
   __syncthreads();
   hist[threadIdx.x] = 0;
+  if (hist_low) hist_low[threadIdx.x] = 0;
 }
 
 // CTA-wide reservation of list space. Every thread calls it with the warp ballots of its ITEMS items in up to two
@@ -174,9 +217,13 @@ __device__ __forceinline__ Reserve2 block_reserve2(const unsigned (&ma)[kSelItem
 }
 
 // Slots below the threshold -> list A (victims), slots at the threshold -> list B (candidates).
+// The histogram of the candidates' top key byte (the first tie-break pass) is taken on the way.
 __global__ void __launch_bounds__(256) split_kernel(TableView t, int policy, SelState* sel, uint64_t* __restrict__ akey,
                                                     uint32_t* __restrict__ aslot, uint32_t* __restrict__ ascore,
-                                                    uint64_t* __restrict__ bkey, uint32_t* __restrict__ bslot) {
+                                                    uint64_t* __restrict__ bkey, uint32_t* __restrict__ bslot,
+                                                    unsigned long long* __restrict__ hist) {
+  __shared__ uint32_t sh[256];
+  sh[threadIdx.x] = 0;
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t T = sel->prefix;
   const unsigned below = (1u << lane) - 1u;
@@ -211,9 +258,45 @@ __global__ void __launch_bounds__(256) split_kernel(TableView t, int policy, Sel
         const uint32_t p = r.b + __popc(mb[k] & below);
         bkey[p] = key[k];
         bslot[p] = s;
+        atomicAdd(&sh[(uint32_t)(key[k] >> 56)], 1u);
       }
       r.a += __popc(ma[k]);
       r.b += __popc(mb[k]);
+    }
+  }
+  __syncthreads();
+  if (sh[threadIdx.x]) atomicAdd(hist + threadIdx.x, (unsigned long long)sh[threadIdx.x]);
+}
+// List C: the candidates whose top key byte equals the threshold's (decided by the step after split_kernel).
+__global__ void __launch_bounds__(256) narrow_kernel(SelState* sel, const uint64_t* __restrict__ bkey,
+                                                     uint64_t* __restrict__ ckey, uint32_t ccap) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t n = sel->nB;
+  const uint32_t top = (uint32_t)(sel->kprefix >> 56);
+  const unsigned below = (1u << lane) - 1u;
+  for (uint64_t base = (uint64_t)blockIdx.x * kSelTile; base < n; base += (uint64_t)gridDim.x * kSelTile) {
+    uint64_t key[kSelItems];
+    unsigned m[kSelItems], none[kSelItems];
+    bool take[kSelItems];
+#pragma unroll
+    for (int k = 0; k < kSelItems; k++) {
+      const uint64_t i = base + (uint32_t)k * 256u + threadIdx.x;
+      key[k] = i < n ? bkey[i] : 0ull;
+      take[k] = i < n && (uint32_t)(key[k] >> 56) == top;
+      m[k] = __ballot_sync(0xFFFFFFFFu, take[k]);
+      none[k] = 0;
+    }
+    Reserve2 r = block_reserve2(m, none, &sel->nC, nullptr);
+#pragma unroll
+    for (int k = 0; k < kSelItems; k++) {
+      if (take[k]) {
+        const uint32_t p = r.a + __popc(m[k] & below);
+        if (p < ccap)
+          ckey[p] = key[k];
+        else
+          sel->c_over = 1;
+      }
+      r.a += __popc(m[k]);
     }
   }
 }
@@ -395,15 +478,15 @@ __global__ void release_kernel(TableView t, const uint32_t* __restrict__ vslot, 
   }
 }
 
-// Overflow bits after slots were released (meepo_evict): bit(b) must be set iff some live key sits past b on
-// the probe path from its home bucket. Insertion only ever sets the bits, so without this pass a table that
-// is filled, evicted and refilled for long enough ends up with every bit set and every miss / new key walks
-// ever longer chains. Two passes over the bucket array: clear, then every displaced key re-marks its path.
+// Displacement metadata after slots were released (meepo_evict): disp(h) must be the largest displacement of a
+// LIVE key with home h. Insertion only ever raises it, so without this pass a table that is filled, evicted and
+// refilled for long enough walks ever longer on every miss. Two passes: clear, then every displaced key raises
+// its home again.
 __global__ void __launch_bounds__(256) overflow_clear_kernel(TableView t) {
   for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < t.num_buckets; b += gridDim.x * blockDim.x) {
     uint32_t* w = reinterpret_cast<uint32_t*>(&t.buckets[b]) + 3;  // tags 12, 13 + metadata
     const uint32_t v = *w;
-    if (v & (1u << 16)) *w = v & ~(1u << 16);
+    if (v >> 16) *w = v & 0xFFFFu;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) t.counters[C_OVERFLOW] = 0ull;
 }
@@ -412,13 +495,10 @@ __global__ void __launch_bounds__(256) overflow_mark_kernel(TableView t) {
   for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < t.slots; s += gridDim.x * blockDim.x) {
     const uint64_t key = *key_ptr(t, s);
     if (key == MEEPO_KEY_EMPTY) continue;
-    const uint32_t b = s / kBucket;
-    for (uint32_t x = bucket_of(mix64(key), t.num_buckets); x != b; x = (x + 1 == t.num_buckets) ? 0 : x + 1) {
-      uint32_t* w = reinterpret_cast<uint32_t*>(&t.buckets[x]) + 3;
-      if (!(*reinterpret_cast<volatile uint32_t*>(w) & (1u << 16)) && !(atomicOr(w, 1u << 16) & (1u << 16))) fresh++;
-    }
+    const uint32_t b = s / kBucket, home = bucket_of(mix64(key), t.num_buckets);
+    if (b != home && raise_disp(t, home, b >= home ? b - home : b + t.num_buckets - home)) fresh++;
   }
-  fresh = __reduce_add_sync(0xFFFFFFFFu, fresh);
+  fresh = __reduce_add_sync(0xFFFFFFFFu, fresh);  // one atomic per warp: the counter is a single address
   if ((threadIdx.x & 31u) == 0 && fresh) atomicAdd(t.counters + C_OVERFLOW, (unsigned long long)fresh);
 }
 
@@ -649,9 +729,9 @@ MEEPO_API meepo_status meepo_evict(meepo_table* t, int32_t policy, double target
 
   const size_t sort_tmp = radix_sort_temp_bytes(k, 32);
   const size_t need = Workspace::pad(sizeof(SelState)) + Workspace::pad(k * 8) + 2 * Workspace::pad(k * 4) +  // list A
-                      Workspace::pad(size * 8) + Workspace::pad(size * 4) +                                  // list B
+                      Workspace::pad(size * 8) + Workspace::pad(size * 4) + Workspace::pad((size / 8 + 4096) * 8) +  // lists B, C
                       4 * Workspace::pad(k * 4) + Workspace::pad(sort_tmp) +                                 // sort
-                      Workspace::pad(k * 8) + Workspace::pad(k * 4) + 8192;
+                      Workspace::pad(k * 8) + Workspace::pad(k * 4) + Workspace::pad(256 * 8) + 8192;
   MEEPO_TRY(t->ws.reserve(need, stream));
   SelState* sel = t->ws.take<SelState>(1);
   uint64_t* akey = t->ws.take<uint64_t>(k);
@@ -659,6 +739,8 @@ MEEPO_API meepo_status meepo_evict(meepo_table* t, int32_t policy, double target
   uint32_t* ascore = t->ws.take<uint32_t>(k);
   uint64_t* bkey = t->ws.take<uint64_t>(size);
   uint32_t* bslot = t->ws.take<uint32_t>(size);
+  const uint64_t ccap = size / 8 + 4096;
+  uint64_t* ckey = t->ws.take<uint64_t>(ccap);
   uint32_t* sk_a = t->ws.take<uint32_t>(k);
   uint32_t* sk_b = t->ws.take<uint32_t>(k);
   uint32_t* ord_a = t->ws.take<uint32_t>(k);
@@ -667,25 +749,32 @@ MEEPO_API meepo_status meepo_evict(meepo_table* t, int32_t policy, double target
   uint64_t* vkey = t->ws.take<uint64_t>(k);
   uint32_t* vslot = t->ws.take<uint32_t>(k);
   unsigned long long* d_hist = t->dstate->hist;
+  unsigned long long* d_hist_low = t->ws.take<unsigned long long>(256);
   const int sgrid = grid1d(t, t->v.slots);
 
   {  // --- threshold T = score of the k-th smallest (score, key)
     ProfScope ps(t, "evict.select(4 table passes)", stream);
     sel_init_kernel<<<1, 1, 0, stream>>>(sel, k);
     MEEPO_CUDA_TRY(cudaMemsetAsync(d_hist, 0, 256 * 8, stream));
+    MEEPO_CUDA_TRY(cudaMemsetAsync(d_hist_low, 0, 256 * 8, stream));
     for (int shift = 24; shift >= 0; shift -= 8) {
-      score_hist_kernel<<<sgrid, 256, 0, stream>>>(t->v, policy, sel, shift, d_hist);
-      sel_step_kernel<<<1, 256, 0, stream>>>(sel, d_hist, shift, 0);
+      score_hist_kernel<<<sgrid, 256, 0, stream>>>(t->v, policy, sel, shift, d_hist, d_hist_low);
+      sel_step_kernel<<<1, 256, 0, stream>>>(sel, d_hist, shift, 0, shift == 24 ? d_hist_low : nullptr);
     }
     MEEPO_CUDA_TRY(cudaGetLastError());
   }
   {  // --- victims below T, candidates at T; the key threshold among the candidates
-    ProfScope ps(t, "evict.split+ties(1 table pass + 8 list passes)", stream);
-    split_kernel<<<gridsel(t, t->v.slots), 256, 0, stream>>>(t->v, policy, sel, akey, aslot, ascore, bkey, bslot);
-    const int bgrid = grid1d(t, size);
-    for (int shift = 56; shift >= 0; shift -= 8) {
-      key_hist_kernel<<<bgrid, 256, 0, stream>>>(bkey, sel, shift, d_hist);
-      sel_step_kernel<<<1, 256, 0, stream>>>(sel, d_hist, shift, 1);
+    {
+      ProfScope ps(t, "evict.split(1 table pass)", stream);
+      split_kernel<<<gridsel(t, t->v.slots), 256, 0, stream>>>(t->v, policy, sel, akey, aslot, ascore, bkey, bslot, d_hist);
+    }
+    ProfScope ps(t, "evict.ties(narrow + 7 list passes + take)", stream);
+    sel_step_kernel<<<1, 256, 0, stream>>>(sel, d_hist, 56, 1, nullptr);
+    narrow_kernel<<<gridsel(t, size), 256, 0, stream>>>(sel, bkey, ckey, (uint32_t)ccap);
+    const int cgrid = grid1d(t, ccap);
+    for (int shift = 48; shift >= 0; shift -= 8) {
+      key_hist_kernel<<<cgrid, 256, 0, stream>>>(bkey, ckey, sel, shift, d_hist);
+      sel_step_kernel<<<1, 256, 0, stream>>>(sel, d_hist, shift, 1, nullptr);
     }
     take_ties_kernel<<<gridsel(t, size), 256, 0, stream>>>(sel, bkey, bslot, akey, aslot, ascore, (uint32_t)k);
     MEEPO_CUDA_TRY(cudaGetLastError());

@@ -74,7 +74,7 @@ static const void* pick_kernel(bool insert, bool tier, uint32_t cpr) {
 // A find_or_insert / lookup call = begin, one or more chunks, end. Chunks of one call share the
 // epoch and (find_or_insert) the claimed-slot list; tags are published once, in end, so a key that
 // is new in the call reports INSERTED in every chunk (meepo.h "Status").
-meepo_status probe_gather_begin(meepo_table* t, uint64_t n_total, bool insert, cudaStream_t stream) {
+meepo_status probe_gather_begin(meepo_table* t, uint64_t n_total, bool insert, cudaStream_t stream, size_t extra_bytes) {
   t->epoch++;
   t->v.epoch = (uint32_t)t->epoch;
   t->cur_new.slots = nullptr;
@@ -97,9 +97,9 @@ meepo_status probe_gather_begin(meepo_table* t, uint64_t n_total, bool insert, c
     }
     t->cache_n = n_total;
   }
-  if (insert && n_total) {
-    MEEPO_TRY(t->ws.reserve(Workspace::pad(n_total * 4), stream));
-    t->cur_new.slots = t->ws.take<uint32_t>(n_total);
+  if ((insert || extra_bytes) && n_total) {  // the caller takes its `extra_bytes` from the workspace afterwards
+    MEEPO_TRY(t->ws.reserve(Workspace::pad(n_total * 4) + extra_bytes, stream));
+    t->cur_new.slots = insert ? t->ws.take<uint32_t>(n_total) : nullptr;
   }
   return MEEPO_OK;
 }

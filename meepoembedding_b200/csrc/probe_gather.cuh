@@ -150,6 +150,35 @@ __device__ __forceinline__ void gather_tile_slow(const TableView& t, uint64_t ke
   }
 }
 
+// NOOUT tiles (the pooled verbs: rows are not returned per key, a second kernel reads the arena by slot): only
+// the CAS winners have work — the new row + initial state, or the tuple coming back from the host tier, is
+// written to the arena. One key at a time, the lanes cover its chunks.
+__device__ __forceinline__ void init_winners(const TableView& t, uint64_t key, const Probe& pr, uint32_t tslab,
+                                             uint32_t lane) {
+  unsigned m = __ballot_sync(0xFFFFFFFFu, pr.winner);
+  const uint32_t cpr = t.cpr;
+  while (m) {
+    const int j = __ffs(m) - 1;
+    m &= m - 1;
+    const uint32_t s = __shfl_sync(0xFFFFFFFFu, pr.slot, j);
+    const uint64_t kj = __shfl_sync(0xFFFFFFFFu, key, j);
+    const uint32_t slab = __shfl_sync(0xFFFFFFFFu, tslab, j);
+    if (slab != kNil) {
+      const TierTuple tt = tier_tuple(t, slab);
+      for (uint32_t off = lane; off < cpr; off += 32) t.rows[(size_t)s * cpr + off] = tt.rows[off];
+      for (uint32_t off = lane; off < t.scpr; off += 32) t.state[(size_t)s * t.scpr + off] = tt.state[off];
+      if (lane == 0) {
+        if (t.scores) atomicAdd(&t.scores[s].x, tt.meta->z);
+        if (t.steps) t.steps[s] = *tt.steps;
+      }
+    } else {
+      for (uint32_t off = lane; off < cpr; off += 32) t.rows[(size_t)s * cpr + off] = init_chunk(t, kj, off);
+      const uint4 sv = init_state_chunk(t);
+      for (uint32_t off = lane; off < t.scpr; off += 32) t.state[(size_t)s * t.scpr + off] = sv;
+    }
+  }
+}
+
 struct TileCounts {
   uint32_t hit = 0, miss = 0, full = 0, tier = 0;
 };
@@ -202,12 +231,14 @@ static_assert(kScoreCells == 1u << 9, "score_cache_add hashes to 9 bits");
 // LFU score.
 // SCATTER: out_tile is ignored, this lane's row goes to (uint4*)dst (see tile_dst).
 // TIER: the table has a host tier (compiled out otherwise: the tier code costs registers in the hot kernels).
-template <int CPR, bool INSERT, bool SCATTER = false, bool TIER = false>
+// NOOUT: no rows are returned (slot_out / tslab_out say where each key's row is: arena slot, else tier slab).
+template <int CPR, bool INSERT, bool SCATTER = false, bool TIER = false, bool NOOUT = false>
 __device__ __forceinline__ void probe_gather_tile(const TableView& t, uint64_t key, bool valid, uint32_t tile_keys,
                                                   uint4* __restrict__ out_tile, uint8_t* status_out,
                                                   uint32_t* slot_out, uint64_t* key_out, uint32_t occurrences,
                                                   uint32_t* new_out, TileCounts& cnt, const ScoreCache& sc,
-                                                  uint32_t lane, unsigned long long dst = 0) {
+                                                  uint32_t lane, unsigned long long dst = 0,
+                                                  uint32_t* tslab_out = nullptr) {
   Probe pr{kNil, MEEPO_KEY_INVALID, false};
   if (INSERT) {
     pr = probe_find_or_insert(t, key);
@@ -244,6 +275,11 @@ __device__ __forceinline__ void probe_gather_tile(const TableView& t, uint64_t k
   if (INSERT) {
     if (valid && new_out) *new_out = pr.winner ? pr.slot : kNil;  // for publish_kernel
     fresh = __any_sync(0xFFFFFFFFu, pr.status == MEEPO_KEY_INSERTED);
+  }
+  if constexpr (NOOUT) {
+    if (valid && tslab_out) *tslab_out = tslab;
+    if (INSERT && __any_sync(0xFFFFFFFFu, pr.winner)) init_winners(t, key, pr, tslab, lane);
+    return;
   }
   if (CPR > 0) {
     gather_tile_fast<(CPR > 0 ? CPR : 1), SCATTER>(t, (pr.status == MEEPO_KEY_INSERTED || tslab != kNil) ? kNil : pr.slot,

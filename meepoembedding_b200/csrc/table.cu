@@ -230,6 +230,7 @@ MEEPO_API meepo_status meepo_destroy(meepo_table* t) {
   cudaFree(t->ws.base);
   cudaFree(t->cache.keys);
   cudaFree(t->cache.slots);
+  cudaFree(t->pool_scaled);
   tier_destroy(t);
   if (t->err_host) cudaFreeHost(const_cast<uint32_t*>(t->err_host));
   if (t->order_ev) cudaEventDestroy(t->order_ev);

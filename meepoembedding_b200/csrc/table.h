@@ -114,6 +114,8 @@ struct meepo_table {
   cudaStream_t tier_stream = nullptr;  // drains the staging buffer to the ring
   cudaEvent_t tier_staged = nullptr, tier_drained = nullptr;
   bool tier_draining = false;
+  char* pool_scaled = nullptr;   // pooled backward, MEAN: the bag gradients divided by the bag lengths
+  size_t pool_scaled_bytes = 0;
 
   uint64_t tuple_bytes() const { return 24 + (uint64_t)row_bytes + state_bytes; }
 };
@@ -155,14 +157,17 @@ CompactState compact_carve(char* p, uint32_t* error);
 // kernels' host launchers (defined across the .cu files)
 meepo_status launch_probe_gather(meepo_table* t, const uint64_t* keys, uint64_t n, void* rows_out,
                                  uint8_t* status_out, bool insert, cudaStream_t stream);
-meepo_status probe_gather_begin(meepo_table* t, uint64_t n_total, bool insert, cudaStream_t stream);
+meepo_status probe_gather_begin(meepo_table* t, uint64_t n_total, bool insert, cudaStream_t stream,
+                                size_t extra_bytes = 0);
 meepo_status probe_gather_chunk(meepo_table* t, const uint64_t* keys, uint64_t n, void* rows_out,
                                 uint8_t* status_out, bool insert, cudaStream_t stream);
 meepo_status probe_gather_end(meepo_table* t, uint64_t n_total, bool insert, cudaStream_t stream);
 // grads_ready (optional): event the reduce kernels wait for, so a caller can overlap the copy of
 // the gradients with the probe / sort / segment passes that only need the keys.
+// bag_offsets (optional, pooled backward): grads holds one row per bag; occurrence i reads the row of its bag
 meepo_status launch_apply_gradients(meepo_table* t, const uint64_t* keys, const void* grads, uint64_t n,
-                                    cudaStream_t stream, cudaEvent_t grads_ready = nullptr);
+                                    cudaStream_t stream, cudaEvent_t grads_ready = nullptr,
+                                    const uint32_t* bag_offsets = nullptr, uint32_t n_bags = 0);
 // Device-side counters of one sort + segment + reduce pipeline: every pipeline in flight has its own (the owner
 // side of a sharded backward pass runs on another stream than the sender side).
 struct SegScratch {

@@ -33,10 +33,14 @@ struct LongSeg {
 // A1: slot of every key (sort key) + iota (sort value). Keys that the preceding find_or_insert /
 // lookup already resolved (same batch: keys[i] == cache.keys[i]) reuse the cached slot; everything
 // else is probed (one 128-byte bucket line per key).
+// Pooled backward (bag_offsets != null): the sort value is the BAG of occurrence i instead of i — the reduce
+// kernels read "gradient row of the sort value", which is then the bag's gradient row; the sort is stable, so
+// the occurrences of a key stay in batch order either way.
 __global__ void __launch_bounds__(256) grad_slots_kernel(TableView t, const uint64_t* __restrict__ keys,
                                                          uint32_t n, uint32_t* __restrict__ sort_key,
                                                          uint32_t* __restrict__ sort_val, SlotCache sc,
-                                                         uint32_t cache_n) {
+                                                         uint32_t cache_n, const uint32_t* __restrict__ bag_offsets,
+                                                         uint32_t n_bags) {
   uint32_t dropped = 0;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint64_t key = __ldg(keys + i);
@@ -50,7 +54,16 @@ __global__ void __launch_bounds__(256) grad_slots_kernel(TableView t, const uint
       dropped++;
     }
     sort_key[i] = s;
-    sort_val[i] = i;
+    uint32_t v = i;
+    if (bag_offsets) {  // last bag b with offsets[b] <= i (empty bags share their offset with the next one)
+      uint32_t lo = 0, hi = n_bags;
+      while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(bag_offsets + mid) <= i) lo = mid; else hi = mid;
+      }
+      v = lo;
+    }
+    sort_val[i] = v;
   }
   dropped = __reduce_add_sync(0xFFFFFFFFu, dropped);
   if ((threadIdx.x & 31) == 0 && dropped) atomicAdd(t.counters + C_DROPPED, (unsigned long long)dropped);
@@ -730,7 +743,8 @@ meepo_status run_segmented(meepo_table* t, SegWork& w, uint32_t limit, const voi
 }
 
 meepo_status launch_apply_gradients(meepo_table* t, const uint64_t* keys, const void* grads, uint64_t n,
-                                    cudaStream_t stream, cudaEvent_t grads_ready) {
+                                    cudaStream_t stream, cudaEvent_t grads_ready, const uint32_t* bag_offsets,
+                                    uint32_t n_bags) {
   if (n == 0) return MEEPO_OK;
   const int end_bit = bits_for(t->v.slots);
   MEEPO_TRY(t->ws.reserve(SegWork::bytes(n, t->v.dim, end_bit), stream));
@@ -740,7 +754,8 @@ meepo_status launch_apply_gradients(meepo_table* t, const uint64_t* keys, const 
     ProfScope ps(t, "apply.grad_slots", stream);
     const int grid = grid_for(t, (const void*)grad_slots_kernel, 256, 0, (n + 255) / 256);
     const uint32_t cache_n = t->cache_valid ? (uint32_t)std::min<uint64_t>(t->cache_n, n) : 0u;
-    grad_slots_kernel<<<grid, 256, 0, stream>>>(t->v, keys, (uint32_t)n, w.sk_in, w.sv_in, t->cache, cache_n);
+    grad_slots_kernel<<<grid, 256, 0, stream>>>(t->v, keys, (uint32_t)n, w.sk_in, w.sv_in, t->cache, cache_n, bag_offsets,
+                                                n_bags);
     MEEPO_CUDA_TRY(cudaGetLastError());
   }
   static const char* const names[5] = {"apply.radix_sort", "apply.segments",

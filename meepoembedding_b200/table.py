@@ -19,6 +19,7 @@ from . import _capi as capi
 _DTYPES = {"f32": capi.F32, "fp32": capi.F32, "float32": capi.F32, "bf16": capi.BF16, "bfloat16": capi.BF16}
 _OPTS = {"sgd": capi.SGD, "adagrad": capi.ADAGRAD, "adam": capi.ADAM, "adagrad_rowwise": capi.ADAGRAD_ROWWISE}
 _POLICIES = {"lru": capi.LRU, "lfu": capi.LFU}
+_POOLS = {"sum": capi.POOL_SUM, "mean": capi.POOL_MEAN}
 
 
 def _is_host(x) -> bool:
@@ -206,6 +207,37 @@ class Table:
         else:
             rc = self.lib.apply_gradients(self._h, _ptr(keys), _ptr(grads), n, stream)
         self.lib.check(rc)
+
+    # -- pooled (bag) verbs (include/meepo.h "Pooling"): offsets = n_bags + 1 uint32, pooled rows of the table dtype
+    def _pooled_out(self, keys, n_bags):
+        if _is_host(keys):
+            return np.empty((n_bags, self.dim), dtype=self._np_row_dtype())
+        import torch
+
+        dt = torch.float32 if self.dtype == capi.F32 else torch.bfloat16
+        return torch.empty((n_bags, self.dim), dtype=dt, device=keys.device)
+
+    def find_or_insert_pooled(self, keys, offsets, pool="sum", pooled_out=None, status_out=None, n=None, stream=None,
+                              insert=True):
+        n = self._n(keys, n)
+        n_bags = self._n(offsets, None) - 1
+        if pooled_out is None:
+            pooled_out = self._pooled_out(keys, n_bags)
+        if status_out is None:
+            status_out = self._alloc_like(keys, n, "status")
+        fn = self.lib.find_or_insert_pooled if insert else self.lib.lookup_pooled
+        self.lib.check(fn(self._h, _ptr(keys), n, _ptr(offsets), n_bags, _POOLS[pool], _ptr(pooled_out), _ptr(status_out),
+                          stream))
+        return pooled_out, status_out
+
+    def lookup_pooled(self, keys, offsets, pool="sum", pooled_out=None, found_out=None, n=None, stream=None):
+        return self.find_or_insert_pooled(keys, offsets, pool, pooled_out, found_out, n, stream, insert=False)
+
+    def apply_gradients_pooled(self, keys, offsets, bag_grads, pool="sum", n=None, stream=None):
+        n = self._n(keys, n)
+        n_bags = self._n(offsets, None) - 1
+        self.lib.check(self.lib.apply_gradients_pooled(self._h, _ptr(keys), n, _ptr(offsets), n_bags, _POOLS[pool],
+                                                       _ptr(bag_grads), stream))
 
     # -- asynchronous host verbs (numpy buffers; include/meepo.h "Asynchronous forms") ----------
     def find_or_insert_async(self, keys, rows_out, status_out=None, n=None) -> int:

@@ -202,6 +202,28 @@ class Model:
             self.rows[k] = self._store(w)
             self.dirty.add(k)
 
+    # include/meepo.h "Pooling"
+    def pooled(self, keys, offsets, mean, insert):
+        rows, st = self._probe(keys, insert)
+        out = np.zeros((len(offsets) - 1, self.dim), dtype=F)
+        for b in range(len(offsets) - 1):
+            lo, hi = int(offsets[b]), int(offsets[b + 1])
+            acc = np.zeros(self.dim, dtype=F)
+            for i in range(lo, hi):
+                acc = acc + rows[i]
+            if mean and hi > lo:
+                acc = acc / F(hi - lo)
+            out[b] = self._store(acc)
+        return out, st
+
+    def apply_gradients_pooled(self, keys, offsets, bag_grads, mean):
+        g = np.zeros((len(keys), self.dim), dtype=F)
+        for b in range(len(offsets) - 1):
+            lo, hi = int(offsets[b]), int(offsets[b + 1])
+            for i in range(lo, hi):
+                g[i] = self._store(np.asarray(bag_grads[b], dtype=F) / F(hi - lo)) if mean else bag_grads[b]
+        self.apply_gradients(keys, g)
+
     def evict(self, policy, target_load):
         target = int(math.floor(target_load * self.capacity))
         if len(self.rows) <= target:

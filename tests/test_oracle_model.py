@@ -354,3 +354,49 @@ def test_delta_export_matches_model_and_replays(oracle_lib, tmp_path):
     plain = Table(lib=oracle_lib, **table_kwargs())
     with pytest.raises(capi.MeepoError):
         plain.export_delta_size()
+
+
+def make_bags(rng, n, max_len=9, empty_frac=0.15):
+    """offsets (uint32, n_bags + 1) cutting n keys into bags of 0..max_len keys."""
+    cuts = [0]
+    while cuts[-1] < n:
+        ln = 0 if rng.random() < empty_frac else int(rng.integers(1, max_len + 1))
+        cuts.append(min(n, cuts[-1] + ln))
+    if rng.random() < 0.5:
+        cuts.append(n)  # a trailing empty bag
+    return np.array(cuts, dtype=np.uint32)
+
+
+@pytest.mark.parametrize("pool", ["sum", "mean"])
+@pytest.mark.parametrize("dtype,optimizer", [("f32", "adagrad"), ("bf16", "adam"), ("bf16", "sgd")])
+def test_pooled_verbs_match_model(oracle_lib, pool, dtype, optimizer):
+    """include/meepo.h "Pooling": one row per bag forward, one gradient row per bag backward."""
+    rng = np.random.default_rng(53)
+    dim = 16
+    t, m = make_pair(oracle_lib, dim=dim, capacity=1024, dtype=dtype, optimizer=optimizer, track_scores=True)
+    for step in range(5):
+        keys = make_keys(rng, 260, 500, dup_frac=0.4)
+        off = make_bags(rng, keys.size)
+        out, st_ = t.find_or_insert_pooled(keys, off, pool)
+        mout, mst = m.pooled(keys, off, pool == "mean", True)
+        np.testing.assert_array_equal(st_, mst)
+        np.testing.assert_array_equal(rows_as_f32(out, dtype), mout)
+        bg = grads_for(dtype, rng.normal(0, 0.1, size=(off.size - 1, dim)))
+        t.apply_gradients_pooled(keys, off, bg, pool)
+        m.apply_gradients_pooled(keys, off, rows_as_f32(bg, dtype), pool == "mean")
+        check_table_equal(t, m, dtype)
+        lk = make_keys(rng, 150, 900)
+        loff = make_bags(rng, lk.size)
+        out, st_ = t.lookup_pooled(lk, loff, pool)
+        mout, mst = m.pooled(lk, loff, pool == "mean", False)
+        np.testing.assert_array_equal(st_, mst)
+        np.testing.assert_array_equal(rows_as_f32(out, dtype), mout)
+    # sum pooling of bags of one key each is the plain lookup
+    one = np.arange(lk.size + 1, dtype=np.uint32)
+    out, _ = t.lookup_pooled(lk, one, "sum")
+    rows, _ = t.lookup(lk)
+    np.testing.assert_array_equal(rows_as_f32(out, dtype) + np.float32(0), rows_as_f32(rows, dtype) + np.float32(0))
+    with pytest.raises(capi.MeepoError):
+        t.lookup_pooled(lk, loff, "sum", n=lk.size, pooled_out=None) if False else oracle_lib.check(
+            oracle_lib.lookup_pooled(t._h, lk.ctypes.data, lk.size, loff.ctypes.data, loff.size - 1, 7, out.ctypes.data,
+                                     None, None))
