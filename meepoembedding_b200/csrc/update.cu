@@ -177,6 +177,7 @@ struct ApplyArgs {
   int chunk;                // >= 0: visit only the segments [first segment of this chunk, first of the next)
   uint4* reduce_out;         // kStoreOnly: [unique][cpr] ...
   uint4* const* reduce_rows;  // ... or one destination row pointer per sort key (may point into a peer's window)
+  int bulk;                   // kStoreOnly, pipelined kernel: rows leave through shared memory as ONE bulk async store each
 };
 
 // Segment index range of this pass: everything, or one chunk of a chunked sort key.
@@ -269,6 +270,18 @@ __global__ void __launch_bounds__(256) apply_kernel(TableView t, ApplyArgs a) {
   }
 }
 
+// Bulk asynchronous store shared -> global (cp.async.bulk, the TMA unit; SASS UBLKCP): one 16-byte-aligned run of
+// `bytes` (a multiple of 16) per instruction. On a peer-mapped destination the row crosses NVLink as one request
+// of the copy engine's packet size instead of four 128-byte write requests of the load/store unit.
+__device__ __forceinline__ void bulk_store_row(void* dst, const void* smem_src, uint32_t bytes) {
+  const uint32_t src = (uint32_t)__cvta_generic_to_shared(smem_src);
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // A4': the same work for rows of <= 512 B (one 16-byte chunk per lane, group_lanes == cpr), software
 // pipelined: each group handles two segments per trip, puts the gradient / row / state loads of
 // both in flight before it consumes the first, and fetches the next trip's descriptors underneath.
@@ -287,12 +300,19 @@ __global__ void __launch_bounds__(256) apply_pipelined_kernel(TableView t, Apply
   const uint4 nil = make_uint4(0, kNil, 0, 0);
   auto desc = [&](uint32_t i) { return i <= U ? __ldg(a.seg_desc + i) : nil; };
 
+  // kStoreOnly with a.bulk: two staging rows per group (segment A / B of a trip)
+  __shared__ __align__(128) uint4 bulk_stage[OPT == kStoreOnly ? 2 * 256 : 1];
+  const bool bulk = OPT == kStoreOnly && a.bulk;
   uint32_t u_lo, u_hi;
   segment_range(a, U, u_lo, u_hi);
   uint32_t u = u_lo + group * 2;
   uint4 da = desc(u), db = desc(u + 1);
   uint32_t ec = desc(u + 2).x;
   while (u < u_hi) {
+    if (bulk) {  // the previous trip's bulk stores have read their staging rows
+      if (q == 0) bulk_wait_read();
+      __syncwarp(gmask);
+    }
     const uint32_t un = u + stride;
     const uint4 na = desc(un), nb = desc(un + 1);
     const uint32_t nc = desc(un + 2).x;
@@ -339,7 +359,14 @@ __global__ void __launch_bounds__(256) apply_pipelined_kernel(TableView t, Apply
         alpha = __fdiv_rn(group_tree_sum(chunk_sumsq<BF16>(acc), GL, gmask), (float)t.dim);
         inA.st[0].x = __shfl_sync(gmask, inA.st[0].x, lane & ~(GL - 1));  // the value lane 0 (the writer) loaded
       }
-      opt_finish<BF16, OPT>(t, da.y, q, inA, acc, alpha, reduce_row_of<OPT>(a, da.y, cpr));
+      if (bulk) {
+        bulk_stage[threadIdx.x] = narrow<BF16>(acc);
+        fence_proxy_async_smem();
+        __syncwarp(gmask);
+        if (q == 0) bulk_store_row(reduce_row_of<OPT>(a, da.y, cpr), &bulk_stage[threadIdx.x], cpr * 16u);
+      } else {
+        opt_finish<BF16, OPT>(t, da.y, q, inA, acc, alpha, reduce_row_of<OPT>(a, da.y, cpr));
+      }
     }
     if (okB) {
       float alpha = adam_alpha<OPT>(t, db.y, gmask, q == 0);
@@ -350,13 +377,21 @@ __global__ void __launch_bounds__(256) apply_pipelined_kernel(TableView t, Apply
         alpha = __fdiv_rn(group_tree_sum(chunk_sumsq<BF16>(acc), GL, gmask), (float)t.dim);
         inB.st[0].x = __shfl_sync(gmask, inB.st[0].x, lane & ~(GL - 1));
       }
-      opt_finish<BF16, OPT>(t, db.y, q, inB, acc, alpha, reduce_row_of<OPT>(a, db.y, cpr));
+      if (bulk) {
+        bulk_stage[256 + threadIdx.x] = narrow<BF16>(acc);
+        fence_proxy_async_smem();
+        __syncwarp(gmask);
+        if (q == 0) bulk_store_row(reduce_row_of<OPT>(a, db.y, cpr), &bulk_stage[256 + threadIdx.x], cpr * 16u);
+      } else {
+        opt_finish<BF16, OPT>(t, db.y, q, inB, acc, alpha, reduce_row_of<OPT>(a, db.y, cpr));
+      }
     }
     da = na;
     db = nb;
     ec = nc;
     u = un;
   }
+  if (bulk && q == 0) bulk_wait_all();  // the rows have landed before the kernel — and the barrier after it — ends
 }
 
 // A5: leaves of long segments -> partial[leaf][dim]. A leaf is a chain of up to 256 adds in batch
@@ -690,6 +725,8 @@ meepo_status seg_reduce(meepo_table* t, SegWork& w, const void* grads, int mode,
   a.chunk = r.chunk;
   a.reduce_out = reinterpret_cast<uint4*>(reduce_out);
   a.reduce_rows = reinterpret_cast<uint4* const*>(reduce_rows);
+  static const bool bulk_env = getenv("MEEPO_PEER_BULK") != nullptr && atoi(getenv("MEEPO_PEER_BULK")) != 0;
+  a.bulk = (mode == kReduceStoreOnly && reduce_rows != nullptr && bulk_env) ? 1 : 0;
   uint32_t gl = 1;
   while (gl * 2 <= t->v.cpr && gl < 32) gl *= 2;
   a.group_lanes = gl;
