@@ -163,20 +163,49 @@ __device__ __forceinline__ uint32_t home_disp(const uint4& h) { return h.w >> 16
 // Slot of `key` or kNil, starting at its home bucket b with the header already in registers: the buckets
 // b .. b + disp(b).
 template <int LD, typename TB>
-__device__ __forceinline__ uint32_t probe_from(const TB& t, uint64_t key, uint32_t tag, uint32_t b, uint4 hdr) {
-  const uint32_t disp = home_disp(hdr);
-  const uint32_t last = disp == kDispUnknown ? t.num_buckets - 1 : min(disp, t.num_buckets - 1);
-  for (uint32_t d = 0;; ++d) {
-    uint32_t m = match_mask(hdr, tag);
-    while (m) {
-      const uint32_t i = __ffs(m) - 1;
-      if (load_key<LD>(t, b, i) == key) return b * kBucket + i;
-      m &= m - 1;
-    }
-    if (d >= last) return kNil;
-    b = (b + 1 == t.num_buckets) ? 0 : b + 1;
-    hdr = load_header<LD>(t, b);
+__device__ __forceinline__ uint32_t match_in_bucket(const TB& t, uint64_t key, uint32_t tag, uint32_t b, const uint4& hdr) {
+  uint32_t m = match_mask(hdr, tag);
+  while (m) {
+    const uint32_t i = __ffs(m) - 1;
+    if (load_key<LD>(t, b, i) == key) return b * kBucket + i;
+    m &= m - 1;
   }
+  return kNil;
+}
+// The walk past the home bucket (10% of the keys at 90% load, 3% at 75%): kept out of line so that its registers
+// do not count against the hot kernels. It is known to be `last` buckets long: the first two lines are fetched
+// together (independent addresses) instead of one dependent HBM round trip after the other.
+#ifdef MEEPO_AB_INLINE_WALK
+#define MEEPO_WALK_INLINE __forceinline__
+#else
+#define MEEPO_WALK_INLINE __noinline__
+#endif
+template <int LD, typename TB>
+__device__ MEEPO_WALK_INLINE uint32_t probe_walk(const TB& t, uint64_t key, uint32_t tag, uint32_t b, uint32_t last) {
+  const uint32_t b1 = (b + 1 == t.num_buckets) ? 0 : b + 1;
+  const uint32_t b2 = (b1 + 1 == t.num_buckets) ? 0 : b1 + 1;
+  const uint4 h1 = load_header<LD>(t, b1);
+  uint4 h2 = make_uint4(0, 0, 0, 0);
+  if (last >= 2) h2 = load_header<LD>(t, b2);
+  uint32_t s = match_in_bucket<LD>(t, key, tag, b1, h1);
+  if (s != kNil || last < 2) return s;
+  s = match_in_bucket<LD>(t, key, tag, b2, h2);
+  if (s != kNil) return s;
+  b = b2;
+  for (uint32_t d = 3; d <= last; ++d) {
+    b = (b + 1 == t.num_buckets) ? 0 : b + 1;
+    s = match_in_bucket<LD>(t, key, tag, b, load_header<LD>(t, b));
+    if (s != kNil) return s;
+  }
+  return kNil;
+}
+template <int LD, typename TB>
+__device__ __forceinline__ uint32_t probe_from(const TB& t, uint64_t key, uint32_t tag, uint32_t b, uint4 hdr) {
+  const uint32_t s = match_in_bucket<LD>(t, key, tag, b, hdr);
+  if (s != kNil) return s;
+  const uint32_t disp = home_disp(hdr);
+  if (disp == 0) return kNil;
+  return probe_walk<LD>(t, key, tag, b, disp == kDispUnknown ? t.num_buckets - 1 : min(disp, t.num_buckets - 1));
 }
 // Probe without insertion. One HBM line per bucket visited.
 template <int LD = kCoherent, typename TB>

@@ -4,20 +4,40 @@
 
 namespace meepo {
 
+// Tiles are handed out statically (warp-strided) except the last eighth, which the warps take from a ticket
+// counter as they run dry: a tile with a new key or a displaced key is several dependent memory round trips
+// slower than a plain hit, and with static shares alone the warps of a CTA wait at the closing barrier for their
+// unluckiest sibling (ncu at 90% load: 23% of the stall samples). The last warp to finish resets the counters.
 template <int CPR, bool INSERT, bool TIER>
 __global__ void __launch_bounds__(256, 4) probe_gather_kernel(TableView t, const uint64_t* __restrict__ keys,
                                                            uint32_t n, uint4* __restrict__ out,
-                                                           uint8_t* __restrict__ status, NewList nl, SlotCache sc) {
+                                                           uint8_t* __restrict__ status, NewList nl, SlotCache sc,
+                                                           uint32_t* __restrict__ sched) {
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
   const uint32_t ntiles = (n + 31u) >> 5;
+#ifdef MEEPO_AB_STATIC_TILES
+  const uint32_t static_end = 0xFFFFFF00u / nwarps * nwarps;  // A/B: static shares only
+#else
+  const uint32_t static_end = (ntiles - ntiles / 8u) / nwarps * nwarps;
+#endif
   const uint32_t cpr = CPR > 0 ? (uint32_t)CPR : t.cpr;
   TileCounts cnt;
   __shared__ uint32_t sc_slot[kScoreCells], sc_freq[kScoreCells];
   const ScoreCache scache{sc_slot, sc_freq};
   score_cache_init(t, scache);
-  for (uint32_t tile = warp; tile < ntiles; tile += nwarps) {
+  uint32_t tile = warp;
+  while (true) {
+#ifdef MEEPO_AB_STATIC_TILES
+    if (tile >= ntiles) break;
+#endif
+    if (tile >= static_end) {
+      uint32_t tk = 0;
+      if (lane == 0) tk = atomicAdd(sched, 1u);
+      tile = static_end + __shfl_sync(0xFFFFFFFFu, tk, 0);
+      if (tile >= ntiles) break;
+    }
     const uint32_t i = tile * 32u + lane;
     const uint32_t tile_keys = min(32u, n - tile * 32u);
     const uint64_t key = i < n ? __ldg(keys + i) : MEEPO_KEY_EMPTY;
@@ -25,6 +45,11 @@ __global__ void __launch_bounds__(256, 4) probe_gather_kernel(TableView t, const
                                    status ? status + i : nullptr, sc.slots ? sc.slots + i : nullptr,
                                    sc.keys ? sc.keys + i : nullptr, 1u, nl.slots ? nl.slots + i : nullptr, cnt,
                                    scache, lane);
+    tile += nwarps;
+  }
+  if (lane == 0 && atomicAdd(sched + 1, 1u) + 1u == nwarps) {  // every warp has drawn its last ticket
+    sched[0] = 0;
+    sched[1] = 0;
   }
   score_cache_flush(t, scache);
   flush_tile_counts(t, cnt, lane);
@@ -121,7 +146,8 @@ meepo_status probe_gather_chunk(meepo_table* t, const uint64_t* keys, uint64_t n
     t->cache_off += n;
     t->cache_valid = t->cache_off == t->cache_n;
   }
-  void* args[] = {&t->v, &keys, &n32, &out, &status_out, &nl, &sc};
+  uint32_t* sched = t->dstate->sched;
+  void* args[] = {&t->v, &keys, &n32, &out, &status_out, &nl, &sc, &sched};
   ProfScope ps(t, insert ? "find_or_insert.probe_gather" : "lookup.probe_gather", stream);
   MEEPO_CUDA_TRY(cudaLaunchKernel(kern, dim3(grid), dim3(256), args, 0, stream));
   return MEEPO_OK;

@@ -268,7 +268,9 @@ __device__ __forceinline__ void probe_gather_tile(const TableView& t, uint64_t k
     // duplicates of a key inside the tile are folded into one update first
     const uint32_t s = valid ? pr.slot : kNil;
     const unsigned peers = __match_any_sync(0xFFFFFFFFu, s);
-    const uint32_t total = __reduce_add_sync(peers, occurrences);
+    // (a reduction over a partial mask is a loop over the groups: skip it when every key counts once)
+    const uint32_t total = __all_sync(0xFFFFFFFFu, occurrences == 1u) ? (uint32_t)__popc(peers)
+                                                                      : __reduce_add_sync(peers, occurrences);
     if (s != kNil && lane == (uint32_t)(__ffs(peers) - 1)) score_cache_add(t, sc, s, total);
   }
   bool fresh = false;

@@ -45,7 +45,7 @@ struct Workspace {
 // Small always-resident device block.
 struct DeviceState {
   unsigned long long counters[16];
-  uint32_t reserved_new[2];
+  uint32_t sched[2];  // probe kernels: dynamic tile tickets of the tail + finished warps (self-resetting)
   uint32_t unused0[3];
   uint32_t evict_count;
   uint32_t pad[2];
