@@ -27,6 +27,7 @@ import json
 import os
 import subprocess
 import sys
+import re
 import tempfile
 import time
 
@@ -470,7 +471,16 @@ class GpuRun:
             alg["dedup.reduce_store"] = B * R + gr * R  # reads every gradient row, stores the unique sums to the owners
             alg["sharded.finish(expand)"] = B * 2 * R
         kernels = {}
-        for name, (cnt, ms) in self.prof.items():
+        prof = dict(self.prof)
+        # the split path of apply_gradients reduces the singletons and the duplicate groups in two launches of the
+        # same kernel: one group for the roofline (the algorithmic bytes are those of the whole batch)
+        dup = prof.pop("apply.reduce_optimizer(duplicates)", None)
+        if dup and "apply.reduce_optimizer" in prof:
+            c0, m0 = prof["apply.reduce_optimizer"]
+            prof["apply.reduce_optimizer"] = (max(c0, dup[0]), m0 + dup[1])
+        elif dup:
+            prof["apply.reduce_optimizer"] = dup
+        for name, (cnt, ms) in prof.items():
             avg = ms / max(cnt, 1)
             k = {"launches": cnt, "avg_ms": avg, "share_of_step": ms / self.ms_total}
             if name in alg:
@@ -514,7 +524,8 @@ class GpuRun:
         for name, k in kernels.items():
             if "(cub)" in name:
                 continue
-            mult = int(name.split("(")[1].split(" ")[0]) if "kernels)" in name else 1
+            m = re.search(r"\((\d+) kernels\)", name)
+            mult = int(m.group(1)) if m else 1
             own_launches += k["launches"] * mult
         return roof, kernels, own_launches
 
