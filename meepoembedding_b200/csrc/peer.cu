@@ -843,8 +843,11 @@ MEEPO_API meepo_status meepo_peer_prepare(meepo_table* t, uint32_t rank, uint32_
   p->region = region_keys;
   p->out_buffers = out_buffers;
   p->out_bytes = (size_t)out_buffers * max_batch * t->row_bytes;
-  // Chunks of the backward pass: worth their barriers and small launches only when a call moves a lot of rows.
-  p->chunks = max_batch * (uint64_t)t->row_bytes >= (256ull << 20) ? kMaxChunks : 1;
+  // Chunks of the backward pass (the owner side of chunk c on its own stream under the sender side of chunk c + 1):
+  // opt-in. Measured on 2 and 4 B200 the per-chunk sorts and the SM sharing of the two pipelines cost what the
+  // overlap gains (N=4 cfg3: 8.47 ms with 1 chunk, 8.52 with 3), and with 3 chunks the forward pass that follows
+  // loses its store locality into the requesters' output buffers (12.96 ms).
+  p->chunks = 1;
   if (const char* e = getenv("MEEPO_PEER_CHUNKS"))
     p->chunks = (uint32_t)std::min<unsigned long>(kMaxChunks, std::max<unsigned long>(1, strtoul(e, nullptr, 10)));
   if (const char* e = getenv("MEEPO_PEER_SENDER_SHARE"))
