@@ -641,8 +641,14 @@ static meepo_status sharded_forward(meepo_table* t, const uint64_t* keys, uint64
   if (insert) MEEPO_CUDA_TRY(cudaMemsetAsync(nl.slots, 0xFF, n_window * 4, stream));
   // does the output tensor live in this rank's output area? then the owners store into it directly
   const char* ro = reinterpret_cast<const char*>(rows_out);
+  // Direct stores pay on 2 GPUs (no return region, no expansion pass). From 4 GPUs on every owner scatters 512-byte
+  // rows over the WHOLE output buffer of every requester instead of its own slice of a return region: the set of
+  // remote 2 MB pages in flight grows with the world size and the owner kernel falls off a cliff (measured:
+  // 2.61 vs 2.35 ms at N=4, 6.45 vs 2.77 ms at N=8). MEEPO_PEER_DIRECT=1 / MEEPO_PEER_NO_DIRECT force the choice.
+  static const bool force_direct = getenv("MEEPO_PEER_DIRECT") != nullptr && atoi(getenv("MEEPO_PEER_DIRECT")) != 0;
   const bool direct = n && p->out_bytes && ro >= p->out_base &&
-                      ro + n * (size_t)t->row_bytes <= p->out_base + p->out_bytes && !getenv("MEEPO_PEER_NO_DIRECT");
+                      ro + n * (size_t)t->row_bytes <= p->out_base + p->out_bytes && !getenv("MEEPO_PEER_NO_DIRECT") &&
+                      (p->world <= 2 || force_direct);
   const unsigned long long out_off = direct ? (unsigned long long)(ro - p->out_base) : kNoOutput;
   MEEPO_TRY(dedup_run(t, keys, nullptr, n, DedupOut{p->ukeys, nullptr, p->inverse, p->n_unique, uocc, nullptr, p->canon},
                       stream));
