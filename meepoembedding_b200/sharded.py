@@ -14,8 +14,12 @@ index arrays.
 from __future__ import annotations
 
 import numpy as np
-import torch
-import torch.distributed as dist
+
+try:  # torch is plumbing here (device tensors, torch.distributed); PeerShardedTable also runs without it
+    import torch
+    import torch.distributed as dist
+except ImportError:  # pragma: no cover
+    torch = dist = None
 
 from . import _capi as capi
 from . import keygen
@@ -151,13 +155,29 @@ class PeerShardedTable:
     synchronisation, no staging copy. Verbs are collective: every rank calls them in the same order.
     """
 
-    def __init__(self, table, group=None, device=None, max_batch=1 << 20, region_keys=0, out_buffers=0):
+    def __init__(self, table, group=None, device=None, max_batch=1 << 20, region_keys=0, out_buffers=0,
+                 rank=None, world=None, allgather=None, barrier=None):
+        """Either a torch.distributed `group` (default WORLD), or — no torch needed — `rank`, `world` and two
+        callables of the caller's own transport (MPI, a file, sockets): allgather(bytes) -> list of `world`
+        bytes objects in rank order, barrier() -> None. The blobs are 256 plain bytes per rank."""
         self.t = table
+        self.out_buffers = out_buffers
+        self._barrier = barrier
+        if allgather is not None:
+            if rank is None or world is None or barrier is None:
+                raise ValueError("allgather needs rank, world and barrier as well")
+            self.group, self.rank, self.world, self.device = None, int(rank), int(world), device
+            blob = table.peer_prepare(self.rank, self.world, max_batch, region_keys, out_buffers)
+            blobs = allgather(blob)
+            if len(blobs) != self.world:
+                raise ValueError("allgather must return one blob per rank")
+            table.peer_attach(b"".join(bytes(b) for b in blobs))
+            barrier()
+            return
         self.group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.group)
         self.rank = dist.get_rank(self.group)
         self.device = torch.device(device) if device is not None else torch.device("cuda", table.device)
-        self.out_buffers = out_buffers
         blob = table.peer_prepare(self.rank, self.world, max_batch, region_keys, out_buffers)
         mine = torch.frombuffer(bytearray(blob), dtype=torch.uint8)
         backend = dist.get_backend(self.group)
@@ -169,6 +189,8 @@ class PeerShardedTable:
         dist.barrier(group=self.group)
 
     def _stream(self):
+        if self.group is None:
+            return None  # the caller's transport: verbs go to the default stream unless the caller passes pointers itself
         return torch.cuda.current_stream(self.device).cuda_stream
 
     def output_buffer(self, index: int, rows: int | None = None):
@@ -177,16 +199,20 @@ class PeerShardedTable:
         return output_rows(self.t, index, rows, self.device)
 
     def find_or_insert(self, keys, rows_out, status_out=None):
-        return self.t.sharded_find_or_insert(keys, rows_out, status_out, n=keys.numel(), stream=self._stream())
+        return self.t.sharded_find_or_insert(keys, rows_out, status_out, n=self.t._n(keys, None), stream=self._stream())
 
     def lookup(self, keys, rows_out, found_out=None):
-        return self.t.sharded_lookup(keys, rows_out, found_out, n=keys.numel(), stream=self._stream())
+        return self.t.sharded_lookup(keys, rows_out, found_out, n=self.t._n(keys, None), stream=self._stream())
 
     def apply_gradients(self, keys, grads):
-        self.t.sharded_apply_gradients(keys, grads, n=keys.numel(), stream=self._stream())
+        self.t.sharded_apply_gradients(keys, grads, n=self.t._n(keys, None), stream=self._stream())
 
     def close(self):
         """All ranks must be done with the table: synchronise, meet, then unmap."""
-        torch.cuda.synchronize(self.device)
-        dist.barrier(group=self.group)
+        if self.group is None:
+            self.t.stats()  # meepo_stats synchronises the device
+            self._barrier()
+        else:
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)
         self.t.peer_detach()

@@ -241,6 +241,38 @@ def test_peer_requires_attach(cuda_lib):
     t.close()
 
 
+def test_peer_sharded_table_without_torch_distributed(oracle_lib, cuda_lib):
+    """PeerShardedTable with the caller's own transport (two callables) instead of a torch.distributed group:
+    the set-up only moves 256 plain bytes per rank. World 1 here; the verbs are the same kernels."""
+    from gpu_util import dkeys, drows, hrows
+    from meepoembedding_b200.sharded import PeerShardedTable
+    import torch
+
+    kw = table_kwargs(dim=32, capacity=4096, dtype="f32", optimizer="adagrad")
+    g, o = Table(lib=cuda_lib, **kw), Table(lib=oracle_lib, **kw)
+    st = PeerShardedTable(g, rank=0, world=1, allgather=lambda blob: [blob], barrier=lambda: None, max_batch=2048)
+    rng = np.random.default_rng(3)
+    for _ in range(3):
+        keys = make_keys(rng, 1500, 2500, dup_frac=0.4)
+        dk = dkeys(keys)
+        rows = torch.empty((keys.size, 32), dtype=torch.float32, device="cuda:0")
+        status = torch.empty(keys.size, dtype=torch.uint8, device="cuda:0")
+        st.find_or_insert(dk, rows, status)
+        torch.cuda.synchronize()
+        orows, ost = o.find_or_insert(keys)
+        np.testing.assert_array_equal(status.cpu().numpy(), ost)
+        np.testing.assert_array_equal(hrows(rows, "f32"), orows)
+        gr = rng.normal(0, 0.1, size=(keys.size, 32)).astype(np.float32)
+        st.apply_gradients(dk, drows(gr, "f32"))
+        torch.cuda.synchronize()
+        uk, ug, nu = np.empty(keys.size, np.uint64), np.empty((keys.size, 32), np.float32), np.zeros(1, np.uint64)
+        o.reduce_duplicates(keys, gr, uk, ug, None, nu)
+        o.apply_gradients(uk[:int(nu[0])], np.ascontiguousarray(ug[:int(nu[0])]))
+    st.close()
+    from test_gpu_capacity import assert_tables_equal
+    assert_tables_equal(g, o)
+
+
 # ---------------------------------------------------------------------------------------------------
 def _free_port():
     s = socket.socket()
