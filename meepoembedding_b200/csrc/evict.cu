@@ -478,28 +478,44 @@ __global__ void release_kernel(TableView t, const uint32_t* __restrict__ vslot, 
   }
 }
 
-// Displacement metadata after slots were released (meepo_evict): disp(h) must be the largest displacement of a
-// LIVE key with home h. Insertion only ever raises it, so without this pass a table that is filled, evicted and
-// refilled for long enough walks ever longer on every miss. Two passes: clear, then every displaced key raises
-// its home again.
-__global__ void __launch_bounds__(256) overflow_clear_kernel(TableView t) {
-  for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < t.num_buckets; b += gridDim.x * blockDim.x) {
-    uint32_t* w = reinterpret_cast<uint32_t*>(&t.buckets[b]) + 3;  // tags 12, 13 + metadata
-    const uint32_t v = *w;
-    if (v >> 16) *w = v & 0xFFFFu;
+// Displacement metadata after slots were released (meepo_evict): disp(h) must stay the largest displacement of a
+// LIVE key with home h — insertion only ever raises it, so without maintenance a table that is filled, evicted
+// and refilled for long enough walks ever longer on every miss. Only the homes of victims that sat past their
+// home bucket can change, and only downwards: one thread per such victim rescans the buckets h .. h + disp(h)
+// for the keys whose home is h and lowers the bound to what it finds (every thread of one home computes the same
+// value; the CAS winner that takes a home to 0 counts it out of overflow_buckets). Round 1 and the first half of
+// round 2 rebuilt the metadata of the WHOLE table after every eviction (clear pass + mark pass, 0.46 ms at 67M
+// slots); this is ~40K local scans for 400K victims.
+__global__ void __launch_bounds__(256) overflow_fix_kernel(TableView t, const uint64_t* __restrict__ vkey,
+                                                           const uint32_t* __restrict__ vslot, uint32_t k) {
+  // one WARP per victim: lane l scans buckets home + 1 + l, home + 33 + l, ... (a thread per victim left the kernel
+  // waiting for the few homes whose bound is in the hundreds: 0.32 ms)
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  uint32_t gone = 0;
+  for (uint32_t j = warp; j < k; j += nwarps) {
+    const uint32_t b = vslot[j] / kBucket;
+    const uint32_t home = bucket_of(mix64(vkey[j]), t.num_buckets);
+    if (b == home) continue;
+    uint32_t* w = reinterpret_cast<uint32_t*>(&t.buckets[home]) + 3;
+    const uint32_t cur = __shfl_sync(0xFFFFFFFFu, *reinterpret_cast<volatile uint32_t*>(w), 0);
+    const uint32_t d_old = cur >> 16;
+    if (d_old == 0) continue;  // a sibling already settled this home
+    const uint32_t last = d_old == kDispUnknown ? t.num_buckets - 1 : min(d_old, t.num_buckets - 1);
+    uint32_t dmax = 0;
+    for (uint32_t d = 1 + lane; d <= last; d += 32) {
+      const uint32_t x = (uint32_t)(((uint64_t)home + d) % t.num_buckets);
+      for (uint32_t i = 0; i < kBucket; i++) {
+        const uint64_t key = t.buckets[x].key[i];
+        if (key != MEEPO_KEY_EMPTY && bucket_of(mix64(key), t.num_buckets) == home) dmax = d;
+      }
+    }
+    dmax = __reduce_max_sync(0xFFFFFFFFu, dmax);
+    if (lane == 0 && dmax < d_old && atomicCAS(w, cur, (cur & 0xFFFFu) | (dmax << 16)) == cur && dmax == 0) gone++;
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) t.counters[C_OVERFLOW] = 0ull;
-}
-__global__ void __launch_bounds__(256) overflow_mark_kernel(TableView t) {
-  uint32_t fresh = 0;
-  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < t.slots; s += gridDim.x * blockDim.x) {
-    const uint64_t key = *key_ptr(t, s);
-    if (key == MEEPO_KEY_EMPTY) continue;
-    const uint32_t b = s / kBucket, home = bucket_of(mix64(key), t.num_buckets);
-    if (b != home && raise_disp(t, home, b >= home ? b - home : b + t.num_buckets - home)) fresh++;
-  }
-  fresh = __reduce_add_sync(0xFFFFFFFFu, fresh);  // one atomic per warp: the counter is a single address
-  if ((threadIdx.x & 31u) == 0 && fresh) atomicAdd(t.counters + C_OVERFLOW, (unsigned long long)fresh);
+  gone = __reduce_add_sync(0xFFFFFFFFu, gone);
+  if (lane == 0 && gone) atomicAdd(t.counters + C_OVERFLOW, (unsigned long long)(-(long long)gone));
 }
 
 // --- meepo_spill_readmit ----------------------------------------------------------------------------------
@@ -798,9 +814,8 @@ MEEPO_API meepo_status meepo_evict(meepo_table* t, int32_t policy, double target
     release_kernel<<<grid1d(t, k), 256, 0, stream>>>(t->v, vslot, (uint32_t)k);
   }
   {
-    ProfScope ps(t, "evict.rebuild_overflow(2 kernels)", stream);
-    overflow_clear_kernel<<<grid1d(t, t->v.num_buckets), 256, 0, stream>>>(t->v);
-    overflow_mark_kernel<<<grid1d(t, t->v.slots), 256, 0, stream>>>(t->v);
+    ProfScope ps(t, "evict.fix_displacements", stream);
+    overflow_fix_kernel<<<gridwarp(t, k), 256, 0, stream>>>(t->v, vkey, vslot, (uint32_t)k);
   }
   MEEPO_CUDA_TRY(cudaGetLastError());
   if (n_evicted) *n_evicted = k;
