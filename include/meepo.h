@@ -357,6 +357,27 @@ MEEPO_API meepo_status meepo_export_delta_buffers(meepo_table* t, uint64_t* keys
                                                   uint64_t* n_out);
 MEEPO_API meepo_status meepo_export_delta(meepo_table* t, const char* path);
 
+/* --- tier dump / load (synchronous): the host tier's side of a checkpoint --- *
+ * meepo_export* cover the HBM level. A table whose host tier is in use is
+ * checkpointed as TWO files: meepo_export + meepo_tier_export, and restored
+ * with meepo_import + meepo_tier_import (a delta only ever holds HBM tuples: a
+ * tuple has to be promoted before it can change). meepo_tier_export(_buffers)
+ * writes the live tuples of the tier sorted by key (same conventions and file
+ * format as meepo_export(_buffers); keys == NULL is a size query);
+ * meepo_tier_import(_buffers) APPENDS tuples with distinct keys to the ring in
+ * the given order, exactly as an eviction would (the a-th append goes to slab
+ * a mod T, a newer copy of a key replaces the older one); state == NULL ->
+ * initial state, scores / steps == NULL -> 0. After a restore the ring holds
+ * the tuples in key order, i.e. the smallest keys are overwritten first. */
+MEEPO_API meepo_status meepo_tier_export_buffers(meepo_table* t, uint64_t* keys, void* rows, void* state,
+                                                 uint64_t* scores, uint32_t* steps, uint64_t max_n,
+                                                 uint64_t* n_out);
+MEEPO_API meepo_status meepo_tier_import_buffers(meepo_table* t, const uint64_t* keys, const void* rows,
+                                                 const void* state, const uint64_t* scores,
+                                                 const uint32_t* steps, uint64_t n);
+MEEPO_API meepo_status meepo_tier_export(meepo_table* t, const char* path);
+MEEPO_API meepo_status meepo_tier_import(meepo_table* t, const char* path);
+
 /* --- sharding helpers (one process per GPU; the exchange itself is the
  *     caller's collective: torch.distributed / NCCL all-to-all, or the fused
  *     peer-memory kernels below) ------------------------------------------- */

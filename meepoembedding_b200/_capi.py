@@ -119,6 +119,10 @@ SIGNATURES = {
     "meepo_export": (C.c_int, [_P, C.c_char_p]),
     "meepo_export_delta": (C.c_int, [_P, C.c_char_p]),
     "meepo_import": (C.c_int, [_P, C.c_char_p]),
+    "meepo_tier_export_buffers": (C.c_int, [_P, _P, _P, _P, _P, _P, _U64, C.POINTER(_U64)]),
+    "meepo_tier_import_buffers": (C.c_int, [_P, _P, _P, _P, _P, _P, _U64]),
+    "meepo_tier_export": (C.c_int, [_P, C.c_char_p]),
+    "meepo_tier_import": (C.c_int, [_P, C.c_char_p]),
     "meepo_owner": (C.c_uint32, [_U64, _U32]),
     "meepo_shard_partition": (C.c_int, [_P, _P, _U64, _U32, _P, _P, _P, _P]),
     "meepo_reduce_duplicates": (C.c_int, [_P, _P, _P, _U64, _P, _P, _P, _P, _P]),

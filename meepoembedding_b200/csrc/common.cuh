@@ -138,7 +138,7 @@ __device__ __forceinline__ uint32_t bytes_eq4(uint32_t w, uint32_t pat) {
   return ((m >> 7) * 0x10204080u) >> 28;           // gather bits 0,8,16,24 into a nibble
 }
 // Load policy of the probe. kCoherent (ld.global.cg, L2): find_or_insert, where other threads CAS
-// keys / OR the overflow bit in the same line (tags and published keys never change in a kernel).
+// keys / raise the displacement bound in the same line (tags and published keys never change in a kernel).
 // kReadOnly (ld.global.nc, L1-cached): lookup / apply_gradients / evict probes — nothing in the
 // bucket array is written while they run, and hot Zipf keys are served by L1.
 enum : int { kCoherent = 0, kReadOnly = 1 };

@@ -1,6 +1,6 @@
 // evict.cu — capacity management (include/meepo.h "Evict" / "Host tier"): exact selection of
 // the lowest-(score,key) victims, hand-over of their tuples to the host tier, slot release without tombstones
-// (the per-bucket overflow bits keep lookups correct), and explicit re-admission.
+// (the per-home displacement bounds keep lookups correct), and explicit re-admission.
 //
 // Everything data-dependent stays on the device. The host reads ONE number (the table size, which fixes the
 // victim count k and with it every grid and scratch size), then enqueues:
@@ -15,11 +15,14 @@
 //            index, file the new keys, gather the tuples into a staging buffer in HBM; a private stream then
 //            drains the staging buffer into the pinned ring with plain DMA copies (the slabs of one eviction
 //            are consecutive) underneath whatever the caller enqueues next
-//   release  keys -> EMPTY, tags -> 0, scores / steps -> 0; overflow bits rebuilt
+//   release  keys -> EMPTY, tags -> 0, scores / steps -> 0; the displacement bounds of the victims' homes lowered
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
+
+#include <cstdio>
+#include <memory>
 
 #include "table.h"
 
@@ -437,32 +440,51 @@ struct TierDst {  // where the tuples of an eviction are written: staging (j) or
   uint32_t* steps;
   uint32_t d0, slabs;  // slabs != 0: destination index = (d0 + j) mod slabs, else j
 };
-// one warp per victim: tuple -> destination
-__global__ void __launch_bounds__(256) tier_gather_kernel(TableView t, TierDst dst, const uint32_t* __restrict__ vslot,
-                                                          uint32_t n) {
+struct TierSrc {  // where the tuples come from: arena slots (eviction) or caller buffers (meepo_tier_import_buffers)
+  const uint32_t* vslot;  // != null: tuple j = arena slot vslot[j]
+  const uint64_t* keys;   // else: tuple j = keys[j], rows[j], state[j] (may be null: initial state), scores, steps
+  const uint4 *rows, *state;
+  const uint64_t* scores;
+  const uint32_t* steps;
+};
+// one warp per tuple: source -> destination
+__global__ void __launch_bounds__(256) tier_gather_kernel(TableView t, TierDst dst, TierSrc src, uint32_t n) {
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
   for (uint32_t j = warp; j < n; j += nwarps) {
-    const uint32_t s = vslot[j];
     uint32_t d = j;
     if (dst.slabs) {
       d = dst.d0 + j;
       if (d >= dst.slabs) d -= dst.slabs;
     }
-    for (uint32_t q = lane; q < t.cpr; q += 32) dst.rows[(size_t)d * t.cpr + q] = ld_stream(t.rows + (size_t)s * t.cpr + q);
-    for (uint32_t q = lane; q < t.scpr; q += 32)
-      dst.state[(size_t)d * t.scpr + q] = ld_stream(t.state + (size_t)s * t.scpr + q);
-    if (lane == 0) {
-      const uint64_t key = *key_ptr(t, s);
-      const uint2 sc = t.scores[s];
-      dst.meta[d] = make_uint4((uint32_t)key, (uint32_t)(key >> 32), sc.x, sc.y);
-      dst.steps[d] = t.steps ? t.steps[s] : 0u;
+    if (src.vslot) {
+      const uint32_t s = src.vslot[j];
+      for (uint32_t q = lane; q < t.cpr; q += 32) dst.rows[(size_t)d * t.cpr + q] = ld_stream(t.rows + (size_t)s * t.cpr + q);
+      for (uint32_t q = lane; q < t.scpr; q += 32)
+        dst.state[(size_t)d * t.scpr + q] = ld_stream(t.state + (size_t)s * t.scpr + q);
+      if (lane == 0) {
+        const uint64_t key = *key_ptr(t, s);
+        const uint2 sc = t.scores[s];
+        dst.meta[d] = make_uint4((uint32_t)key, (uint32_t)(key >> 32), sc.x, sc.y);
+        dst.steps[d] = t.steps ? t.steps[s] : 0u;
+      }
+    } else {
+      for (uint32_t q = lane; q < t.cpr; q += 32) dst.rows[(size_t)d * t.cpr + q] = src.rows[(size_t)j * t.cpr + q];
+      const uint4 s0 = init_state_chunk(t);
+      for (uint32_t q = lane; q < t.scpr; q += 32)
+        dst.state[(size_t)d * t.scpr + q] = src.state ? src.state[(size_t)j * t.scpr + q] : s0;
+      if (lane == 0) {
+        const uint64_t key = src.keys[j];
+        const uint64_t sc = src.scores ? src.scores[j] : 0ull;
+        dst.meta[d] = make_uint4((uint32_t)key, (uint32_t)(key >> 32), (uint32_t)sc, (uint32_t)(sc >> 32));
+        dst.steps[d] = src.steps ? src.steps[j] : 0u;
+      }
     }
   }
 }
 
-// release the victims' slots: key -> EMPTY, tag -> 0, scores/steps -> 0 (overflow bits are rebuilt below)
+// release the victims' slots: key -> EMPTY, tag -> 0, scores/steps -> 0 (displacement bounds: overflow_fix_kernel)
 __global__ void release_kernel(TableView t, const uint32_t* __restrict__ vslot, uint32_t k) {
   for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < k; j += gridDim.x * blockDim.x) {
     const uint32_t s = vslot[j];
@@ -575,6 +597,47 @@ __global__ void __launch_bounds__(256) readmit_drop_kernel(TableView t, const ui
     if (status[i] == MEEPO_KEY_FOUND) tier_erase(t, keys[i]);
 }
 
+// --- the tier's side of a checkpoint -----------------------------------------------------------------------
+// live slabs of the ring -> (key, slab), any order (sorted by key afterwards)
+__global__ void __launch_bounds__(256) tier_live_kernel(TableView t, uint64_t* __restrict__ keys, uint32_t* __restrict__ slabs,
+                                                        uint32_t* __restrict__ count) {
+  const uint32_t lane = threadIdx.x & 31u;
+  for (uint32_t d0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; d0 < t.tier.slabs; d0 += gridDim.x * blockDim.x) {
+    const uint32_t d = d0 + lane;
+    const uint64_t key = d < t.tier.slabs ? t.tier.ring_key[d] : MEEPO_KEY_EMPTY;
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, key != MEEPO_KEY_EMPTY);
+    if (!m) continue;
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(count, (uint32_t)__popc(m));
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (key != MEEPO_KEY_EMPTY) {
+      const uint32_t p = base + __popc(m & ((1u << lane) - 1u));
+      keys[p] = key;
+      slabs[p] = d;
+    }
+  }
+}
+// one warp per exported tuple: tier (staging or ring) -> caller buffers (each may be null)
+__global__ void __launch_bounds__(256) tier_export_kernel(TableView t, const uint32_t* __restrict__ slabs, uint32_t n,
+                                                          uint4* __restrict__ rows, uint4* __restrict__ state,
+                                                          uint64_t* __restrict__ scores, uint32_t* __restrict__ steps) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t j = warp; j < n; j += nwarps) {
+    const TierTuple tt = tier_tuple(t, slabs[j]);
+    if (rows)
+      for (uint32_t q = lane; q < t.cpr; q += 32) rows[(size_t)j * t.cpr + q] = tt.rows[q];
+    if (state)
+      for (uint32_t q = lane; q < t.scpr; q += 32) state[(size_t)j * t.scpr + q] = tt.state[q];
+    if (lane == 0) {
+      const uint4 m = *tt.meta;
+      if (scores) scores[j] = ((uint64_t)m.w << 32) | m.z;
+      if (steps) steps[j] = *tt.steps;
+    }
+  }
+}
+
 static int grid1d(const meepo_table* t, uint64_t n) {
   return (int)std::max<uint64_t>(1, std::min<uint64_t>((n + 255) / 256, (uint64_t)t->num_sms * 8));
 }
@@ -639,8 +702,7 @@ void tier_destroy(meepo_table* t) {
 
 // Hands the victims vslot[j0 .. j0 + m) / vkey[..] (eviction order) to the ring. head = tuples appended before
 // this eviction, k = victims of this eviction (the first k - m would be overwritten by the later ones anyway).
-static meepo_status tier_append(meepo_table* t, const uint32_t* vslot, const uint64_t* vkey, uint64_t k,
-                                cudaStream_t stream) {
+static meepo_status tier_append(meepo_table* t, TierSrc src, const uint64_t* vkey, uint64_t k, cudaStream_t stream) {
   TierView& tv = t->v.tier;
   const uint64_t slabs = tv.slabs;
   const uint64_t m = std::min<uint64_t>(k, slabs), j0 = k - m;
@@ -686,7 +748,16 @@ static meepo_status tier_append(meepo_table* t, const uint32_t* vslot, const uin
   }
   {
     ProfScope ps(t, staged ? "evict.gather_to_staging" : "evict.spill_copy(pcie, zero-copy)", stream);
-    tier_gather_kernel<<<gridwarp(t, m), 256, 0, stream>>>(t->v, dst, vslot + j0, (uint32_t)m);
+    if (src.vslot) {
+      src.vslot += j0;
+    } else {
+      src.keys += j0;
+      src.rows += j0 * t->v.cpr;
+      if (src.state) src.state += j0 * t->v.scpr;
+      if (src.scores) src.scores += j0;
+      if (src.steps) src.steps += j0;
+    }
+    tier_gather_kernel<<<gridwarp(t, m), 256, 0, stream>>>(t->v, dst, src, (uint32_t)m);
     MEEPO_CUDA_TRY(cudaGetLastError());
   }
   tv.stage_d0 = staged ? d0 : 0;
@@ -808,7 +879,7 @@ MEEPO_API meepo_status meepo_evict(meepo_table* t, int32_t policy, double target
     victims_kernel<<<kgrid, 256, 0, stream>>>(ord_b, aslot, akey, (uint32_t)k, vslot, vkey);
     MEEPO_CUDA_TRY(cudaGetLastError());
   }
-  if (t->v.tier.slabs) MEEPO_TRY(tier_append(t, vslot, vkey, k, stream));
+  if (t->v.tier.slabs) MEEPO_TRY(tier_append(t, TierSrc{vslot, nullptr, nullptr, nullptr, nullptr, nullptr}, vkey, k, stream));
   {
     ProfScope ps(t, "evict.release", stream);
     release_kernel<<<grid1d(t, k), 256, 0, stream>>>(t->v, vslot, (uint32_t)k);
@@ -850,6 +921,223 @@ MEEPO_API meepo_status meepo_spill_readmit(meepo_table* t, const uint64_t* keys,
   if (status_out) MEEPO_CUDA_TRY(cudaMemcpyAsync(status_out, d_status, n, cudaMemcpyDeviceToHost, stream));
   MEEPO_CUDA_TRY(cudaStreamSynchronize(stream));
   return MEEPO_OK;
+}
+
+
+// --- the host tier's side of a checkpoint (include/meepo.h "tier dump / load") -----------------------------
+}  // extern "C"
+
+namespace {
+struct TierFileHeader {  // the MEEPOTB1 header (io.cu)
+  char magic[8];
+  uint32_t version, dim, dtype, opt;
+  uint64_t n, row_bytes, state_bytes, epoch;
+};
+static_assert(sizeof(TierFileHeader) == 56, "header layout");
+
+// Live tier tuples as (key, slab) sorted by key, left in the workspace. Synchronises.
+meepo_status tier_sorted_live(meepo_table* t, uint64_t* n_out, uint64_t** keys_sorted, uint32_t** slabs_sorted,
+                              cudaStream_t stream) {
+  unsigned long long live = 0;
+  MEEPO_CUDA_TRY(cudaDeviceSynchronize());
+  MEEPO_CUDA_TRY(cudaMemcpy(&live, t->dstate->counters + C_TIER_LIVE, 8, cudaMemcpyDeviceToHost));
+  *n_out = live;
+  if (live == 0) return MEEPO_OK;
+  const uint64_t n = live;
+  if (!radix_sort_supported(n, 32)) return fail(MEEPO_EINVAL, "tier export: too many tuples");
+  const size_t tmp_bytes = radix_sort_temp_bytes(n, 32);
+  MEEPO_TRY(t->ws.reserve(2 * Workspace::pad(n * 8) + 6 * Workspace::pad(n * 4) + Workspace::pad(tmp_bytes) + 4096, stream));
+  uint64_t* k_in = t->ws.take<uint64_t>(n);
+  uint64_t* k_out = t->ws.take<uint64_t>(n);
+  uint32_t* s_in = t->ws.take<uint32_t>(n);
+  uint32_t* s_out = t->ws.take<uint32_t>(n);
+  uint32_t* sk_a = t->ws.take<uint32_t>(n);
+  uint32_t* sk_b = t->ws.take<uint32_t>(n);
+  uint32_t* ord_a = t->ws.take<uint32_t>(n);
+  uint32_t* ord_b = t->ws.take<uint32_t>(n);
+  char* tmp = t->ws.take<char>(tmp_bytes);
+  uint32_t* count = &t->dstate->evict_count;
+  MEEPO_CUDA_TRY(cudaMemsetAsync(count, 0, 4, stream));
+  tier_live_kernel<<<grid1d(t, t->v.tier.slabs), 256, 0, stream>>>(t->v, k_in, s_in, count);
+  const int g = grid1d(t, n);
+  sort_key_kernel<<<g, 256, 0, stream>>>(0, k_in, nullptr, nullptr, (uint32_t)n, sk_a, ord_a);
+  MEEPO_TRY(radix_sort_pairs(t, tmp, sk_a, sk_b, ord_a, ord_b, (uint32_t)n, 32, stream));
+  sort_key_kernel<<<g, 256, 0, stream>>>(1, k_in, nullptr, ord_b, (uint32_t)n, sk_a, nullptr);
+  MEEPO_TRY(radix_sort_pairs(t, tmp, sk_a, sk_b, ord_b, ord_a, (uint32_t)n, 32, stream));
+  victims_kernel<<<g, 256, 0, stream>>>(ord_a, s_in, k_in, (uint32_t)n, s_out, k_out);
+  MEEPO_CUDA_TRY(cudaGetLastError());
+  MEEPO_CUDA_TRY(cudaStreamSynchronize(stream));
+  *keys_sorted = k_out;
+  *slabs_sorted = s_out;
+  return MEEPO_OK;
+}
+}  // namespace
+
+extern "C" {
+
+MEEPO_API meepo_status meepo_tier_export_buffers(meepo_table* t, uint64_t* keys, void* rows, void* state, uint64_t* scores,
+                                                 uint32_t* steps, uint64_t max_n, uint64_t* n_out) {
+  if (!t || !n_out) return fail(MEEPO_EINVAL, "null argument");
+  DeviceGuard guard(t->device);
+  VerbScope vs(t, nullptr);
+  MEEPO_TRY(vs.rc);
+  *n_out = 0;
+  if (!t->v.tier.slabs) return MEEPO_OK;
+  cudaStream_t stream = nullptr;
+  uint64_t n = 0;
+  uint64_t* ks = nullptr;
+  uint32_t* ss = nullptr;
+  if (!keys) {  // size query
+    unsigned long long live = 0;
+    MEEPO_CUDA_TRY(cudaDeviceSynchronize());
+    MEEPO_CUDA_TRY(cudaMemcpy(&live, t->dstate->counters + C_TIER_LIVE, 8, cudaMemcpyDeviceToHost));
+    *n_out = live;
+    return MEEPO_OK;
+  }
+  MEEPO_TRY(tier_sorted_live(t, &n, &ks, &ss, stream));
+  *n_out = n;
+  if (n == 0) return MEEPO_OK;
+  if (max_n < n) return fail(MEEPO_EINVAL, "export buffers too small");
+  MEEPO_CUDA_TRY(cudaMemcpyAsync(keys, ks, n * 8, cudaMemcpyDeviceToDevice, stream));
+  tier_export_kernel<<<gridwarp(t, n), 256, 0, stream>>>(t->v, ss, (uint32_t)n, reinterpret_cast<uint4*>(rows),
+                                                         t->v.scpr ? reinterpret_cast<uint4*>(state) : nullptr, scores, steps);
+  MEEPO_CUDA_TRY(cudaGetLastError());
+  MEEPO_CUDA_TRY(cudaStreamSynchronize(stream));
+  return MEEPO_OK;
+}
+
+MEEPO_API meepo_status meepo_tier_import_buffers(meepo_table* t, const uint64_t* keys, const void* rows, const void* state,
+                                                 const uint64_t* scores, const uint32_t* steps, uint64_t n) {
+  if (!t) return fail(MEEPO_EINVAL, "null table");
+  if (n && (!keys || !rows)) return fail(MEEPO_EINVAL, "null buffer");
+  if (n > 0xFFFFFFFFull) return fail(MEEPO_EINVAL, "batch too large (n must fit in 32 bits)");
+  if (n == 0) return MEEPO_OK;
+  if (!t->v.tier.slabs) return fail(MEEPO_EINVAL, "the table has no host tier (host_spill_bytes == 0)");
+  DeviceGuard guard(t->device);
+  cudaStream_t stream = nullptr;
+  VerbScope vs(t, stream);
+  MEEPO_TRY(vs.rc);
+  TierSrc src{nullptr, keys, reinterpret_cast<const uint4*>(rows), reinterpret_cast<const uint4*>(state), scores, steps};
+  MEEPO_TRY(tier_append(t, src, keys, n, stream));
+  MEEPO_CUDA_TRY(cudaStreamSynchronize(stream));
+  return MEEPO_OK;
+}
+
+MEEPO_API meepo_status meepo_tier_export(meepo_table* t, const char* path) {
+  if (!t || !path) return fail(MEEPO_EINVAL, "null argument");
+  DeviceGuard guard(t->device);
+  VerbScope vs(t, nullptr);
+  MEEPO_TRY(vs.rc);
+  cudaStream_t stream = nullptr;
+  uint64_t n = 0;
+  uint64_t* ks = nullptr;
+  uint32_t* ss = nullptr;
+  if (t->v.tier.slabs) MEEPO_TRY(tier_sorted_live(t, &n, &ks, &ss, stream));
+  FILE* f = fopen(path, "wb");
+  if (!f) return fail(MEEPO_EIO, std::string("cannot open ") + path);
+  std::unique_ptr<FILE, int (*)(FILE*)> closer(f, fclose);
+  TierFileHeader h{};
+  memcpy(h.magic, "MEEPOTB1", 8);
+  h.version = 1;
+  h.dim = t->cfg.dim;
+  h.dtype = (uint32_t)t->cfg.dtype;
+  h.opt = (uint32_t)t->cfg.opt;
+  h.n = n;
+  h.row_bytes = t->row_bytes;
+  h.state_bytes = t->state_bytes;
+  h.epoch = t->epoch;
+  if (fwrite(&h, sizeof h, 1, f) != 1) return fail(MEEPO_EIO, "short write");
+  if (n == 0) return MEEPO_OK;
+  const uint64_t chunk = 1u << 16;
+  const size_t widest = std::max<size_t>({(size_t)t->row_bytes, (size_t)t->state_bytes, 8});
+  char *d_stage = nullptr, *h_stage = nullptr;
+  MEEPO_CUDA_TRY(cudaMalloc(&d_stage, chunk * widest));
+  if (cudaHostAlloc(&h_stage, chunk * widest, cudaHostAllocDefault) != cudaSuccess) {
+    cudaFree(d_stage);
+    return fail(MEEPO_ENOMEM, "cudaHostAlloc(export bounce)");
+  }
+  meepo_status rc = MEEPO_OK;
+  auto section = [&](int what, size_t width) {  // sections in file order: keys, rows, state, scores, steps
+    for (uint64_t lo = 0; lo < n && rc == MEEPO_OK; lo += chunk) {
+      const uint64_t m = std::min(chunk, n - lo);
+      const void* src = d_stage;
+      uint4* st = reinterpret_cast<uint4*>(d_stage);
+      if (what == 0)
+        src = ks + lo;
+      else
+        tier_export_kernel<<<gridwarp(t, m), 256, 0, stream>>>(
+            t->v, ss + lo, (uint32_t)m, what == 1 ? st : nullptr, what == 2 ? st : nullptr,
+            what == 3 ? reinterpret_cast<uint64_t*>(d_stage) : nullptr, what == 4 ? reinterpret_cast<uint32_t*>(d_stage) : nullptr);
+      if (cudaMemcpyAsync(h_stage, src, m * width, cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
+          cudaStreamSynchronize(stream) != cudaSuccess)
+        rc = fail(MEEPO_ECUDA, "tier export copy failed");
+      else if (fwrite(h_stage, width, m, f) != m)
+        rc = fail(MEEPO_EIO, "short write");
+    }
+  };
+  section(0, 8);
+  section(1, t->row_bytes);
+  if (t->state_bytes) section(2, t->state_bytes);
+  section(3, 8);
+  section(4, 4);
+  cudaFree(d_stage);
+  cudaFreeHost(h_stage);
+  if (rc == MEEPO_OK && fflush(f) != 0) rc = fail(MEEPO_EIO, "flush failed");
+  return rc;
+}
+
+MEEPO_API meepo_status meepo_tier_import(meepo_table* t, const char* path) {
+  if (!t || !path) return fail(MEEPO_EINVAL, "null argument");
+  DeviceGuard guard(t->device);
+  FILE* f = fopen(path, "rb");
+  if (!f) return fail(MEEPO_EIO, std::string("cannot open ") + path);
+  std::unique_ptr<FILE, int (*)(FILE*)> closer(f, fclose);
+  TierFileHeader h{};
+  if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, "MEEPOTB1", 8) != 0 || h.version != 1)
+    return fail(MEEPO_EIO, "bad header");
+  if (h.dim != t->cfg.dim || (int32_t)h.dtype != t->cfg.dtype || h.row_bytes != t->row_bytes ||
+      h.state_bytes != t->state_bytes || (int32_t)h.opt != t->cfg.opt)
+    return fail(MEEPO_EINVAL, "file does not match table configuration");
+  const uint64_t n = h.n, R = t->row_bytes, S = t->state_bytes;
+  const uint64_t tuple_file = 8 + R + S + 8 + 4;
+  if (fseeko(f, 0, SEEK_END) != 0) return fail(MEEPO_EIO, "seek failed");
+  const off_t fsz = ftello(f);
+  if (fsz < 0 || (uint64_t)fsz != sizeof h + n * tuple_file || n > 0xFFFFFFFFull)
+    return fail(MEEPO_EIO, "file size does not match the tuple count in the header");
+  if (n == 0) return MEEPO_OK;
+  if (!t->v.tier.slabs) return fail(MEEPO_EINVAL, "the table has no host tier (host_spill_bytes == 0)");
+  const uint64_t off_keys = sizeof h, off_rows = off_keys + n * 8, off_state = off_rows + n * R,
+                 off_scores = off_state + n * S, off_steps = off_scores + n * 8;
+  const uint64_t chunk = 1u << 16;
+  char *d_stage = nullptr, *h_stage = nullptr;
+  MEEPO_CUDA_TRY(cudaMalloc(&d_stage, chunk * tuple_file + 1024));
+  if (cudaHostAlloc(&h_stage, chunk * tuple_file + 1024, cudaHostAllocDefault) != cudaSuccess) {
+    cudaFree(d_stage);
+    return fail(MEEPO_ENOMEM, "cudaHostAlloc(import bounce)");
+  }
+  meepo_status rc = MEEPO_OK;
+  for (uint64_t lo = 0; lo < n && rc == MEEPO_OK; lo += chunk) {
+    const uint64_t m = std::min(chunk, n - lo);
+    const size_t o_k = 0, o_r = o_k + chunk * 8, o_s = o_r + chunk * R, o_c = o_s + chunk * S, o_t = o_c + chunk * 8;
+    auto rd = [&](uint64_t file_off, size_t width, size_t stage_off) {
+      if (width == 0) return true;
+      return fseeko(f, (off_t)(file_off + lo * width), SEEK_SET) == 0 && fread(h_stage + stage_off, width, m, f) == m;
+    };
+    if (!rd(off_keys, 8, o_k) || !rd(off_rows, R, o_r) || !rd(off_state, S, o_s) || !rd(off_scores, 8, o_c) ||
+        !rd(off_steps, 4, o_t)) {
+      rc = fail(MEEPO_EIO, "short read");
+      break;
+    }
+    if (cudaMemcpy(d_stage, h_stage, o_t + chunk * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+      rc = fail(MEEPO_ECUDA, "import copy failed");
+      break;
+    }
+    rc = meepo_tier_import_buffers(t, reinterpret_cast<uint64_t*>(d_stage + o_k), d_stage + o_r, S ? d_stage + o_s : nullptr,
+                                   reinterpret_cast<uint64_t*>(d_stage + o_c), reinterpret_cast<uint32_t*>(d_stage + o_t), m);
+  }
+  cudaFree(d_stage);
+  cudaFreeHost(h_stage);
+  return rc;
 }
 
 }  // extern "C"

@@ -311,6 +311,28 @@ class Table:
     def import_file(self, path: str):
         self.lib.check(self.lib.import_(self._h, path.encode()))
 
+    # -- the host tier's side of a checkpoint (include/meepo.h "tier dump / load") --------------
+    def tier_export_size(self) -> int:
+        n = C.c_uint64(0)
+        self.lib.check(self.lib.tier_export_buffers(self._h, None, None, None, None, None, 0, C.byref(n)))
+        return int(n.value)
+
+    def tier_export_buffers(self, keys, rows=None, state=None, scores=None, steps=None, max_n=None) -> int:
+        n = C.c_uint64(0)
+        self.lib.check(self.lib.tier_export_buffers(self._h, _ptr(keys), _ptr(rows), _ptr(state), _ptr(scores), _ptr(steps),
+                                                    self._n(keys, max_n), C.byref(n)))
+        return int(n.value)
+
+    def tier_import_buffers(self, keys, rows, state=None, scores=None, steps=None, n=None):
+        self.lib.check(self.lib.tier_import_buffers(self._h, _ptr(keys), _ptr(rows), _ptr(state), _ptr(scores), _ptr(steps),
+                                                    self._n(keys, n)))
+
+    def tier_export_file(self, path: str):
+        self.lib.check(self.lib.tier_export(self._h, path.encode()))
+
+    def tier_import_file(self, path: str):
+        self.lib.check(self.lib.tier_import(self._h, path.encode()))
+
     # -- sharding helpers -------------------------------------------------------
     def owner(self, key: int, num_shards: int) -> int:
         return int(self.lib.owner(int(key) & 0xFFFFFFFFFFFFFFFF, int(num_shards)))

@@ -263,6 +263,14 @@ class Model:
                 st[i] = capi.KEY_INSERTED
         return st
 
+    def tier_export(self):
+        """[(key, (row, state, step, freq, last))] of the tier, by key."""
+        return [(k, self.ring[d][1]) for k, d in sorted(self.spill.items())]
+
+    def tier_import(self, tuples):
+        for k, tup in tuples:
+            self._tier_append(k, tup)
+
     def export_delta(self):
         """Keys touched since the last delta export, ascending; marks them clean."""
         out = sorted(self.dirty)

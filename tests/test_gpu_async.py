@@ -107,9 +107,9 @@ def test_verbs_on_different_streams_are_ordered(oracle_lib, cuda_lib):
 
 
 def test_evict_rebuilds_overflow_bits(oracle_lib, cuda_lib):
-    """Fill to 92%, evict to 40%, repeat: after every evict the overflow bits are exactly the buckets that the
-    surviving displaced keys still pass (none when nothing is displaced), they do not accumulate from cycle to
-    cycle, and lookups stay exact."""
+    """Fill to 92%, evict to 40%, repeat: after every evict the displacement bounds are exact again — a home bucket
+    counts as overflowed only while one of its keys still sits in a later bucket (none when nothing is displaced),
+    the count does not accumulate from cycle to cycle, and lookups stay exact."""
     from gpu_util import gpu_foi
 
     cap = 1 << 15

@@ -297,3 +297,67 @@ def test_delta_export_parity(oracle_lib, cuda_lib, tmp_path, dtype, optimizer):
     assert replica.export_delta_size() == rk.size
     with pytest.raises(capi.MeepoError):
         Table(lib=cuda_lib, **table_kwargs()).export_delta_size()
+
+
+def gpu_tier_export(t):
+    import torch
+    from gpu_util import DEV
+
+    n = t.tier_export_size()
+    m = max(n, 1)
+    keys = torch.empty(m, dtype=torch.int64, device=DEV)
+    rows = torch.empty((m, t.row_bytes), dtype=torch.uint8, device=DEV)
+    state = torch.empty((m, max(t.state_bytes, 1)), dtype=torch.uint8, device=DEV)
+    scores = torch.empty(m, dtype=torch.int64, device=DEV)
+    steps = torch.empty(m, dtype=torch.int32, device=DEV)
+    got = t.tier_export_buffers(keys, rows, state if t.state_bytes else None, scores, steps, max_n=m)
+    assert got == n
+    rdt = np.float32 if t.dtype == capi.F32 else np.uint16
+    return (keys.cpu().numpy().view(np.uint64)[:n], rows.cpu().numpy().view(rdt).reshape(m, t.dim)[:n],
+            state.cpu().numpy()[:, :t.state_bytes].copy().view(np.float32).reshape(m, t.state_bytes // 4)[:n],
+            scores.cpu().numpy().view(np.uint64)[:n], steps.cpu().numpy().view(np.uint32)[:n])
+
+
+@pytest.mark.parametrize("dtype,optimizer", [("bf16", "adam"), ("f32", "adagrad")])
+def test_two_level_checkpoint(oracle_lib, cuda_lib, tmp_path, dtype, optimizer):
+    """include/meepo.h "tier dump / load": the tier dump equals the oracle's (buffers and files byte for byte);
+    HBM file + tier file restored into a fresh CUDA table carry on bit-exactly like the oracle restored the same way
+    (promotions out of the re-imported tier included)."""
+    from test_oracle_model import tier_export_sorted
+
+    dim = 16
+    probe = Table(lib=oracle_lib, **table_kwargs(dim=dim, capacity=64, dtype=dtype, optimizer=optimizer))
+    tuple_bytes = 24 + probe.row_bytes + probe.state_bytes
+    kw = table_kwargs(dim=dim, capacity=4096, dtype=dtype, optimizer=optimizer, track_scores=True,
+                      host_spill_bytes=9000 * tuple_bytes)
+    g, o = Table(lib=cuda_lib, **kw), Table(lib=oracle_lib, **kw)
+
+    def steps(tables, n_steps, seed):
+        rng = np.random.default_rng(seed)
+        for _ in range(n_steps):
+            run_stream(tables, dtype, dim, int(rng.integers(1 << 30)), steps=1, n=1500, universe=12000)
+            if tables[1].stats()["size"] > 0.7 * 4096:
+                assert tables[0].evict("lfu", 0.4) == tables[1].evict("lfu", 0.4)
+
+    steps((g, o), 12, 5)
+    assert o.stats()["spill_keys"] > 1000
+    for name, a, b in zip(("keys", "rows", "state", "scores", "steps"), gpu_tier_export(g), tier_export_sorted(o)):
+        np.testing.assert_array_equal(a, b, err_msg=f"tier {name}")
+    hg, tg, ho, to = (str(tmp_path / f) for f in ("hbm_g.meepo", "tier_g.meepo", "hbm_o.meepo", "tier_o.meepo"))
+    g.export_file(hg), g.tier_export_file(tg), o.export_file(ho), o.tier_export_file(to)
+    assert filecmp.cmp(hg, ho, shallow=False) and filecmp.cmp(tg, to, shallow=False)
+    g2, o2 = Table(lib=cuda_lib, **kw), Table(lib=oracle_lib, **kw)
+    g2.import_file(ho), g2.tier_import_file(to)  # each side loads the OTHER side's files
+    o2.import_file(hg), o2.tier_import_file(tg)
+    assert_tables_equal(g2, o2)
+    for name, a, b in zip(("keys", "rows", "state", "scores", "steps"), gpu_tier_export(g2), tier_export_sorted(o2)):
+        np.testing.assert_array_equal(a, b, err_msg=f"restored tier {name}")
+    before = o2.stats()["promotions"]
+    steps((g2, o2), 8, 6)
+    assert_tables_equal(g2, o2)
+    gs, os_ = g2.stats(), o2.stats()
+    for k in ("size", "hits", "inserts", "promotions", "tier_hits", "spill_keys", "evictions"):
+        assert gs[k] == os_[k], k
+    assert os_["promotions"] - before > 200
+    with pytest.raises(capi.MeepoError):  # a table without a tier refuses tier tuples
+        Table(lib=cuda_lib, **table_kwargs(dim=dim, capacity=4096, dtype=dtype, optimizer=optimizer)).tier_import_file(tg)

@@ -400,3 +400,69 @@ def test_pooled_verbs_match_model(oracle_lib, pool, dtype, optimizer):
         t.lookup_pooled(lk, loff, "sum", n=lk.size, pooled_out=None) if False else oracle_lib.check(
             oracle_lib.lookup_pooled(t._h, lk.ctypes.data, lk.size, loff.ctypes.data, loff.size - 1, 7, out.ctypes.data,
                                      None, None))
+
+
+def tier_export_sorted(t):
+    n = t.tier_export_size()
+    keys = np.empty(max(n, 1), dtype=np.uint64)
+    rows = np.empty((max(n, 1), t.dim), dtype=np.float32 if t.dtype == capi.F32 else np.uint16)
+    state = np.empty((max(n, 1), max(t.state_bytes // 4, 1)), dtype=np.float32)
+    scores = np.empty(max(n, 1), dtype=np.uint64)
+    steps = np.empty(max(n, 1), dtype=np.uint32)
+    got = t.tier_export_buffers(keys, rows, state if t.state_bytes else None, scores, steps, max_n=max(n, 1))
+    assert got == n
+    return keys[:n], rows[:n], state[:n, :t.state_bytes // 4], scores[:n], steps[:n]
+
+
+def test_two_level_checkpoint(oracle_lib, tmp_path):
+    """include/meepo.h "tier dump / load": export + tier_export, then import + tier_import into a fresh table give a
+    table that carries on exactly like the original (statuses, rows, promotions) and like the model."""
+    rng = np.random.default_rng(71)
+    kw = dict(dim=8, capacity=252, dtype="bf16", optimizer="adam", track_scores=True, host_spill_bytes=400 * (24 + 16 + 64))
+    t, m = make_pair(oracle_lib, **kw)
+
+    def some_steps(tabs, n_steps, seed):
+        r = np.random.default_rng(seed)
+        for _ in range(n_steps):
+            keys = make_keys(r, 70, 900, dup_frac=0.3)
+            outs = [x.find_or_insert(keys) for x in tabs]
+            for o in outs[1:]:
+                np.testing.assert_array_equal(rows_as_f32(outs[0][0], "bf16") if not isinstance(tabs[0], Model) else outs[0][0],
+                                              rows_as_f32(o[0], "bf16") if o[0].dtype == np.uint16 else o[0])
+                np.testing.assert_array_equal(outs[0][1], o[1])
+            g = grads_for("bf16", r.normal(0, 0.1, size=(keys.size, 8)))
+            for x in tabs:
+                x.apply_gradients(keys, rows_as_f32(g, "bf16") if isinstance(x, Model) else g)
+            if tabs[0].stats()["size"] > 180:
+                ns = [x.evict("lru", 0.4) if not isinstance(x, Model) else x.evict(capi.LRU, 0.4) for x in tabs]
+                assert len(set(ns)) == 1
+
+    some_steps([t, m], 14, 1)
+    assert len(m.spill) > 100
+    # the tier dump equals the model's
+    tk, trows, tstate, tscores, tsteps = tier_export_sorted(t)
+    mt = m.tier_export()
+    assert tk.tolist() == [k for k, _ in mt]
+    for j, (k, tup) in enumerate(mt):
+        np.testing.assert_array_equal(rows_as_f32(trows[j:j + 1], "bf16")[0], tup[0])
+        np.testing.assert_array_equal(tstate[j], tup[1])
+        assert int(tsteps[j]) == tup[2] and int(tscores[j]) == (tup[4] << 32) | tup[3]
+    # checkpoint = two files; restore into a fresh table
+    base, tier = str(tmp_path / "hbm.meepo"), str(tmp_path / "tier.meepo")
+    t.export_file(base), t.tier_export_file(tier)
+    t2 = Table(lib=oracle_lib, **table_kwargs(**kw))
+    t2.import_file(base), t2.tier_import_file(tier)
+    for x, y in zip(export_sorted(t), export_sorted(t2)):
+        np.testing.assert_array_equal(x, y)
+    for x, y in zip(tier_export_sorted(t), tier_export_sorted(t2)):
+        np.testing.assert_array_equal(x, y)
+    # the restored table and a model restored the same way carry on identically (promotions included); the
+    # original differs only in ring order, which shows in what a full ring drops, not here (the ring has room)
+    m2 = Model(8, 252, capi.BF16, capi.ADAM, 0.05, 1e-6, 0.9, 0.99, 0.1, 0.05, 0xC0FFEE, True, m.spill_tuples)
+    m2.rows, m2.state, m2.step, m2.freq, m2.last, m2.epoch = dict(m.rows), dict(m.state), dict(m.step), dict(m.freq), dict(m.last), m.epoch
+    m2.tier_import(mt)
+    t2_stats = t2.stats()
+    assert t2_stats["spill_keys"] == len(m2.spill)
+    some_steps([t2, m2], 8, 2)
+    check_table_equal(t2, m2, "bf16")
+    assert m2.promotions > 20
