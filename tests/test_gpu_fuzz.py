@@ -34,12 +34,12 @@ def test_random_verb_sequences(oracle_lib, cuda_lib, tmp_path, seed, dtype, dim,
                       host_spill_bytes=700 * tuple_bytes)
     g, o = Table(lib=cuda_lib, **kw), Table(lib=oracle_lib, **kw)
     last_keys = None
-    ops = ["foi", "foi_host", "lookup", "apply_last", "apply_other", "evict", "readmit", "roundtrip"]
+    ops = ["foi", "foi_host", "lookup", "apply_last", "apply_other", "evict", "readmit", "roundtrip", "pooled", "apply_pooled"]
     for step in range(90):
         if o.stats()["size"] > 0.6 * cap:  # +1500 new keys at most per call: never runs full
             op = "evict"
         else:
-            op = str(rng.choice(ops, p=[0.25, 0.1, 0.15, 0.2, 0.1, 0.06, 0.09, 0.05]))
+            op = str(rng.choice(ops, p=[0.2, 0.08, 0.12, 0.17, 0.08, 0.06, 0.09, 0.05, 0.08, 0.07]))
         n = int(rng.choice([1, 31, 33, 257, 700, 1500]))
         if op in ("foi", "foi_host"):
             keys = make_keys(rng, n, universe, dup_frac=0.4, invalid=n >= 8)
@@ -69,6 +69,26 @@ def test_random_verb_sequences(oracle_lib, cuda_lib, tmp_path, seed, dtype, dim,
             gr = grads_for(dtype, rng.normal(0, 0.1, size=(keys.size, dim)))
             gpu_apply(g, keys, gr, dtype)
             o.apply_gradients(keys, gr)
+        elif op in ("pooled", "apply_pooled"):
+            from test_gpu_pool import gpu_apply_pooled, gpu_pooled
+            from test_oracle_model import make_bags
+
+            pool = "mean" if rng.random() < 0.5 else "sum"
+            if op == "pooled":  # pooled forward (insert or lookup): leaves the slot cache for a following apply
+                insert = rng.random() < 0.6
+                keys = make_keys(rng, n, universe + (0 if insert else 2000), dup_frac=0.4, invalid=n >= 8)
+                off = make_bags(rng, keys.size)
+                out, st = gpu_pooled(g, keys, off, pool, dtype, insert=insert)
+                oout, ost = (o.find_or_insert_pooled if insert else o.lookup_pooled)(keys, off, pool)
+                np.testing.assert_array_equal(st, ost, err_msg=f"step {step} {op}")
+                np.testing.assert_array_equal(out, oout, err_msg=f"step {step} {op}")
+                last_keys = keys
+            else:
+                keys = last_keys if last_keys is not None and rng.random() < 0.6 else make_keys(rng, n, universe + 500, dup_frac=0.5)
+                off = make_bags(rng, keys.size)
+                bg = grads_for(dtype, rng.normal(0, 0.1, size=(off.size - 1, dim)))
+                gpu_apply_pooled(g, keys, off, bg, pool, dtype)
+                o.apply_gradients_pooled(keys, off, bg, pool)
         elif op == "evict":
             policy = "lfu" if rng.random() < 0.5 else "lru"
             target = float(rng.choice([0.3, 0.5, 0.6]))

@@ -271,13 +271,13 @@ def test_bad_arguments(oracle_lib):
         t.evict("lfu", 0.5)  # scores not tracked
 
 
-@settings(max_examples=40, deadline=None)
-@given(st.lists(st.tuples(st.sampled_from(["foi", "lookup", "grad", "evict", "readmit"]),
+@settings(max_examples=60, deadline=None)
+@given(st.lists(st.tuples(st.sampled_from(["foi", "lookup", "grad", "evict", "readmit", "pooled", "grad_pooled", "delta"]),
                           st.lists(st.integers(0, 40), min_size=0, max_size=60)), min_size=1, max_size=8),
        st.sampled_from(["f32", "bf16"]), st.sampled_from(["sgd", "adagrad", "adam", "adagrad_rowwise"]))
 def test_hypothesis_streams(oracle_lib, ops, dtype, optimizer):
     special = {38: capi.KEY_EMPTY, 39: capi.KEY_RESERVED, 40: capi.KEY_RESERVED - 1, 0: 0}
-    t, m = make_pair(oracle_lib, dim=8, capacity=32, dtype=dtype, optimizer=optimizer, track_scores=True,
+    t, m = make_pair(oracle_lib, dim=8, capacity=32, dtype=dtype, optimizer=optimizer, track_scores=True, track_dirty=True,
                      host_spill_bytes=1000)  # a ring of 7..17 slabs: wraps, promotes, reads through
     rng = np.random.default_rng(0)
     for op, ids in ops:
@@ -298,6 +298,22 @@ def test_hypothesis_streams(oracle_lib, ops, dtype, optimizer):
             m.apply_gradients(keys, rows_as_f32(g, dtype))
         elif op == "readmit":
             np.testing.assert_array_equal(t.spill_readmit(keys), m.readmit(keys))
+        elif op in ("pooled", "grad_pooled"):
+            cuts = sorted(set([0, keys.size] + [int(x) for x in rng.integers(0, keys.size + 1, size=3)]))
+            off = np.array(cuts + [keys.size] * int(rng.integers(0, 2)), dtype=np.uint32)  # maybe a trailing empty bag
+            mean = bool(rng.integers(0, 2))
+            if op == "pooled":
+                insert = bool(rng.integers(0, 2))
+                r, s = t.find_or_insert_pooled(keys, off, "mean" if mean else "sum", insert=insert)
+                mr, ms = m.pooled(keys, off, mean, insert)
+                np.testing.assert_array_equal(s, ms)
+                np.testing.assert_array_equal(rows_as_f32(r, dtype), mr)
+            elif keys.size:
+                bg = grads_for(dtype, rng.normal(0, 0.5, size=(off.size - 1, 8)))
+                t.apply_gradients_pooled(keys, off, bg, "mean" if mean else "sum")
+                m.apply_gradients_pooled(keys, off, rows_as_f32(bg, dtype), mean)
+        elif op == "delta":
+            assert export_sorted(t, delta=True)[0].tolist() == m.export_delta()
         else:
             assert t.evict("lfu", 0.5) == m.evict(capi.LFU, 0.5)
         check_tier_equal(t, m)
