@@ -136,7 +136,10 @@ def test_random_sharded_sequences_world1(oracle_lib, cuda_lib, seed, dtype, dim,
     cap, universe, max_batch = 8192, 9000, 2000
     rdt = np.float32 if dtype == "f32" else np.uint16
     tdt = torch.float32 if dtype == "f32" else torch.bfloat16
-    kw = table_kwargs(dim=dim, capacity=cap, dtype=dtype, optimizer=optimizer, track_scores=True)
+    probe = Table(lib=oracle_lib, **table_kwargs(dim=dim, capacity=64, dtype=dtype, optimizer=optimizer))
+    # two of the three runs have a host tier: the owner kernel then promotes / reads through (generic-width variant)
+    spill = 0 if seed == 10 else 2500 * (24 + probe.row_bytes + probe.state_bytes)
+    kw = table_kwargs(dim=dim, capacity=cap, dtype=dtype, optimizer=optimizer, track_scores=True, host_spill_bytes=spill)
     g, o = Table(lib=cuda_lib, **kw), Table(lib=oracle_lib, **kw)
     g.peer_attach(g.peer_prepare(0, 1, max_batch, 0))
     sp = torch.cuda.current_stream().cuda_stream
@@ -172,7 +175,8 @@ def test_random_sharded_sequences_world1(oracle_lib, cuda_lib, seed, dtype, dim,
         if step % 10 == 9:
             assert_tables_equal(g, o)
             gs, os_ = g.stats(), o.stats()
-            for k in ("size", "inserts", "hits", "misses", "evictions", "updates", "grad_dropped"):
+            for k in ("size", "inserts", "hits", "misses", "evictions", "updates", "grad_dropped", "promotions",
+                      "tier_hits", "spill_keys"):
                 assert gs[k] == os_[k], (step, k)
     assert_tables_equal(g, o)
     g.peer_detach()
