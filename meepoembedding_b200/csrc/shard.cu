@@ -156,12 +156,20 @@ __global__ void __launch_bounds__(256) dedup_inverse_kernel(const uint32_t* __re
                                                             uint32_t* __restrict__ occurrences,
                                                             const uint32_t* __restrict__ skip) {
   if (skip && *skip) return;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const uint32_t p = pos[i];
+  const uint32_t lane = threadIdx.x & 31u;
+  // whole warps iterate together (the occurrence count below is folded per warp)
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i - lane < n; i += gridDim.x * blockDim.x) {
+    const bool in = i < n;
+    const uint32_t p = in ? pos[i] : kNil;
     const uint32_t u = p == kNil ? kNil : uid_of_slot[p];
-    if (inverse_out) inverse_out[i] = u;
-    if (occurrences && u != kNil) atomicAdd(occurrences + u, 1u);
-    if (sort_key) {
+    if (in && inverse_out) inverse_out[i] = u;
+    if (occurrences) {
+      // one atomic per distinct key and warp: the hottest Zipf key is 8% of a batch, and 84K atomics on ONE address
+      // serialise in L2 (0.1 ms of a 1M-key batch's 0.17 ms dedup)
+      const unsigned peers = __match_any_sync(0xFFFFFFFFu, u);
+      if (u != kNil && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(occurrences + u, (uint32_t)__popc(peers));
+    }
+    if (in && sort_key) {
       sort_key[i] = u == kNil ? n : u;  // invalid keys sort last and are skipped
       sort_val[i] = i;
     }
