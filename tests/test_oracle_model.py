@@ -482,3 +482,51 @@ def test_two_level_checkpoint(oracle_lib, tmp_path):
     some_steps([t2, m2], 8, 2)
     check_table_equal(t2, m2, "bf16")
     assert m2.promotions > 20
+
+
+def test_known_answers_round2(oracle_lib):
+    """Closed-form anchors for the round-2 verbs (no model involved): pooling, the ring rule of the host tier,
+    promotion, delta marks."""
+    # --- pooling: rows set by import, so every sum is known exactly
+    kw = table_kwargs(dim=4, capacity=64, optimizer="sgd", lr=1.0, init_scale=0.0, track_scores=True, track_dirty=True,
+                      host_spill_bytes=3 * (24 + 16))  # a ring of exactly 3 slabs
+    t = Table(lib=oracle_lib, **kw)
+    keys = np.array([10, 20, 30, 40, 50], dtype=np.uint64)
+    rows = np.array([[1, 2, 3, 4], [10, 20, 30, 40], [0.5, 0.5, 0.5, 0.5], [-1, -1, -1, -1], [7, 0, 0, 0]], dtype=np.float32)
+    scores = np.array([(1 << 32) | 5, (1 << 32) | 1, (1 << 32) | 3, (1 << 32) | 2, (1 << 32) | 4], dtype=np.uint64)  # epoch 1, freq
+    t.import_buffers(keys, rows, scores=scores)
+    assert t.export_delta_size() == 5  # imported tuples are dirty
+    export_sorted(t, delta=True)
+    assert t.export_delta_size() == 0
+    bag_keys = np.array([10, 20, 999, 30, 30, 40], dtype=np.uint64)  # 999 is absent: contributes nothing
+    off = np.array([0, 3, 3, 6], dtype=np.uint32)                   # bags {10,20,999}, {}, {30,30,40}
+    out, st = t.lookup_pooled(bag_keys, off, "sum")
+    np.testing.assert_array_equal(st, [capi.KEY_FOUND, capi.KEY_FOUND, capi.KEY_MISS, capi.KEY_FOUND, capi.KEY_FOUND, capi.KEY_FOUND])
+    np.testing.assert_array_equal(out, [[11, 22, 33, 44], [0, 0, 0, 0], [0, 0, 0, 0]])
+    out, _ = t.lookup_pooled(bag_keys, off, "mean")
+    np.testing.assert_array_equal(out, np.array([[11, 22, 33, 44], [0, 0, 0, 0], [0, 0, 0, 0]], dtype=np.float32) / np.float32(3))
+    many = np.full(4097, 50, dtype=np.uint64)
+    out, _ = t.lookup_pooled(many, np.array([0, 4097], dtype=np.uint32), "sum")
+    np.testing.assert_array_equal(out, [[7 * 4097, 0, 0, 0]])
+    # --- pooled backward, SGD lr = 1: w -= sum over the key's occurrences of its bag's gradient
+    bg = np.array([[1, 1, 1, 1], [9, 9, 9, 9], [2, 0, 0, 0]], dtype=np.float32)
+    t.apply_gradients_pooled(bag_keys, off, bg, "sum")
+    r, _ = t.lookup(np.array([10, 30, 40], dtype=np.uint64))
+    np.testing.assert_array_equal(r, [[0, 1, 2, 3], [0.5 - 4, 0.5, 0.5, 0.5], [-3, -1, -1, -1]])
+    assert sorted(export_sorted(t, delta=True)[0].tolist()) == [10, 20, 30, 40]  # exactly the updated keys
+    # --- the ring rule: LFU evicts in (freq, key) order 20 (1), 40 (2), 30 (3), 50 (4); lookups above added to freq
+    # of 10, 20, 30 (x2 occurrences x2 calls), 40, 50 — recompute the order from the table itself
+    k_all, _, _, sc_all, _ = export_sorted(t)
+    order = [int(k) for _, k in sorted((int(s) & 0xFFFFFFFF, int(k)) for k, s in zip(k_all, sc_all))]
+    assert t.evict("lfu", 1.0 / 70) == 4  # capacity 70 slots -> floor(70/70) = 1 key stays
+    victims = order[:4]
+    tk = tier_export_sorted(t)[0].tolist()
+    assert tk == sorted(victims[1:])  # 4 appends into 3 slabs: the first victim was overwritten
+    # --- promotion: the key comes back with its row; a never-seen key is initialised (init_scale 0 -> zeros)
+    back = np.array([victims[3], 12345], dtype=np.uint64)
+    r, st = t.find_or_insert(back)
+    np.testing.assert_array_equal(st, [capi.KEY_FOUND, capi.KEY_INSERTED])
+    want = {10: [0, 1, 2, 3], 20: [9, 19, 29, 39], 30: [-3.5, 0.5, 0.5, 0.5], 40: [-3, -1, -1, -1], 50: [7, 0, 0, 0]}
+    np.testing.assert_array_equal(r, [want[victims[3]], [0, 0, 0, 0]])
+    s = t.stats()
+    assert s["promotions"] == 1 and s["spill_keys"] == 2 and s["size"] == 3
