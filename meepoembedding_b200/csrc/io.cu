@@ -1,7 +1,6 @@
 // io.cu — bulk dump / load (include/meepo.h "bulk dump / load"): export_buffers,
-// import_buffers and the "MEEPOTB1" file format. Not on the timed path, so the sort of the live
-// keys uses cub::DeviceRadixSort; the row movement reuses the 16-byte gather/scatter kernels.
-#include <cub/device/device_radix_sort.cuh>
+// import_buffers and the "MEEPOTB1" file format. The live keys are sorted with the library's own radix sort
+// (two stable passes over the 32-bit halves of the key); the row movement reuses the 16-byte gather/scatter kernels.
 
 #include <algorithm>
 #include <cstdio>
@@ -152,31 +151,58 @@ static meepo_status dirty_clear(meepo_table* t, cudaStream_t stream) {
   return MEEPO_OK;
 }
 
+// sort keys of the two passes that order 64-bit keys: the low word of key[ord[i]] (ord == null: i), then the high word
+__global__ void key_word_kernel(int high, const uint64_t* __restrict__ key, const uint32_t* __restrict__ ord, uint32_t n,
+                                uint32_t* __restrict__ out, uint32_t* __restrict__ iota) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint64_t k = key[ord ? ord[i] : i];
+    out[i] = high ? (uint32_t)(k >> 32) : (uint32_t)k;
+    if (iota) iota[i] = i;
+  }
+}
+__global__ void permute_kernel(const uint32_t* __restrict__ ord, const uint64_t* __restrict__ k_in,
+                               const uint32_t* __restrict__ s_in, uint32_t n, uint64_t* __restrict__ k_out,
+                               uint32_t* __restrict__ s_out) {
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    k_out[j] = k_in[ord[j]];
+    s_out[j] = s_in[ord[j]];
+  }
+}
+
 // Live (key, slot) pairs sorted by key, left in the workspace (delta: the dirty ones only). Synchronous.
 meepo_status sorted_live(meepo_table* t, uint64_t n, uint64_t** keys_sorted, uint32_t** slots_sorted,
                          cudaStream_t stream, bool delta = false) {
   const uint32_t m = t->v.slots;
   const size_t cbytes = compact_state_bytes(m);
-  size_t cub_bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr,
-                                  (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n, 0, 64);
-  const size_t need = 2 * Workspace::pad(n * 8) + 2 * Workspace::pad(n * 4) + Workspace::pad(cub_bytes) +
+  if (n && !radix_sort_supported(n, 32)) return fail(MEEPO_EINVAL, "export: more than 2^30 tuples in one call");
+  const size_t tmp_bytes = n ? radix_sort_temp_bytes(n, 32) : 0;
+  const size_t need = 2 * Workspace::pad(n * 8) + 6 * Workspace::pad(n * 4) + Workspace::pad(tmp_bytes) +
                       Workspace::pad(cbytes) + 4096;
   MEEPO_TRY(t->ws.reserve(need, stream));
   uint64_t* k_in = t->ws.take<uint64_t>(n);
   uint64_t* k_out = t->ws.take<uint64_t>(n);
   uint32_t* s_in = t->ws.take<uint32_t>(n);
   uint32_t* s_out = t->ws.take<uint32_t>(n);
-  char* tmp = t->ws.take<char>(cub_bytes);
+  uint32_t* w_a = t->ws.take<uint32_t>(n);
+  uint32_t* w_b = t->ws.take<uint32_t>(n);
+  uint32_t* ord_a = t->ws.take<uint32_t>(n);
+  uint32_t* ord_b = t->ws.take<uint32_t>(n);
+  char* tmp = t->ws.take<char>(tmp_bytes);
   char* cstate = t->ws.take<char>(cbytes);
   MEEPO_CUDA_TRY(cudaMemsetAsync(cstate, 0, cbytes, stream));
   live_compact_kernel<<<compact_tiles(m), kCompactThreads, 0, stream>>>(t->v, m, k_in, s_in,
                                                                         compact_carve(cstate, t->err_word + kErrLookback),
                                                                         delta ? 1 : 0);
   MEEPO_CUDA_TRY(cudaGetLastError());
-  if (n)
-    MEEPO_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, cub_bytes, (const uint64_t*)k_in, k_out, (const uint32_t*)s_in,
-                                                   s_out, (int)n, 0, 64, stream));
+  if (n) {
+    const int g = (int)std::max<uint64_t>(1, std::min<uint64_t>((n + 255) / 256, (uint64_t)t->num_sms * 8));
+    key_word_kernel<<<g, 256, 0, stream>>>(0, k_in, nullptr, (uint32_t)n, w_a, ord_a);
+    MEEPO_TRY(radix_sort_pairs(t, tmp, w_a, w_b, ord_a, ord_b, (uint32_t)n, 32, stream));
+    key_word_kernel<<<g, 256, 0, stream>>>(1, k_in, ord_b, (uint32_t)n, w_a, nullptr);
+    MEEPO_TRY(radix_sort_pairs(t, tmp, w_a, w_b, ord_b, ord_a, (uint32_t)n, 32, stream));
+    permute_kernel<<<g, 256, 0, stream>>>(ord_a, k_in, s_in, (uint32_t)n, k_out, s_out);
+    MEEPO_CUDA_TRY(cudaGetLastError());
+  }
   MEEPO_CUDA_TRY(cudaStreamSynchronize(stream));
   *keys_sorted = k_out;
   *slots_sorted = s_out;
